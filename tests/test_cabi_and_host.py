@@ -1,0 +1,176 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/frcnn_b200.h declares,
+the ctypes signature table covers the header, host-side argument logic, loud failure without CUDA,
+and the multi-process sharding / all-gather plumbing over gloo (world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "frcnn_b200.h")
+
+
+def header_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(frcnn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from two_stage_object_detection_b200 import build, _lib
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    names = header_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+    loaded = _lib.load()
+    assert loaded.frcnn_abi_version() == _lib.ABI_VERSION
+    assert loaded.frcnn_last_error() is not None
+
+
+def test_ctypes_structs_match_header_layout():
+    from two_stage_object_detection_b200 import _lib
+    # sizes implied by the C declarations (natural alignment, x86-64)
+    assert ctypes.sizeof(_lib.AnchorSpec) == 32
+    assert ctypes.sizeof(_lib.ProposalParams) == 56
+    assert _lib.ProposalParams.nms_thresh.offset == 32
+    assert ctypes.sizeof(_lib.AnchorTargetParams) == 28
+    assert ctypes.sizeof(_lib.ProposalTargetParams) == 32
+
+
+def test_host_side_argument_checks_need_no_gpu():
+    """Calls that fail validation return before any CUDA work."""
+    from two_stage_object_detection_b200 import _lib
+    lib = _lib.load()
+    p = _lib.ProposalParams()
+    assert lib.frcnn_proposals_workspace_bytes(ctypes.byref(p)) == 0
+    p.batch, p.num_anchors, p.n_pre_nms, p.n_post_nms = 16, 12996, 3000, 300
+    n = lib.frcnn_proposals_workspace_bytes(ctypes.byref(p))
+    assert n > 16 * 12996 * 20 and n % 256 == 0
+    assert lib.frcnn_topk_workspace_bytes(2, 1000) >= 2 * 1000 * 16
+    rc = lib.frcnn_bbox_iou(None, None, -1, 4, None, None)
+    assert rc == -1 and b"bad shape" in lib.frcnn_last_error()
+    rc = lib.frcnn_proposals(ctypes.byref(p), None, None, None, None, None, None, None, None, 0, None)
+    assert rc == -1
+    rc = lib.frcnn_roi_pool_forward(None, 0, 1, 1, 1, None, 0, 7, 7, 1.0, None, None, None, 0, None)
+    assert rc == -1
+
+
+def test_no_cpu_fallback():
+    from two_stage_object_detection_b200 import functional as F, _lib
+    from two_stage_object_detection_b200.nets import AnchorTargetCreator, ProposalCreator
+    with pytest.raises(_lib.FrcnnError):
+        F.bbox_iou(torch.zeros(2, 4), torch.zeros(3, 4))
+    with pytest.raises(_lib.FrcnnError):
+        F.loc2bbox(torch.zeros(2, 4), torch.zeros(2, 4))
+    with pytest.raises(_lib.FrcnnError):
+        ProposalCreator("test")(torch.zeros(9, 4), torch.zeros(9), torch.zeros(9, 4), (3, 16, 16))
+    with pytest.raises(_lib.FrcnnError):
+        AnchorTargetCreator()(torch.zeros(1, 4), torch.zeros(9, 4))
+    with pytest.raises(_lib.FrcnnError):
+        F.roi_pool(torch.zeros(1, 1, 4, 4), torch.zeros(1, 5), 2)
+
+
+def test_product_package_never_imports_the_oracle():
+    """The product path may not route through the oracle, torchvision ops or any CPU fallback."""
+    pkg = os.path.join(ROOT, "two_stage_object_detection_b200")
+    bad = re.compile(r"^\s*(import|from)\s+(oracle|torchvision|triton)\b", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not bad.search(text), f
+                assert "ref_port" not in text, f
+
+
+def test_dropin_signatures_match_reference_table():
+    """names, argument order and defaults."""
+    import inspect
+    from two_stage_object_detection_b200 import nets, utils
+
+    def params(fn):
+        return [(p.name, p.default) for p in inspect.signature(fn).parameters.values() if p.name != "self"]
+
+    E = inspect.Parameter.empty
+    assert params(utils.generate_basic_anchor) == [("base_size", 8), ("ratios", [0.5, 1, 2]), ("anchor_scales", [8, 16, 32])]
+    assert params(utils.enumerate_shifted_anchor) == [("anchor_base", E), ("feat_stride", E), ("height", E), ("width", E)]
+    assert [n for n, _ in params(utils.bbox_iou)] == ["bbox_a", "bbox_b"]
+    assert [n for n, _ in params(utils.loc2bbox)] == ["src_bbox", "loc"]
+    assert [n for n, _ in params(utils.bbox2loc)] == ["src_bbox", "dst_bbox"]
+    assert params(nets.ProposalCreator.__init__) == [("mode", E), ("nms_iou", 0.7), ("n_train_pre_nms", 12000),
+                                                     ("n_train_post_nms", 600), ("n_test_pre_nms", 3000),
+                                                     ("n_test_post_nms", 300), ("min_size", 16)]
+    assert params(nets.ProposalCreator.__call__) == [("loc", E), ("score", E), ("anchor", E), ("img_size", E), ("scale", 1.)]
+    assert params(nets.RegionProposalNetwork.__init__) == [("in_channels", 512), ("ratios", [0.5, 1, 2]),
+                                                           ("anchor_scales", [8, 16, 32]), ("feat_stride", 16),
+                                                           ("mode", "training")]
+    assert params(nets.RegionProposalNetwork.forward) == [("x", E), ("img_size", E), ("scale", 1.)]
+    assert params(nets.AnchorTargetCreator.__init__) == [("n_sample", 256), ("pos_iou_thresh", 0.7),
+                                                         ("neg_iou_thresh", 0.3), ("pos_ratio", 0.5)]
+    assert params(nets.AnchorTargetCreator.__call__) == [("bbox", E), ("anchor", E)]
+    assert params(nets.ProposalTargetCreator.__init__) == [("n_sample", 128), ("pos_ratio", 0.5), ("pos_iou_thresh", 0.5),
+                                                           ("neg_iou_thresh_high", 0.5), ("neg_iou_thresh_low", 0)]
+    assert params(nets.ProposalTargetCreator.__call__) == [("roi", E), ("bbox", E), ("label", E),
+                                                           ("loc_normalize_std", (0.1, 0.1, 0.2, 0.2))]
+    assert params(nets.HarNetRoIHead.__init__)[:4] == [("n_class", E), ("roi_size", E), ("spatial_scale", E), ("classifier", E)]
+    assert params(nets.HarNetRoIHead.forward) == [("x", E), ("rois", E), ("roi_indices", E), ("img_size", E)]
+    assert params(nets.FasterRCNN.__init__)[:5] == [("num_classes", E), ("mode", "training"), ("feat_stride", 16),
+                                                    ("anchor_scales", [8, 16, 32]), ("ratios", [0.5, 1, 2])]
+    assert params(nets.FasterRCNN.forward) == [("x", E), ("scale", 1.), ("mode", "forward")]
+    pc = nets.ProposalCreator("train")
+    assert pc.limits() == (12000, 600) and nets.ProposalCreator("training").limits() == (3000, 300)
+
+
+def test_shard_bounds():
+    from two_stage_object_detection_b200.distributed import shard_bounds
+    for n in (0, 1, 7, 16, 64):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from two_stage_object_detection_b200.distributed import shard_bounds, all_gather_detections
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+B, n_post = 5, 7            # uneven split: 3 + 2
+full = torch.arange(B * n_post * 4, dtype=torch.float32).view(B, n_post, 4)
+keep = torch.arange(B, dtype=torch.int32) + 10
+lo, hi = shard_bounds(B, rank, 2)
+rois, n_keep = all_gather_detections(full[lo:hi].clone(), keep[lo:hi].clone())
+assert torch.equal(rois, full), rank
+assert torch.equal(n_keep, keep), rank
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+@pytest.mark.timeout(120)
+def test_all_gather_detections_gloo_world2(tmp_path):
+    """Sharded result == single-process result, bit-identical, over a real 2-process group."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=100)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"ok {r}" in o

@@ -1,0 +1,433 @@
+"""GPU parity: the CUDA path (through the C ABI) against the committed golden vectors (outputs of the
+real reference) and against the oracle on seeded inputs.  Bit-exact for indices / labels / RoIPool /
+every exp-free fp32 result; 1e-5 relative (see conftest.box_close) for decode / encode."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import box_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def T(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t.to(dtype) if dtype is not None else t
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def F():
+    from two_stage_object_detection_b200 import functional
+    return functional
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import ref_port
+    return ref_port
+
+
+# ------------------------------------------------------------------------------------------------
+def test_anchors_exact(F):
+    from two_stage_object_detection_b200.utils import enumerate_shifted_anchor, generate_basic_anchor
+    g = load_golden("anchors_kat")
+    base = generate_basic_anchor()
+    assert np.array_equal(N(base), g["base"])
+    base2 = generate_basic_anchor(base_size=16, ratios=[0.5, 1, 2, 3], anchor_scales=[4, 8])
+    assert np.array_equal(N(base2), g["base2"])
+    assert np.array_equal(N(enumerate_shifted_anchor(base, 16, 5, 7)), g["shifted_5x7"])
+    assert np.array_equal(N(enumerate_shifted_anchor(base, 16, 38, 38)), g["shifted_38x38"])
+    assert np.array_equal(N(enumerate_shifted_anchor(base2, 8, 9, 4)), g["shifted_rect"])
+
+
+def test_boxmath(F):
+    from two_stage_object_detection_b200.utils import bbox2loc, bbox_iou, loc2bbox
+    g = load_golden("boxmath")
+    k = load_golden("anchors_kat")
+    a = T(np.array([[100, 100, 200, 200]], np.float32))
+    b = T(np.array([[150, 150, 250, 250]], np.float32))
+    assert np.array_equal(N(bbox_iou(a, b)), k["kat_iou"])
+    assert box_close(N(loc2bbox(a, bbox2loc(a, b))), N(b), 250.0)
+    assert np.array_equal(N(bbox_iou(T(g["src"]), T(g["gts"]))), g["iou"])
+    assert np.array_equal(N(bbox_iou(T(g["src"][:64]), T(g["src_d"][:64]))), g["iou_self"])
+    assert box_close(N(loc2bbox(T(g["src"]), T(g["loc"]))), g["decode"], 600.0)
+    assert box_close(N(loc2bbox(T(g["src"]), T(g["loc8"]))), g["decode8"], 600.0)
+    assert box_close(N(bbox2loc(T(g["src"]), T(g["dst"]))), g["encode"], 1.0)
+    assert box_close(N(bbox2loc(T(g["src_d"]), T(g["dst_d"]))), g["encode_d"], 1.0)
+    with pytest.raises(IndexError):
+        bbox_iou(torch.zeros(3, 5, device=DEV), torch.zeros(2, 4, device=DEV))
+    assert loc2bbox(torch.zeros(0, 4, device=DEV), torch.zeros(0, 4, device=DEV)).shape == (0, 4)
+
+
+def test_nms_exact(F):
+    g = load_golden("nms")
+    for i in range(int(g["n_cases"])):
+        keep = F.nms(T(g[f"boxes{i}"]), T(g[f"scores{i}"]), float(g[f"thr{i}"]))
+        assert keep.dtype == torch.int64
+        assert np.array_equal(N(keep), g[f"keep{i}"].astype(np.int64)), i
+    assert F.nms(torch.zeros(0, 4, device=DEV), torch.zeros(0, device=DEV), 0.5).shape == (0,)
+
+
+@pytest.mark.parametrize("superblock", [256, 512, 0])
+def test_nms_superblocks_agree(F, O, superblock):
+    """Multi-super-block path (kept-list suppression) against the oracle, dense overlaps."""
+    rng = np.random.default_rng(5)
+    n = 3000
+    c = rng.uniform(0, 300, (n, 2)).astype(np.float32)
+    wh = rng.uniform(20, 120, (n, 2)).astype(np.float32)
+    boxes = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    scores = np.sort(rng.uniform(0, 1, n).astype(np.float32))[::-1].copy()
+    ref = O.nms(boxes, scores, 0.6)
+    for cap in (n, 100):
+        keep, n_keep = F.nms_sorted(T(boxes)[None], torch.tensor([n], dtype=torch.int32, device=DEV), 0.6, cap,
+                                    superblock)
+        k = int(n_keep[0])
+        assert k == min(cap, ref.shape[0])
+        assert np.array_equal(N(keep[0, :k]).astype(np.int64), ref[:k])
+
+
+PROPOSAL_CASES = ["proposal_small_train", "proposal_small_overlap", "proposal_small_ties", "proposal_small_pad",
+                  "proposal_small_error", "proposal_small_scale", "proposal_600_test", "proposal_600_train"]
+
+
+def _proposal_kw(g):
+    img = tuple(int(v) for v in g["img_size"])
+    return dict(clip_x_max=img[1], clip_y_max=img[2], n_pre_nms=int(g["n_pre"]), n_post_nms=int(g["n_post"]),
+                nms_iou=float(g["nms_iou"]), min_size=float(g["min_size"]) * float(g["scale"]))
+
+
+@pytest.mark.parametrize("name", PROPOSAL_CASES)
+def test_proposal_stages_bit_exact(F, name):
+    """Fed the reference's own decoded boxes, each stage and the fused pipeline are bit-exact."""
+    g = load_golden(name)
+    kw = _proposal_kw(g)
+    dec, score = T(g["decoded"])[None], T(g["score"])[None]
+    boxes, keys, _ = F.decode_clip_score(dec, score, clip_x_max=kw["clip_x_max"], clip_y_max=kw["clip_y_max"],
+                                         min_size=kw["min_size"], boxes_are_decoded=True)
+    valid = np.nonzero(N(keys[0]) != 0)[0]
+    assert np.array_equal(valid, g["valid_idx"].astype(np.int64))
+    order, n_sel, sb = F.topk_sorted(keys, boxes, kw["n_pre_nms"])
+    ref_order = g["valid_idx"].astype(np.int64)[g["order"].astype(np.int64)]
+    ns = int(n_sel[0])
+    assert ns == ref_order.shape[0]
+    assert np.array_equal(N(order[0, :ns]).astype(np.int64), ref_order)
+    assert np.array_equal(N(sb[0, :ns]), N(boxes[0])[ref_order])
+    ref_keep = g["nms_keep"].astype(np.int64)
+    if ns:
+        keep, n_keep = F.nms_sorted(sb, n_sel, kw["nms_iou"], max(ns, 1))
+        assert int(n_keep[0]) == ref_keep.shape[0]
+        assert np.array_equal(N(keep[0, :ref_keep.shape[0]]).astype(np.int64), ref_keep)
+    rois, src, n_keep, status = F.proposals(dec, score, boxes_are_decoded=True, **kw)
+    if int(g["expect_error"]):
+        assert int(status[0]) == 1
+        return
+    assert int(status[0]) == 0
+    assert int(n_keep[0]) == min(ref_keep.shape[0], kw["n_post_nms"])
+    assert np.array_equal(N(rois[0]), g["roi"])
+    assert np.array_equal(N(boxes[0])[N(src[0]).astype(np.int64)], g["roi"])
+
+
+@pytest.mark.parametrize("name", ["proposal_small_train", "proposal_small_scale", "proposal_600_test"])
+def test_proposal_creator_dropin(F, name):
+    """ProposalCreator.__call__ with the reference's signature, from (loc, score, anchor)."""
+    from two_stage_object_detection_b200.nets import ProposalCreator
+    from two_stage_object_detection_b200.utils import enumerate_shifted_anchor, generate_basic_anchor
+    g = load_golden(name)
+    img = tuple(int(v) for v in g["img_size"])
+    mode = str(g["mode"])
+    lim = ({"n_train_pre_nms": int(g["n_pre"]), "n_train_post_nms": int(g["n_post"])} if mode == "train"
+           else {"n_test_pre_nms": int(g["n_pre"]), "n_test_post_nms": int(g["n_post"])})
+    pc = ProposalCreator(mode, nms_iou=float(g["nms_iou"]), min_size=float(g["min_size"]), **lim)
+    anchor = enumerate_shifted_anchor(generate_basic_anchor(), 16, int(g["H"]), int(g["W"]))
+    roi = pc(T(g["loc"]), T(g["score"]), anchor, img, scale=float(g["scale"]))
+    assert tuple(roi.shape) == g["roi"].shape
+    # decode uses expf: boxes agree to 1e-5 relative; a rare threshold flip may move a row
+    frac = np.mean(np.all(np.abs(N(roi) - g["roi"]) <= 1e-5 * float(max(img)), axis=1))
+    assert frac >= 0.99, frac
+
+
+def test_proposal_creator_raises_like_reference(F):
+    from two_stage_object_detection_b200.nets import ProposalCreator
+    from two_stage_object_detection_b200.utils import enumerate_shifted_anchor, generate_basic_anchor
+    g = load_golden("proposal_small_error")
+    pc = ProposalCreator("test", nms_iou=float(g["nms_iou"]), n_test_pre_nms=int(g["n_pre"]),
+                         n_test_post_nms=int(g["n_post"]))
+    anchor = enumerate_shifted_anchor(generate_basic_anchor(), 16, int(g["H"]), int(g["W"]))
+    with pytest.raises(IndexError):
+        pc(T(g["loc"]), T(g["score"]), anchor, tuple(int(v) for v in g["img_size"]))
+
+
+def test_proposals_batched_vs_oracle_full_size(F, O):
+    """B=6 images at the 600x600 size (N=12996), test limits, generated anchors, vs the oracle fed the
+    GPU's own decoded boxes (stage isolation); plus batch independence."""
+    g = torch.Generator().manual_seed(11)
+    B, H, W = 6, 38, 38
+    Nn = H * W * 9
+    loc = (torch.randn(B, Nn, 4, generator=g) * 0.2).float()
+    logits = torch.randn(B, Nn, 2, generator=g)
+    logits[3, :, 1] = torch.round(logits[3, :, 1] * 8) / 8  # many exact ties in image 3
+    logits[3, :, 0] = 0
+    base = F.base_anchors(device=DEV)
+    kw = dict(clip_x_max=600, clip_y_max=600, min_size=16.0)
+    boxes, keys, fg = F.decode_clip_score(loc.to(DEV), logits.to(DEV), base=base, feat_stride=16, feat_hw=(H, W),
+                                          score_is_logits=True, **kw)
+    anchor = O.shifted_anchors(O.base_anchors(), 16, H, W)
+    assert box_close(N(boxes[0]), O.clip_filter(O.decode(anchor, loc[0].numpy()), (3, 600, 600), 16)[0], 600.0)
+    assert np.allclose(N(fg), O.fg_scores(logits.numpy()), rtol=1e-5, atol=1e-7)
+    rois, src, n_keep, status = F.proposals(loc.to(DEV), logits.to(DEV), base=base, feat_stride=16, feat_hw=(H, W),
+                                            score_is_logits=True, n_pre_nms=3000, n_post_nms=300, nms_iou=0.7, **kw)
+    # oracle on the GPU's decoded (pre-clip == post-clip input, clip is idempotent) boxes and fg scores
+    ref, ref_src, ref_nk, rc = O.proposal_layer_batch_from_boxes(N(boxes), N(fg), (3, 600, 600), 1.0, 0.7, 3000,
+                                                                 300, 16)
+    assert not rc.any() and not N(status).any()
+    assert np.array_equal(N(rois), ref)
+    assert np.array_equal(N(src).astype(np.int64), ref_src)
+    assert np.array_equal(N(n_keep).astype(np.int64), np.minimum(ref_nk, 300))
+    one, *_ = F.proposals(loc[2:3].to(DEV), logits[2:3].to(DEV), base=base, feat_stride=16, feat_hw=(H, W),
+                          score_is_logits=True, n_pre_nms=3000, n_post_nms=300, nms_iou=0.7, **kw)
+    assert torch.equal(one[0], rois[2])
+
+
+def test_proposals_stress_size_properties(F, O):
+    """1024x1024 stress size (N=36864, 30k pre / 2k post): oracle parity on one image + invariants."""
+    g = torch.Generator().manual_seed(12)
+    B, H, W = 2, 64, 64
+    Nn = H * W * 9
+    loc = (torch.randn(B, Nn, 4, generator=g) * 0.1).float().to(DEV)
+    score = torch.rand(B, Nn, generator=g).to(DEV)
+    base = F.base_anchors(device=DEV)
+    kw = dict(clip_x_max=1024, clip_y_max=1024, min_size=16.0)
+    boxes, keys, fg = F.decode_clip_score(loc, score, base=base, feat_stride=16, feat_hw=(H, W), **kw)
+    rois, src, n_keep, status = F.proposals(loc, score, base=base, feat_stride=16, feat_hw=(H, W), n_pre_nms=30000,
+                                            n_post_nms=2000, nms_iou=0.7, **kw)
+    assert not N(status).any()
+    ref, ref_src, ref_nk, rc = O.proposal_layer_batch_from_boxes(N(boxes[:1]), N(fg[:1]), (3, 1024, 1024), 1.0, 0.7,
+                                                                 30000, 2000, 16)
+    assert np.array_equal(N(rois[:1]), ref)
+    assert np.array_equal(N(src[:1]).astype(np.int64), ref_src)
+    # invariants on every image: scores non-increasing along the kept rows, kept boxes mutually <= thr
+    for b in range(B):
+        k = int(n_keep[b])
+        s = N(score[b])[N(src[b, :k]).astype(np.int64)]
+        assert np.all(s[:-1] >= s[1:])
+        again = F.nms(rois[b, :k], torch.from_numpy(s.copy()).to(DEV), 0.7)
+        assert again.shape[0] == k  # idempotence: NMS of an NMS output keeps everything
+
+
+# ------------------------------------------------------------------------------------------------
+def test_anchor_targets_golden(F):
+    from two_stage_object_detection_b200.nets import AnchorTargetCreator
+    from two_stage_object_detection_b200.utils import enumerate_shifted_anchor, generate_basic_anchor
+    g = load_golden("anchor_targets")
+    base = generate_basic_anchor()
+    for name in [str(n) for n in g["names"]] + ["custom"]:
+        anchor = enumerate_shifted_anchor(base, 16, int(g[f"{name}_H"]), int(g[f"{name}_W"]))
+        kw = {}
+        if name == "custom":
+            p = g["custom_params"]
+            kw = dict(n_sample=int(p[0]), pos_iou_thresh=float(p[1]), neg_iou_thresh=float(p[2]), pos_ratio=float(p[3]))
+        loc, label = AnchorTargetCreator(**kw)(T(g[f"{name}_bbox"]).view(-1, 4), anchor)
+        assert label.dtype == torch.int64
+        assert np.array_equal(N(label), g[f"{name}_label"].astype(np.int64)), name
+        assert box_close(N(loc), g[f"{name}_loc"], 1.0), name
+
+
+def test_anchor_targets_batched_vs_oracle(F, O):
+    rng = np.random.default_rng(21)
+    B, H, W = 5, 50, 50
+    base = F.base_anchors(device=DEV)
+    anchor = O.shifted_anchors(O.base_anchors(), 16, H, W)
+    gts, labels = [], []
+    for b in range(B):
+        G = [8, 0, 1, 37, 90][b]
+        c = rng.uniform(0, 800, (G, 2))
+        wh = rng.uniform(50, 300, (G, 2))
+        bb = np.clip(np.concatenate([c - wh / 2, c + wh / 2], 1), 0, 800).astype(np.float32)
+        if G > 3:
+            bb[2] = bb[0]  # duplicate GT: later one wins the shared best anchor
+        gts.append(torch.from_numpy(bb))
+    bb, _, n_gt = F.pad_gt(gts, device=DEV)
+    loc, label, argmax = F.anchor_targets(bb, n_gt, base=base, feat_stride=16, feat_hw=(H, W), return_argmax=True)
+    for b in range(B):
+        rl, rlab, ram, _, _ = O.anchor_targets(gts[b].numpy(), anchor, return_extra=True)
+        assert np.array_equal(N(label[b]), rlab), b
+        assert np.array_equal(N(argmax[b]).astype(np.int64), ram), b
+        assert box_close(N(loc[b]), rl, 1.0), b
+
+
+def test_proposal_targets_golden(F):
+    from two_stage_object_detection_b200.nets import ProposalTargetCreator
+    g = load_golden("proposal_targets")
+    for name in [str(n) for n in g["names"]]:
+        p = g[f"{name}_params"]
+        ptc = ProposalTargetCreator(n_sample=int(p[0]), pos_ratio=float(p[1]), pos_iou_thresh=float(p[2]),
+                                    neg_iou_thresh_high=float(p[3]), neg_iou_thresh_low=float(p[4]))
+        args = (T(g[f"{name}_roi"]), T(g[f"{name}_bbox"]).view(-1, 4), T(g[f"{name}_label"]).view(-1))
+        if int(g[f"{name}_error"]):
+            with pytest.raises(IndexError):
+                ptc(*args)
+            continue
+        s, l, y = ptc(*args)
+        assert np.array_equal(N(s), g[f"{name}_sample_roi"]), name
+        assert np.array_equal(N(y), g[f"{name}_gt_label"]), name
+        assert box_close(N(l), g[f"{name}_gt_loc"], 1.0), name
+
+
+def test_proposal_targets_batched_vs_oracle(F, O):
+    rng = np.random.default_rng(22)
+    B, R = 4, 600
+    rois = np.zeros((B, R, 4), np.float32)
+    gts, labels = [], []
+    for b in range(B):
+        G = [8, 0, 3, 20][b]
+        c = rng.uniform(0, 600, (G, 2))
+        wh = rng.uniform(50, 250, (G, 2))
+        bb = np.clip(np.concatenate([c - wh / 2, c + wh / 2], 1), 0, 600).astype(np.float32)
+        c = rng.uniform(0, 600, (R, 2))
+        wh = rng.uniform(16, 300, (R, 2))
+        rois[b] = np.clip(np.concatenate([c - wh / 2, c + wh / 2], 1), 0, 600)
+        if G:
+            jitter = bb[rng.integers(0, G, 30)] + rng.normal(0, 5, (30, 4)).astype(np.float32)
+            rois[b, 100:130] = jitter  # positives late in the list -> scatter stays in range
+        gts.append(torch.from_numpy(bb))
+        labels.append(torch.from_numpy(rng.integers(0, 20, G)))
+    bb, ll, n_gt = F.pad_gt(gts, labels, device=DEV)
+    s, l, y, n_out, status = F.proposal_targets(T(rois), bb, ll, n_gt)
+    for b in range(B):
+        try:
+            rs, rl, ry = O.proposal_targets(rois[b], gts[b].numpy(), labels[b].numpy())
+        except IndexError:
+            assert int(status[b]) == 2, b
+            continue
+        assert int(status[b]) == 0, b
+        k = int(n_out[b])
+        assert k == rs.shape[0]
+        assert np.array_equal(N(s[b, :k]), rs), b
+        assert np.array_equal(N(y[b, :k]), ry), b
+        assert box_close(N(l[b, :k]), rl, 1.0), b
+
+
+# ------------------------------------------------------------------------------------------------
+def test_roi_pool_and_align_golden(F):
+    g = load_golden("roi_ops")
+    feat, rois = T(g["feat"]), T(g["rois"])
+    for key in g.files:
+        if key.startswith("pool_P"):
+            _, P, s = key.split("_")
+            out = F.roi_pool(feat, rois, int(P[1:]), float(s[1:]))
+            assert np.array_equal(N(out), g[key]), key
+        elif key.startswith("align_P"):
+            _, P, sr, al, s = key.split("_")
+            out = F.roi_align(feat, rois, int(P[1:]), float(s[1:]), int(sr[2:]), bool(int(al[2:])))
+            assert np.array_equal(N(out), g[key]), key  # same op order, no FMA: bit-exact
+    out, am = F.roi_pool_forward(feat, rois, 7, 1.0, with_argmax=True)
+    assert np.array_equal(N(am), g["pool_argmax_P7_s1.0"])
+    assert np.array_equal(N(out), g["pool_P7_s1.0"])
+
+
+@pytest.mark.parametrize("shape", [(3, 40, 38, 38, 14), (2, 24, 50, 50, 7), (2, 12, 37, 37, 7), (1, 6, 64, 64, 5)])
+def test_roi_ops_vs_oracle(F, O, shape):
+    """Config-shaped maps (38x38 / 50x50 / 64x64) and an odd 37x37 map (non-TMA staging path)."""
+    B, Cc, H, W, P = shape
+    rng = np.random.default_rng(31 + H)
+    feat = rng.standard_normal((B, Cc, H, W)).astype(np.float32)
+    feat[0, 0] = np.maximum(feat[0, 0], 0)
+    K = 150
+    c = rng.uniform(-4, W + 4, (K, 2))
+    wh = rng.uniform(0.5, W * 0.8, (K, 2))
+    rois = np.concatenate([rng.integers(0, B, (K, 1)), c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    out, am = F.roi_pool_forward(T(feat), T(rois), P, 1.0, with_argmax=True)
+    ro, ra = O.roi_pool(feat, rois, P, 1.0, return_argmax=True)
+    assert np.array_equal(N(out), ro)
+    assert np.array_equal(N(am), ra)
+    assert np.array_equal(N(F.roi_pool(T(feat), T(rois), P, 0.5)), O.roi_pool(feat, rois, P, 0.5))
+    for sr, al in ((2, False), (-1, False), (2, True)):
+        assert np.array_equal(N(F.roi_align(T(feat), T(rois), P, 1.0, sr, al)), O.roi_align(feat, rois, P, 1.0, sr, al))
+
+
+def test_roi_head_dropin(F):
+    from two_stage_object_detection_b200.nets import HarNetRoIHead
+    from two_stage_object_detection_b200.nets.frcnn import GlobalAvgClassifier
+    g = load_golden("roi_head")
+    head = HarNetRoIHead(n_class=3, roi_size=7, spatial_scale=1, classifier=GlobalAvgClassifier()).to(DEV)
+    with torch.no_grad():
+        head.cls_loc.weight.copy_(T(g["w_loc"]))
+        head.cls_loc.bias.copy_(T(g["b_loc"]))
+        head.score.weight.copy_(T(g["w_score"]))
+        head.score.bias.copy_(T(g["b_score"]))
+    x, rois = T(g["x"]), T(g["rois"])
+    idx = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for tag in ("chw", "hw"):
+        img = tuple(int(v) for v in g[f"{tag}_img"])
+        r5 = F.roi_head_coords(rois, idx, img, (x.shape[2], x.shape[3]))
+        assert np.array_equal(N(r5), g[f"{tag}_rois5"]), tag
+        pool = head.gather(x, rois, idx, img)
+        assert np.array_equal(N(pool[:16, :32]), g[f"{tag}_pool_head"]), tag
+        assert np.allclose(N(pool).astype(np.float64).sum((2, 3)), g[f"{tag}_pool_sum"], rtol=0, atol=1e-9)
+        with torch.no_grad():
+            locs, scores = head(x, rois, idx, img)
+        assert np.allclose(N(locs), g[f"{tag}_cls_locs"], rtol=1e-4, atol=1e-5)
+        assert np.allclose(N(scores), g[f"{tag}_scores"], rtol=1e-4, atol=1e-5)
+
+
+def test_rpn_forward_dropin(F):
+    from two_stage_object_detection_b200.nets import ProposalCreator, RegionProposalNetwork
+    g = load_golden("rpn_forward")
+    rpn = RegionProposalNetwork(in_channels=16, mode="test").to(DEV)
+    rpn.proposal_layer = ProposalCreator("test", n_test_pre_nms=500, n_test_post_nms=40)
+    with torch.no_grad():
+        rpn.loc.weight.copy_(T(g["w_loc"]))
+        rpn.loc.bias.copy_(T(g["b_loc"]))
+        rpn.score.weight.copy_(T(g["w_score"]))
+        rpn.score.bias.copy_(T(g["b_score"]))
+    img = tuple(int(v) for v in g["img_size"])
+    # cuDNN conv vs the CPU conv differ in the last bits, which can reorder near-tied scores; feed the
+    # reference's own conv outputs through the post-conv part for the strict comparison ...
+    roi, _, _, st = rpn.proposal_layer.batched(T(g["rpn_locs"]), T(g["rpn_scores"]), img, 1.0, base=rpn.anchor_base,
+                                                feat_stride=16, feat_hw=tuple(g["x"].shape[2:]), score_is_logits=True)
+    assert int(st[0]) == 0
+    assert box_close(N(roi), g["rois"], float(max(img)))
+    # ... and run the module end to end for shapes / arity / anchors
+    with torch.no_grad():
+        for fused in (True, False):
+            rpn.fused_softmax = fused
+            locs, scores, rois, anchor = rpn(T(g["x"]), img, 1.0)
+            assert tuple(locs.shape) == g["rpn_locs"].shape and tuple(scores.shape) == g["rpn_scores"].shape
+            assert tuple(rois.shape) == g["rois"].shape
+            assert np.array_equal(N(anchor), g["anchor"])
+            assert np.allclose(N(locs), g["rpn_locs"], rtol=1e-4, atol=1e-5)
+            frac = np.mean(np.all(np.abs(N(rois) - g["rois"]) <= 1e-3 * float(max(img)), axis=2))
+            assert frac >= 0.9, frac
+
+
+def test_roi_pool_backward_matches_autograd_definition(F):
+    """d(sum(out*w))/d(feat): every output element routes its weight to its argmax cell."""
+    rng = np.random.default_rng(41)
+    feat = torch.from_numpy(rng.standard_normal((2, 6, 20, 24)).astype(np.float32)).to(DEV).requires_grad_(True)
+    c = rng.uniform(0, 22, (40, 2))
+    wh = rng.uniform(2, 18, (40, 2))
+    rois = T(np.concatenate([rng.integers(0, 2, (40, 1)), c - wh / 2, c + wh / 2], 1).astype(np.float32))
+    out = F.roi_pool(feat, rois, 7, 1.0)
+    w = torch.from_numpy(rng.standard_normal(tuple(out.shape)).astype(np.float32)).to(DEV)
+    (out * w).sum().backward()
+    _, am = F.roi_pool_forward(feat.detach(), rois, 7, 1.0, with_argmax=True)
+    ref = np.zeros((2, 6, 20 * 24), np.float64)
+    amn, wn, rn = N(am), N(w), N(rois)
+    for k in range(40):
+        b = int(rn[k, 0])
+        for ch in range(6):
+            idx = amn[k, ch].reshape(-1)
+            m = idx >= 0
+            np.add.at(ref[b, ch], idx[m], wn[k, ch].reshape(-1)[m])
+    assert np.allclose(N(feat.grad).reshape(2, 6, -1), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_cpu_tensors_fail_loudly(F):
+    with pytest.raises(RuntimeError):
+        F.bbox_iou(torch.zeros(2, 4), torch.zeros(2, 4))

@@ -1,0 +1,192 @@
+// boxmath.cu -- anchors (utils/basic_anchors.py) and box arithmetic (utils/loc_bbox_iou.py) of the
+// reference as sm_100a kernels, plus the library's runtime helpers.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace frcnn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+// ---------------------------------------------------------------------------------------------
+// utils/basic_anchors.py:11-23
+// ---------------------------------------------------------------------------------------------
+struct BaseAnchorArgs {
+    float ratio[FRCNN_MAX_BASE_ANCHORS];
+    float inv_ratio[FRCNN_MAX_BASE_ANCHORS];
+    float size[FRCNN_MAX_BASE_ANCHORS];
+    int num_ratios, num_sizes;
+};
+
+__global__ void base_anchor_kernel(BaseAnchorArgs a, float4* __restrict__ out) {
+    int t = threadIdx.x;
+    if (t >= a.num_ratios * a.num_sizes) return;
+    int i = t / a.num_sizes, j = t % a.num_sizes;
+    float h = a.size[j] * __fsqrt_rn(a.ratio[i]);
+    float w = a.size[j] * __fsqrt_rn(a.inv_ratio[i]);
+    float hw = w / 2.f, hh = h / 2.f;
+    out[t] = make_float4(-hw, -hh, hw, hh);
+}
+
+// utils/basic_anchors.py:27-57 -- one float4 store per anchor, fully coalesced
+__global__ void shifted_anchor_kernel(AnchorGen g, int n, float4* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = load_anchor(g, i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// utils/loc_bbox_iou.py:29-61   loc [R, 4*groups]; thread per (row, group)
+// ---------------------------------------------------------------------------------------------
+__global__ void loc2bbox_kernel(const float4* __restrict__ src, const float4* __restrict__ loc,
+                                int64_t total, int groups, float4* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float4 a = __ldg(src + i / groups);
+    out[i] = decode_box(a, __ldg(loc + i));
+}
+
+__global__ void bbox2loc_kernel(const float4* __restrict__ src, const float4* __restrict__ dst,
+                                int64_t rows, float4* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    out[i] = encode_box(__ldg(src + i), __ldg(dst + i));
+}
+
+// ---------------------------------------------------------------------------------------------
+// utils/loc_bbox_iou.py:4-27   dense [Na,Nb]; a tile of b staged in shared memory, each thread
+// owns one a-row and streams over the b tile; stores are coalesced along Nb via a transposed
+// thread mapping (threadIdx.x walks b).
+// ---------------------------------------------------------------------------------------------
+constexpr int IOU_TB = 128;  // b boxes per CTA tile (threadIdx.x)
+constexpr int IOU_TA = 8;    // a rows per thread-row group (threadIdx.y)
+constexpr int IOU_ROWS = 32; // a rows per CTA
+
+__global__ void __launch_bounds__(IOU_TB* IOU_TA)
+bbox_iou_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int64_t na, int64_t nb,
+                float* __restrict__ out) {
+    __shared__ float4 sa[IOU_ROWS];
+    __shared__ float sarea[IOU_ROWS];
+    int64_t a0 = (int64_t)blockIdx.y * IOU_ROWS;
+    int64_t j = (int64_t)blockIdx.x * IOU_TB + threadIdx.x;
+    int tid = threadIdx.y * IOU_TB + threadIdx.x;
+    if (tid < IOU_ROWS && a0 + tid < na) {
+        float4 v = __ldg(a + a0 + tid);
+        sa[tid] = v;
+        sarea[tid] = box_area(v);
+    }
+    __syncthreads();
+    if (j >= nb) return;
+    float4 bb = __ldg(b + j);
+    float barea = box_area(bb);
+#pragma unroll
+    for (int r = threadIdx.y; r < IOU_ROWS; r += IOU_TA) {
+        if (a0 + r < na) out[(a0 + r) * nb + j] = iou_eps(sa[r], sarea[r], bb, barea);
+    }
+}
+
+}  // namespace frcnn
+
+using namespace frcnn;
+
+extern "C" {
+
+int frcnn_abi_version(void) { return FRCNN_ABI_VERSION; }
+const char* frcnn_last_error(void) { return g_err; }
+
+int frcnn_device_info(int* sm, int* major, int* minor) {
+    int dev = 0;
+    FRCNN_CUDA(cudaGetDevice(&dev));
+    if (sm) FRCNN_CUDA(cudaDeviceGetAttribute(sm, cudaDevAttrMultiProcessorCount, dev));
+    if (major) FRCNN_CUDA(cudaDeviceGetAttribute(major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (minor) FRCNN_CUDA(cudaDeviceGetAttribute(minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return FRCNN_OK;
+}
+
+int frcnn_base_anchors(const float* ratios, const float* inv_ratios, int32_t nr, const float* sizes,
+                       int32_t ns, float* out, frcnn_stream_t stream) {
+    FRCNN_CHECK_ARG(ratios && inv_ratios && sizes && out, "frcnn_base_anchors: null pointer");
+    FRCNN_CHECK_ARG(nr > 0 && ns > 0 && nr <= FRCNN_MAX_BASE_ANCHORS && ns <= FRCNN_MAX_BASE_ANCHORS &&
+                        nr * ns <= FRCNN_MAX_BASE_ANCHORS,
+                    "frcnn_base_anchors: need 0 < ratios*scales <= %d", FRCNN_MAX_BASE_ANCHORS);
+    BaseAnchorArgs a;
+    memset(&a, 0, sizeof(a));
+    memcpy(a.ratio, ratios, nr * sizeof(float));
+    memcpy(a.inv_ratio, inv_ratios, nr * sizeof(float));
+    memcpy(a.size, sizes, ns * sizeof(float));
+    a.num_ratios = nr;
+    a.num_sizes = ns;
+    base_anchor_kernel<<<1, FRCNN_MAX_BASE_ANCHORS, 0, (cudaStream_t)stream>>>(a, (float4*)out);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
+int frcnn_shifted_anchors(const float* base, int32_t A, int32_t stride, int32_t H, int32_t W,
+                          float* out, frcnn_stream_t stream) {
+    FRCNN_CHECK_ARG(base && out, "frcnn_shifted_anchors: null pointer");
+    FRCNN_CHECK_ARG(A > 0 && H >= 0 && W >= 0, "frcnn_shifted_anchors: bad shape");
+    int64_t n64 = (int64_t)A * H * W;
+    FRCNN_CHECK_ARG(n64 < (1ll << 31), "frcnn_shifted_anchors: too many anchors");
+    int n = (int)n64;
+    if (n == 0) return FRCNN_OK;
+    AnchorGen g{nullptr, (const float4*)base, A, stride, H, W};
+    shifted_anchor_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(g, n, (float4*)out);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
+int frcnn_loc2bbox(const float* src, const float* loc, int64_t rows, int32_t groups, float* out,
+                   frcnn_stream_t stream) {
+    FRCNN_CHECK_ARG(rows >= 0 && groups > 0, "frcnn_loc2bbox: bad shape");
+    if (rows == 0) return FRCNN_OK;
+    FRCNN_CHECK_ARG(src && loc && out, "frcnn_loc2bbox: null pointer");
+    int64_t total = rows * groups;
+    loc2bbox_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)src, (const float4*)loc, total, groups, (float4*)out);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
+int frcnn_bbox2loc(const float* src, const float* dst, int64_t rows, float* out, frcnn_stream_t stream) {
+    FRCNN_CHECK_ARG(rows >= 0, "frcnn_bbox2loc: bad shape");
+    if (rows == 0) return FRCNN_OK;
+    FRCNN_CHECK_ARG(src && dst && out, "frcnn_bbox2loc: null pointer");
+    bbox2loc_kernel<<<cdiv(rows, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)src, (const float4*)dst, rows, (float4*)out);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
+int frcnn_bbox_iou(const float* a, const float* b, int64_t na, int64_t nb, float* out,
+                   frcnn_stream_t stream) {
+    FRCNN_CHECK_ARG(na >= 0 && nb >= 0, "frcnn_bbox_iou: bad shape");
+    if (na == 0 || nb == 0) return FRCNN_OK;
+    FRCNN_CHECK_ARG(a && b && out, "frcnn_bbox_iou: null pointer");
+    dim3 grid(cdiv(nb, IOU_TB), cdiv(na, IOU_ROWS));
+    FRCNN_CHECK_ARG(grid.y <= 65535, "frcnn_bbox_iou: Na too large (max %d)", 65535 * IOU_ROWS);
+    bbox_iou_kernel<<<grid, dim3(IOU_TB, IOU_TA), 0, (cudaStream_t)stream>>>(
+        (const float4*)a, (const float4*)b, na, nb, out);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+// common.cuh -- shared helpers for the sm_100a kernels behind include/frcnn_b200.h.
+// Compiled with -fmad=false: every fp32 multiply/add is a separate IEEE rounding, as the
+// reference's ATen/torchvision CPU kernels do them.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/frcnn_b200.h"
+
+namespace frcnn {
+
+void set_error(const char* fmt, ...);
+
+#define FRCNN_CHECK_ARG(cond, ...)                    \
+    do {                                              \
+        if (!(cond)) {                                \
+            ::frcnn::set_error(__VA_ARGS__);          \
+            return FRCNN_ERR_INVALID_ARG;             \
+        }                                             \
+    } while (0)
+
+#define FRCNN_CUDA(expr)                                                                      \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            ::frcnn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),       \
+                               __FILE__, __LINE__);                                           \
+            return FRCNN_ERR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+
+#define FRCNN_LAUNCH_CHECK() FRCNN_CUDA(cudaGetLastError())
+
+static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+int sm_count();
+
+// Bump allocator over the caller-provided workspace.
+struct Workspace {
+    char* base;
+    size_t cap;
+    size_t off;
+    Workspace(void* p, size_t n) : base((char*)p), cap(n), off(0) {}
+    template <typename T>
+    T* take(size_t count) {
+        size_t bytes = align_up(count * sizeof(T));
+        T* r = (T*)(base + off);
+        off += bytes;
+        return r;
+    }
+    bool ok() const { return off <= cap && ((uintptr_t)base % 256) == 0; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+struct BaseAnchors {
+    float v[FRCNN_MAX_BASE_ANCHORS][4];
+};
+
+struct AnchorGen {
+    const float4* anchors;  // explicit [N,4] or nullptr
+    const float4* base;     // [A,4]
+    int num_base, stride, height, width;
+};
+
+__device__ __forceinline__ float4 load_anchor(const AnchorGen& g, int i) {
+    if (g.anchors) return __ldg(g.anchors + i);
+    int a = i % g.num_base;
+    int k = i / g.num_base;
+    int x = k % g.width;
+    int y = k / g.width;
+    float4 b = __ldg(g.base + a);
+    float sx = (float)(x * g.stride), sy = (float)(y * g.stride);
+    return make_float4(b.x + sx, b.y + sy, b.z + sx, b.w + sy);
+}
+
+// Order-preserving map fp32 -> uint32 (bigger score = bigger key), matching torch.sort's view of
+// floats: NaN is the largest, -0 == +0.  Result is never 0 (0 is reserved for "filtered out").
+__device__ __forceinline__ uint32_t score_key(float s) {
+    if (s != s) return 0xFFFFFFFFu;
+    if (s == 0.f) s = 0.f;
+    uint32_t u = __float_as_uint(s);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// torch.max / argmax semantics: NaN beats everything, first index wins ties.
+__device__ __forceinline__ bool beats(float v, float best) {
+    return (v > best) || (v != v && best == best);
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// utils/loc_bbox_iou.py:18-26 -- inter / (((area_a + area_b) - inter) + 1e-8f)
+// torch.maximum / torch.minimum propagate NaN (fmaxf/fminf do not)
+__device__ __forceinline__ float tmax(float a, float b) {
+    float m = a > b ? a : b;
+    return (a != a) ? a : ((b != b) ? b : m);
+}
+__device__ __forceinline__ float tmin(float a, float b) {
+    float m = a < b ? a : b;
+    return (a != a) ? a : ((b != b) ? b : m);
+}
+
+__device__ __forceinline__ float iou_eps(const float4& a, float area_a, const float4& b, float area_b) {
+    float tlx = tmax(a.x, b.x), tly = tmax(a.y, b.y);
+    float brx = tmin(a.z, b.z), bry = tmin(a.w, b.w);
+    float w = brx - tlx, h = bry - tly;
+    w = w < 0.f ? 0.f : w;  // clamp_(min=0); NaN stays NaN
+    h = h < 0.f ? 0.f : h;
+    float inter = w * h;
+    float uni = area_a + area_b;
+    uni = uni - inter;
+    uni = uni + 1e-8f;
+    return inter / uni;
+}
+
+__device__ __forceinline__ float box_area(const float4& b) { return (b.z - b.x) * (b.w - b.y); }
+
+// utils/loc_bbox_iou.py:63-89
+__device__ __forceinline__ float4 encode_box(const float4& s, const float4& d) {
+    float w = s.z - s.x, h = s.w - s.y;
+    float cx = s.x + 0.5f * w, cy = s.y + 0.5f * h;
+    float bw = d.z - d.x, bh = d.w - d.y;
+    float bcx = d.x + 0.5f * bw, bcy = d.y + 0.5f * bh;
+    const float eps = 1.1920928955078125e-07f;
+    // torch.maximum propagates NaN
+    w = (w != w) ? w : (w > eps ? w : eps);
+    h = (h != h) ? h : (h > eps ? h : eps);
+    float4 o;
+    o.x = (bcx - cx) / w;
+    o.y = (bcy - cy) / h;
+    o.z = logf(bw / w);
+    o.w = logf(bh / h);
+    return o;
+}
+
+// utils/loc_bbox_iou.py:36-59
+__device__ __forceinline__ float4 decode_box(const float4& a, const float4& l) {
+    float w = a.z - a.x, h = a.w - a.y;
+    float cx = a.x + 0.5f * w, cy = a.y + 0.5f * h;
+    float ncx = l.x * w + cx, ncy = l.y * h + cy;
+    float nw = expf(l.z) * w, nh = expf(l.w) * h;
+    float hw = 0.5f * nw, hh = 0.5f * nh;
+    return make_float4(ncx - hw, ncy - hh, ncx + hw, ncy + hh);
+}
+
+}  // namespace frcnn

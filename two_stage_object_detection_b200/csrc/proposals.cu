@@ -1,0 +1,786 @@
+// proposals.cu -- the RPN proposal layer (nets/rpn.py:36-70 + the per-image loop :129-139 +
+// torchvision.ops.nms), batched over images, no host synchronisation anywhere.
+//
+//   decode_clip_key   one thread per anchor: loc2bbox, clamp, min-size test, score -> sortable key
+//   topk_sort         one CTA per image: stable LSD radix sort of (~key) with warp-match ranking;
+//                     emits anchor indices in (score desc, index asc) order + gathered boxes
+//   nms_mask          super-block S of sorted candidates: warp-ballot IoU>thr bitmask tiles
+//                     (upper triangle only) + suppression by boxes kept in earlier super-blocks
+//   nms_scan          one CTA per image: resolves 32 candidates per step, early exit at keep_cap
+//   finalize          pad-with-arange / truncate / gather (nets/rpn.py:65-69)
+#include "common.cuh"
+
+namespace frcnn {
+
+// ---------------------------------------------------------------------------------------------
+// decode + clip + min-size + key
+// ---------------------------------------------------------------------------------------------
+struct DecodeArgs {
+    const float4* loc;
+    const float* score;
+    AnchorGen gen;
+    int batch, n;
+    float xmax, ymax, min_size;
+    int score_mode, decoded;
+    float4* boxes;
+    uint32_t* keys;
+    float* fg_out;
+};
+
+__device__ __forceinline__ float clamp_torch(float v, float hi) {
+    v = v < 0.f ? 0.f : v;  // NaN propagates like torch.clamp
+    v = v > hi ? hi : v;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) decode_clip_key_kernel(DecodeArgs a) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)a.batch * a.n;
+    if (t >= total) return;
+    int i = (int)(t % a.n);
+    float4 l = __ldg(a.loc + t);
+    float4 r;
+    if (a.decoded) {
+        r = l;
+    } else {
+        r = decode_box(load_anchor(a.gen, i), l);
+    }
+    float s;
+    if (a.score_mode == 0) {
+        s = __ldg(a.score + t);
+    } else {
+        float2 lg = __ldg(reinterpret_cast<const float2*>(a.score) + t);
+        float m = fmaxf(lg.x, lg.y);
+        float e0 = expf(lg.x - m), e1 = expf(lg.y - m);
+        s = e1 / (e0 + e1);
+    }
+    r.x = clamp_torch(r.x, a.xmax);
+    r.z = clamp_torch(r.z, a.xmax);
+    r.y = clamp_torch(r.y, a.ymax);
+    r.w = clamp_torch(r.w, a.ymax);
+    bool ok = ((r.z - r.x) >= a.min_size) && ((r.w - r.y) >= a.min_size);
+    a.boxes[t] = r;
+    a.keys[t] = ok ? score_key(s) : 0u;
+    if (a.fg_out) a.fg_out[t] = s;
+}
+
+__global__ void scores_to_keys_kernel(const float* __restrict__ s, int n, uint32_t* __restrict__ keys) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = score_key(__ldg(s + i));
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-image stable radix sort (descending key, ascending index on ties)
+// ---------------------------------------------------------------------------------------------
+constexpr int TOPK_THREADS = 1024;
+constexpr int TOPK_WARPS = TOPK_THREADS / 32;
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+topk_sort_kernel(const uint32_t* __restrict__ keys_all, const float4* __restrict__ boxes_all, int n,
+                 int k_cap, uint32_t* __restrict__ ws_keys, uint32_t* __restrict__ ws_idx,
+                 int* __restrict__ order_all, int* __restrict__ n_sel_all,
+                 float4* __restrict__ sorted_all) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t warp_cnt[TOPK_WARPS][256];
+    __shared__ uint32_t warp_tot[8];
+    __shared__ uint32_t s_nzero;
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t* keys = keys_all + (size_t)b * n;
+    uint32_t* bufK[2] = {ws_keys + (size_t)b * 2 * n, ws_keys + (size_t)b * 2 * n + n};
+    uint32_t* bufI[2] = {ws_idx + (size_t)b * 2 * n, ws_idx + (size_t)b * 2 * n + n};
+    const uint32_t lt = lanemask_lt();
+
+    if (tid == 0) s_nzero = 0;
+    int cur = -1;  // -1: data still in `keys` (identity permutation)
+
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 8 * pass;
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        // digit histogram, warp-aggregated
+        for (int base = 0; base < n; base += TOPK_THREADS) {
+            int i = base + tid;
+            bool valid = i < n;
+            uint32_t k = 0;
+            if (valid) k = (cur < 0) ? ~__ldg(keys + i) : bufK[cur][i];
+            uint32_t d = valid ? ((k >> shift) & 255u) : 256u;
+            uint32_t m = __match_any_sync(0xFFFFFFFFu, d);
+            if (valid && (m & lt) == 0) atomicAdd(&hist[d], (uint32_t)__popc(m));
+            if (pass == 0) {
+                uint32_t z = __ballot_sync(0xFFFFFFFFu, valid && k == 0xFFFFFFFFu);
+                if (lane == 0 && z) atomicAdd(&s_nzero, (uint32_t)__popc(z));
+            }
+        }
+        __syncthreads();
+        int trivial = __syncthreads_or(tid < 256 && hist[tid] == (uint32_t)n);
+        if (trivial) continue;  // every key shares this digit: pass is the identity
+        // exclusive scan of hist -> running base offsets
+        uint32_t v = 0, incl = 0;
+        if (tid < 256) {
+            v = hist[tid];
+            incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) warp_tot[warp] = incl;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t pre = 0;
+            for (int w = 0; w < warp; ++w) pre += warp_tot[w];
+            hist[tid] = pre + incl - v;
+        }
+        __syncthreads();
+        const int dst = (cur < 0) ? 0 : (cur ^ 1);
+        for (int base = 0; base < n; base += TOPK_THREADS) {
+            int i = base + tid;
+            bool valid = i < n;
+            uint32_t k = 0, id = (uint32_t)i;
+            if (valid) {
+                if (cur < 0) {
+                    k = ~__ldg(keys + i);
+                } else {
+                    k = bufK[cur][i];
+                    id = bufI[cur][i];
+                }
+            }
+            uint32_t d = valid ? ((k >> shift) & 255u) : 256u;
+            __syncwarp();
+            for (int j = lane; j < 256; j += 32) warp_cnt[warp][j] = 0;
+            __syncwarp();
+            uint32_t m = __match_any_sync(0xFFFFFFFFu, d);
+            uint32_t rank = __popc(m & lt);
+            if (valid && rank == 0) warp_cnt[warp][d] = __popc(m);
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t run = hist[tid];
+#pragma unroll 8
+                for (int w = 0; w < TOPK_WARPS; ++w) {
+                    uint32_t c = warp_cnt[w][tid];
+                    warp_cnt[w][tid] = run;
+                    run += c;
+                }
+                hist[tid] = run;
+            }
+            __syncthreads();
+            if (valid) {
+                uint32_t pos = warp_cnt[warp][d] + rank;
+                bufK[dst][pos] = k;
+                bufI[dst][pos] = id;
+            }
+        }
+        __syncthreads();  // scatter visible to the whole CTA before the next pass reads it
+        cur = dst;
+    }
+    __syncthreads();
+    const int n_valid = n - (int)s_nzero;
+    const int n_sel = n_valid < k_cap ? n_valid : k_cap;
+    if (tid == 0) n_sel_all[b] = n_sel;
+    int* order = order_all + (size_t)b * k_cap;
+    for (int j = tid; j < k_cap; j += TOPK_THREADS) {
+        int id = -1;
+        if (j < n_sel) id = (cur < 0) ? j : (int)bufI[cur][j];
+        order[j] = id;
+        if (sorted_all) {
+            float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (id >= 0) bx = __ldg(boxes_all + (size_t)b * n + id);
+            sorted_all[(size_t)b * k_cap + j] = bx;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NMS over score-sorted boxes
+// ---------------------------------------------------------------------------------------------
+struct NmsState {
+    int n_kept;
+    int done;
+};
+
+constexpr int NMS_CB = 256;   // columns per CTA tile (8 warps x 32 lanes)
+constexpr int NMS_RB = 64;    // rows staged per in-block tile
+constexpr int NMS_KC = 256;   // kept boxes staged per prev tile
+
+// torchvision nms_kernel: inter / (area_i + area_j - inter) > thr  (no eps; NaN never suppresses).
+// `thr` is the largest float <= the double threshold, so (float)ovr > thr <=> (double)ovr > thr_d.
+__device__ __forceinline__ bool nms_suppresses(const float4& r, float ra, const float4& c, float ca, float thr) {
+    float xx1 = fmaxf(r.x, c.x), yy1 = fmaxf(r.y, c.y);
+    float xx2 = fminf(r.z, c.z), yy2 = fminf(r.w, c.w);
+    float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
+    float inter = w * h;
+    float uni = ra + ca;
+    uni = uni - inter;
+    return (inter / uni) > thr;
+}
+
+struct NmsArgs {
+    const float4* boxes;   // [B,row_stride]
+    const int* n_sel;      // [B]
+    int row_stride, S, sb, keep_cap;
+    float thr;
+    uint32_t* mask;        // [B][S/32][S]
+    uint32_t* removed;     // [B][S/32]
+    float4* kept_box;      // [B][keep_cap]
+    NmsState* state;       // [B]
+    int* keep;             // [B][keep_cap]
+    int* n_keep;           // [B]
+    int tri_tiles;
+};
+
+__global__ void __launch_bounds__(NMS_CB) nms_mask_kernel(NmsArgs a) {
+    __shared__ float4 srow[NMS_KC];
+    __shared__ float sarea[NMS_KC];
+    const int b = blockIdx.y;
+    const NmsState st = a.state[b];
+    if (st.done) return;
+    const int n = a.n_sel[b];
+    const int c0 = a.sb * a.S;
+    if (c0 >= n) return;
+    const int c1 = min(c0 + a.S, n);
+    const float4* boxes = a.boxes + (size_t)b * a.row_stride;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int t = blockIdx.x;
+    if (t < a.tri_tiles) {
+        // in-block tile: decode t -> (cb, rb), rb < 4*(cb+1)
+        int cb = 0;
+        while (2 * (cb + 1) * (cb + 2) <= t) ++cb;
+        int rb = t - 2 * cb * (cb + 1);
+        int col0 = c0 + cb * NMS_CB, row0 = c0 + rb * NMS_RB;
+        if (col0 >= c1 || row0 >= c1) return;
+        if (threadIdx.x < NMS_RB) {
+            int r = row0 + threadIdx.x;
+            float4 v = r < c1 ? __ldg(boxes + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+            srow[threadIdx.x] = v;
+            sarea[threadIdx.x] = box_area(v);
+        }
+        __syncthreads();
+        int c = col0 + warp * 32 + lane;
+        bool cvalid = c < c1;
+        float4 cbx = cvalid ? __ldg(boxes + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float ca = box_area(cbx);
+        int cw = cb * (NMS_CB / 32) + warp;
+        if (col0 + warp * 32 >= c1) return;
+        uint32_t* mrow = a.mask + ((size_t)b * (a.S / 32) + cw) * a.S + (row0 - c0);
+        uint32_t mine = 0;
+#pragma unroll 4
+        for (int r = 0; r < NMS_RB; ++r) {
+            bool p = cvalid && (row0 + r < c1) && nms_suppresses(srow[r], sarea[r], cbx, ca, a.thr);
+            uint32_t w = __ballot_sync(0xFFFFFFFFu, p);
+            if ((r & 31) == lane) mine = w;
+            if ((r & 31) == 31) mrow[(r - 31) + lane] = mine;
+        }
+    } else {
+        // suppression by boxes kept in earlier super-blocks
+        t -= a.tri_tiles;
+        int ncb = a.S / NMS_CB;
+        int cb = t % ncb, kc = t / ncb;
+        int k0 = kc * NMS_KC;
+        if (k0 >= st.n_kept) return;
+        int col0 = c0 + cb * NMS_CB;
+        if (col0 >= c1) return;
+        int kn = min(NMS_KC, st.n_kept - k0);
+        if (threadIdx.x < kn) {
+            float4 v = a.kept_box[(size_t)b * a.keep_cap + k0 + threadIdx.x];
+            srow[threadIdx.x] = v;
+            sarea[threadIdx.x] = box_area(v);
+        }
+        __syncthreads();
+        int c = col0 + warp * 32 + lane;
+        bool cvalid = c < c1;
+        float4 cbx = cvalid ? __ldg(boxes + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float ca = box_area(cbx);
+        bool sup = false;
+        for (int r = 0; r < kn; ++r) {
+            sup = sup || nms_suppresses(srow[r], sarea[r], cbx, ca, a.thr);
+            if ((r & 15) == 15 && __all_sync(0xFFFFFFFFu, sup || !cvalid)) break;
+        }
+        uint32_t w = __ballot_sync(0xFFFFFFFFu, sup && cvalid);
+        if (lane == 0 && w) atomicOr(a.removed + (size_t)b * (a.S / 32) + cb * (NMS_CB / 32) + warp, w);
+    }
+}
+
+constexpr int NMS_SCAN_THREADS = 512;
+constexpr int NMS_MAX_WORDS = 256;  // S <= 8192
+
+__global__ void __launch_bounds__(NMS_SCAN_THREADS) nms_scan_kernel(NmsArgs a) {
+    __shared__ uint32_t R[NMS_MAX_WORDS];      // removed bits of this super-block
+    __shared__ uint32_t Kb[NMS_MAX_WORDS];     // kept bits of this super-block
+    __shared__ uint32_t partial[NMS_SCAN_THREADS / 32];
+    __shared__ int s_nkept, s_done;
+    const int b = blockIdx.x;
+    NmsState st = a.state[b];
+    if (st.done) return;
+    const int n = a.n_sel[b];
+    const int c0 = a.sb * a.S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (c0 >= n) {
+        if (tid == 0) {
+            a.state[b].done = 1;
+            a.n_keep[b] = st.n_kept;
+        }
+        return;
+    }
+    const int c1 = min(c0 + a.S, n);
+    const int ncol = c1 - c0, nw = (ncol + 31) / 32;
+    const float4* boxes = a.boxes + (size_t)b * a.row_stride;
+    uint32_t* removed = a.removed + (size_t)b * (a.S / 32);
+    const uint32_t* mask = a.mask + (size_t)b * (a.S / 32) * a.S;
+    for (int j = tid; j < a.S / 32; j += NMS_SCAN_THREADS) {
+        uint32_t v = removed[j];
+        removed[j] = 0;  // ready for the next super-block
+        if (j == nw - 1 && (ncol & 31)) v |= ~0u << (ncol & 31);
+        R[j] = v;
+        Kb[j] = 0;
+    }
+    if (tid == 0) {
+        s_nkept = st.n_kept;
+        s_done = 0;
+    }
+    __syncthreads();
+    // software pipeline: the column-w words M[w][0..32w) are loaded one step ahead
+    const int rows_per_iter = NMS_SCAN_THREADS * 4;
+    for (int w = 0; w < nw; ++w) {
+        // (1) R[w] |= OR over kept rows r < 32w of M[w][r]
+        uint32_t acc = 0;
+        const uint32_t* mcol = mask + (size_t)w * a.S;
+        for (int r4 = tid * 4; r4 < 32 * w; r4 += rows_per_iter) {
+            uint4 m = *reinterpret_cast<const uint4*>(mcol + r4);
+            uint32_t sel = Kb[r4 >> 5] >> (r4 & 31);
+            acc |= (sel & 1u) ? m.x : 0u;
+            acc |= (sel & 2u) ? m.y : 0u;
+            acc |= (sel & 4u) ? m.z : 0u;
+            acc |= (sel & 8u) ? m.w : 0u;
+        }
+        acc = __reduce_or_sync(0xFFFFFFFFu, acc);
+        if (lane == 0) partial[warp] = acc;
+        __syncthreads();
+        // (2) warp 0 resolves the 32 candidates of block w
+        if (warp == 0) {
+            uint32_t pv = lane < NMS_SCAN_THREADS / 32 ? partial[lane] : 0u;
+            uint32_t rw = R[w] | __reduce_or_sync(0xFFFFFFFFu, pv);
+            int row = 32 * w + lane;
+            uint32_t D = (row < ncol) ? mcol[row] : 0u;
+            D &= ~((2u << lane) - 1u);  // only later candidates can be suppressed
+            uint32_t kb = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                uint32_t di = __shfl_sync(0xFFFFFFFFu, D, i);
+                if (!((rw >> i) & 1u)) {
+                    kb |= 1u << i;
+                    rw |= di;
+                }
+            }
+            int nk = s_nkept;
+            int room = a.keep_cap - nk;
+            int cnt = __popc(kb);
+            int done = 0;
+            if (cnt >= room) {
+                while (__popc(kb) > room) kb &= ~(0x80000000u >> __clz(kb));
+                cnt = __popc(kb);
+                done = 1;
+            }
+            if ((kb >> lane) & 1u) {
+                int pos = nk + __popc(kb & ((1u << lane) - 1u));
+                a.keep[(size_t)b * a.keep_cap + pos] = c0 + row;
+                a.kept_box[(size_t)b * a.keep_cap + pos] = __ldg(boxes + c0 + row);
+            }
+            if (lane == 0) {
+                Kb[w] = kb;
+                s_nkept = nk + cnt;
+                if (done) s_done = 1;
+            }
+        }
+        __syncthreads();
+        if (s_done) break;
+    }
+    if (tid == 0) {
+        int done = s_done || (c1 >= n);
+        a.state[b].n_kept = s_nkept;
+        a.state[b].done = done;
+        a.n_keep[b] = s_nkept;
+    }
+}
+
+// nets/rpn.py:65-69: pad with arange, truncate, gather
+__global__ void finalize_kernel(const float4* __restrict__ sorted, const int* __restrict__ order,
+                                const int* __restrict__ n_sel_all, const int* __restrict__ keep,
+                                const int* __restrict__ n_keep_all, int row_stride, int n_post,
+                                float4* __restrict__ rois, int* __restrict__ roi_src,
+                                int* __restrict__ n_keep_out, int* __restrict__ status) {
+    const int b = blockIdx.x;
+    const int n_sel = n_sel_all[b], k = n_keep_all[b];
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (int r = threadIdx.x; r < n_post; r += blockDim.x) {
+        int p = r < k ? keep[(size_t)b * n_post + r] : r - k;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        int src = -1;
+        if (p < n_sel) {
+            v = sorted[(size_t)b * row_stride + p];
+            src = order[(size_t)b * row_stride + p];
+        } else {
+            bad = 1;
+        }
+        rois[(size_t)b * n_post + r] = v;
+        if (roi_src) roi_src[(size_t)b * n_post + r] = src;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        status[b] = bad ? FRCNN_IMG_PAD_INDEX_ERROR : FRCNN_IMG_OK;
+        if (n_keep_out) n_keep_out[b] = k;
+    }
+}
+
+__global__ void keep_to_index_kernel(const int* __restrict__ keep, const int* __restrict__ n_keep,
+                                     const int* __restrict__ order, int64_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_keep[0]) out[i] = order[keep[i]];
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static float float_threshold(double thr) {
+    // largest float T with T <= thr, so that for every float x: x > T  <=>  (double)x > thr
+    float t = (float)thr;
+    if ((double)t > thr) t = nextafterf(t, -INFINITY);
+    return t;
+}
+
+static int pick_superblock(int requested, int n_rows) {
+    int S = requested > 0 ? requested : 2048;
+    S = (S + NMS_CB - 1) / NMS_CB * NMS_CB;
+    if (S > NMS_MAX_WORDS * 32) S = NMS_MAX_WORDS * 32;
+    int need = (n_rows + NMS_CB - 1) / NMS_CB * NMS_CB;
+    if (need < NMS_CB) need = NMS_CB;
+    if (S > need) S = need;
+    return S;
+}
+
+struct NmsLayout {
+    int S;
+    size_t mask_words, removed_words;
+};
+
+static size_t nms_ws_layout(Workspace& ws, int batch, int n_rows, int keep_cap, int superblock,
+                            NmsArgs* a) {
+    int S = pick_superblock(superblock, n_rows);
+    uint32_t* mask = ws.take<uint32_t>((size_t)batch * (S / 32) * S);
+    // state + removed are cleared together by one memset
+    size_t clear_bytes = align_up((size_t)batch * sizeof(NmsState)) + align_up((size_t)batch * (S / 32) * 4);
+    NmsState* state = ws.take<NmsState>(batch);
+    uint32_t* removed = ws.take<uint32_t>((size_t)batch * (S / 32));
+    float4* kept_box = ws.take<float4>((size_t)batch * (keep_cap > 0 ? keep_cap : 1));
+    if (a) {
+        a->S = S;
+        a->mask = mask;
+        a->state = state;
+        a->removed = removed;
+        a->kept_box = kept_box;
+    }
+    return clear_bytes;
+}
+
+static int run_nms_sorted(const float* sorted_boxes, const int32_t* n_sel, int batch, int row_stride,
+                          double thresh, int keep_cap, int superblock, int32_t* keep, int32_t* n_keep,
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    Workspace ws(workspace, workspace_bytes);
+    NmsArgs a;
+    memset(&a, 0, sizeof(a));
+    size_t clear_bytes = nms_ws_layout(ws, batch, row_stride, keep_cap, superblock, &a);
+    if (!ws.ok()) {
+        set_error("nms: workspace too small or misaligned (%zu needed, %zu given)", ws.off, workspace_bytes);
+        return FRCNN_ERR_WORKSPACE;
+    }
+    a.boxes = (const float4*)sorted_boxes;
+    a.n_sel = n_sel;
+    a.row_stride = row_stride;
+    a.keep_cap = keep_cap;
+    a.thr = float_threshold(thresh);
+    a.keep = keep;
+    a.n_keep = n_keep;
+    FRCNN_CUDA(cudaMemsetAsync(a.state, 0, clear_bytes, stream));
+    int ncb = a.S / NMS_CB;
+    a.tri_tiles = 2 * ncb * (ncb + 1);
+    int n_sb = cdiv(row_stride, a.S);
+    int prev_tiles = ncb * cdiv(keep_cap, NMS_KC);
+    for (int sb = 0; sb < n_sb; ++sb) {
+        a.sb = sb;
+        dim3 grid(a.tri_tiles + (sb > 0 ? prev_tiles : 0), batch);
+        nms_mask_kernel<<<grid, NMS_CB, 0, stream>>>(a);
+        FRCNN_LAUNCH_CHECK();
+        nms_scan_kernel<<<batch, NMS_SCAN_THREADS, 0, stream>>>(a);
+        FRCNN_LAUNCH_CHECK();
+    }
+    return FRCNN_OK;
+}
+
+static int run_topk(const uint32_t* keys, const float* boxes, int batch, int n, int k_cap, int32_t* order,
+                    int32_t* n_sel, float* sorted_boxes, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream) {
+    Workspace ws(workspace, workspace_bytes);
+    uint32_t* wk = ws.take<uint32_t>((size_t)batch * 2 * n);
+    uint32_t* wi = ws.take<uint32_t>((size_t)batch * 2 * n);
+    if (!ws.ok()) {
+        set_error("topk: workspace too small or misaligned (%zu needed, %zu given)", ws.off, workspace_bytes);
+        return FRCNN_ERR_WORKSPACE;
+    }
+    topk_sort_kernel<<<batch, TOPK_THREADS, 0, stream>>>(keys, (const float4*)boxes, n, k_cap, wk, wi, order,
+                                                         n_sel, (float4*)sorted_boxes);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
+static AnchorGen make_gen(const frcnn_anchor_spec* s) {
+    AnchorGen g;
+    g.anchors = (const float4*)s->anchors;
+    g.base = (const float4*)s->base;
+    g.num_base = s->num_base;
+    g.stride = s->feat_stride;
+    g.height = s->height;
+    g.width = s->width;
+    return g;
+}
+
+static int check_anchor_spec(const frcnn_anchor_spec* s, int n, const char* who) {
+    if (!s) {
+        set_error("%s: anchor spec is null", who);
+        return FRCNN_ERR_INVALID_ARG;
+    }
+    if (s->anchors) return FRCNN_OK;
+    if (!s->base || s->num_base <= 0 || s->num_base > FRCNN_MAX_BASE_ANCHORS || s->width <= 0 ||
+        (int64_t)s->num_base * s->height * s->width != n) {
+        set_error("%s: generated anchors need base/num_base and H*W*A == N (%d)", who, n);
+        return FRCNN_ERR_INVALID_ARG;
+    }
+    return FRCNN_OK;
+}
+
+static int run_decode(const frcnn_proposal_params* p, const frcnn_anchor_spec* anchors, const float* loc,
+                      const float* score, float* boxes, uint32_t* keys, float* fg_out, cudaStream_t stream) {
+    DecodeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.loc = (const float4*)loc;
+    a.score = score;
+    if (!p->boxes_are_decoded) a.gen = make_gen(anchors);
+    a.batch = p->batch;
+    a.n = p->num_anchors;
+    a.xmax = p->clip_x_max;
+    a.ymax = p->clip_y_max;
+    a.min_size = p->min_size;
+    a.score_mode = p->score_mode;
+    a.decoded = p->boxes_are_decoded;
+    a.boxes = (float4*)boxes;
+    a.keys = keys;
+    a.fg_out = fg_out;
+    int64_t total = (int64_t)p->batch * p->num_anchors;
+    decode_clip_key_kernel<<<cdiv(total, 256), 256, 0, stream>>>(a);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
+static int check_params(const frcnn_proposal_params* p, const frcnn_anchor_spec* anchors, const char* who) {
+    FRCNN_CHECK_ARG(p, "%s: params is null", who);
+    FRCNN_CHECK_ARG(p->batch > 0 && p->num_anchors > 0, "%s: batch and num_anchors must be positive", who);
+    FRCNN_CHECK_ARG(p->n_post_nms >= 0, "%s: n_post_nms must be >= 0", who);
+    FRCNN_CHECK_ARG((int64_t)p->batch * p->num_anchors < (1ll << 31), "%s: batch*num_anchors too large", who);
+    FRCNN_CHECK_ARG(p->score_mode == 0 || p->score_mode == 1, "%s: bad score_mode", who);
+    if (!p->boxes_are_decoded) {
+        int rc = check_anchor_spec(anchors, p->num_anchors, who);
+        if (rc) return rc;
+    }
+    return FRCNN_OK;
+}
+
+static int n_pre_rows(const frcnn_proposal_params* p) {
+    return (p->n_pre_nms > 0 && p->n_pre_nms < p->num_anchors) ? p->n_pre_nms : p->num_anchors;
+}
+
+}  // namespace frcnn
+
+using namespace frcnn;
+
+extern "C" {
+
+size_t frcnn_topk_workspace_bytes(int32_t batch, int32_t n) {
+    Workspace ws(nullptr, 0);
+    ws.take<uint32_t>((size_t)batch * 2 * n);
+    ws.take<uint32_t>((size_t)batch * 2 * n);
+    return ws.off;
+}
+
+size_t frcnn_nms_sorted_workspace_bytes(int32_t batch, int32_t n_rows, int32_t keep_cap, int32_t superblock) {
+    Workspace ws(nullptr, 0);
+    nms_ws_layout(ws, batch, n_rows, keep_cap, superblock, nullptr);
+    return ws.off;
+}
+
+int frcnn_decode_clip_score(const frcnn_proposal_params* p, const frcnn_anchor_spec* anchors,
+                            const float* loc, const float* score, float* boxes, uint32_t* keys,
+                            float* fg_out, frcnn_stream_t stream) {
+    int rc = check_params(p, anchors, "frcnn_decode_clip_score");
+    if (rc) return rc;
+    FRCNN_CHECK_ARG(loc && score && boxes && keys, "frcnn_decode_clip_score: null pointer");
+    return run_decode(p, anchors, loc, score, boxes, keys, fg_out, (cudaStream_t)stream);
+}
+
+int frcnn_topk_sorted(const uint32_t* keys, const float* boxes, int32_t batch, int32_t n, int32_t k_cap,
+                      int32_t* order, int32_t* n_sel, float* sorted_boxes, void* workspace,
+                      size_t workspace_bytes, frcnn_stream_t stream) {
+    FRCNN_CHECK_ARG(batch > 0 && n > 0 && k_cap > 0, "frcnn_topk_sorted: bad shape");
+    FRCNN_CHECK_ARG(keys && order && n_sel, "frcnn_topk_sorted: null pointer");
+    FRCNN_CHECK_ARG((sorted_boxes == nullptr) || (boxes != nullptr), "frcnn_topk_sorted: sorted_boxes needs boxes");
+    return run_topk(keys, boxes, batch, n, k_cap, order, n_sel, sorted_boxes, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
+}
+
+int frcnn_nms_sorted(const float* sorted_boxes, const int32_t* n_sel, int32_t batch, int32_t row_stride,
+                     double thresh, int32_t keep_cap, int32_t superblock, int32_t* keep, int32_t* n_keep,
+                     void* workspace, size_t workspace_bytes, frcnn_stream_t stream) {
+    FRCNN_CHECK_ARG(batch > 0 && row_stride > 0 && keep_cap > 0, "frcnn_nms_sorted: bad shape");
+    FRCNN_CHECK_ARG(sorted_boxes && n_sel && keep && n_keep, "frcnn_nms_sorted: null pointer");
+    return run_nms_sorted(sorted_boxes, n_sel, batch, row_stride, thresh, keep_cap, superblock, keep, n_keep,
+                          workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// workspace of the fused pipeline: boxes, keys, order, n_sel, sorted, keep, n_keep, topk ws, nms ws
+struct ProposalWs {
+    float* boxes;
+    uint32_t* keys;
+    int32_t* order;
+    int32_t* n_sel;
+    float* sorted;
+    int32_t* keep;
+    int32_t* n_keep;
+    void* topk_ws;
+    size_t topk_bytes;
+    void* nms_ws;
+    size_t nms_bytes;
+};
+
+static size_t proposal_layout(Workspace& ws, const frcnn_proposal_params* p, ProposalWs* out) {
+    int B = p->batch, N = p->num_anchors, rows = n_pre_rows(p);
+    int cap = p->n_post_nms > 0 ? p->n_post_nms : 1;
+    ProposalWs w;
+    w.boxes = ws.take<float>((size_t)B * N * 4);
+    w.keys = ws.take<uint32_t>((size_t)B * N);
+    w.order = ws.take<int32_t>((size_t)B * rows);
+    w.n_sel = ws.take<int32_t>(B);
+    w.sorted = ws.take<float>((size_t)B * rows * 4);
+    w.keep = ws.take<int32_t>((size_t)B * cap);
+    w.n_keep = ws.take<int32_t>(B);
+    w.topk_bytes = frcnn_topk_workspace_bytes(B, N);
+    w.topk_ws = ws.take<char>(w.topk_bytes);
+    w.nms_bytes = frcnn_nms_sorted_workspace_bytes(B, rows, cap, p->nms_superblock);
+    w.nms_ws = ws.take<char>(w.nms_bytes);
+    if (out) *out = w;
+    return ws.off;
+}
+
+size_t frcnn_proposals_workspace_bytes(const frcnn_proposal_params* p) {
+    if (!p || p->batch <= 0 || p->num_anchors <= 0) return 0;
+    Workspace ws(nullptr, 0);
+    return proposal_layout(ws, p, nullptr);
+}
+
+int frcnn_proposals(const frcnn_proposal_params* p, const frcnn_anchor_spec* anchors, const float* loc,
+                    const float* score, float* rois, int32_t* roi_src, int32_t* n_keep, int32_t* status,
+                    void* workspace, size_t workspace_bytes, frcnn_stream_t stream_) {
+    int rc = check_params(p, anchors, "frcnn_proposals");
+    if (rc) return rc;
+    FRCNN_CHECK_ARG(loc && score && status, "frcnn_proposals: null pointer");
+    FRCNN_CHECK_ARG(p->n_post_nms == 0 || rois, "frcnn_proposals: rois is null");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Workspace ws(workspace, workspace_bytes);
+    ProposalWs w;
+    proposal_layout(ws, p, &w);
+    if (!ws.ok()) {
+        set_error("frcnn_proposals: workspace too small or misaligned (%zu needed, %zu given)", ws.off,
+                  workspace_bytes);
+        return FRCNN_ERR_WORKSPACE;
+    }
+    int B = p->batch, N = p->num_anchors, rows = n_pre_rows(p);
+    if (p->n_post_nms == 0) {
+        FRCNN_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * B, stream));
+        if (n_keep) FRCNN_CUDA(cudaMemsetAsync(n_keep, 0, sizeof(int32_t) * B, stream));
+        return FRCNN_OK;
+    }
+    rc = run_decode(p, anchors, loc, score, w.boxes, w.keys, nullptr, stream);
+    if (rc) return rc;
+    rc = run_topk(w.keys, w.boxes, B, N, rows, w.order, w.n_sel, w.sorted, w.topk_ws, w.topk_bytes, stream);
+    if (rc) return rc;
+    rc = run_nms_sorted(w.sorted, w.n_sel, B, rows, p->nms_thresh, p->n_post_nms, p->nms_superblock, w.keep,
+                        w.n_keep, w.nms_ws, w.nms_bytes, stream);
+    if (rc) return rc;
+    finalize_kernel<<<B, 256, 0, stream>>>((const float4*)w.sorted, w.order, w.n_sel, w.keep, w.n_keep, rows,
+                                           p->n_post_nms, (float4*)rois, roi_src, n_keep, status);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
+struct NmsWs {
+    uint32_t* keys;
+    int32_t* order;
+    int32_t* n_sel;
+    float* sorted;
+    int32_t* keep;
+    void* topk_ws;
+    size_t topk_bytes;
+    void* nms_ws;
+    size_t nms_bytes;
+};
+
+static size_t nms_layout(Workspace& ws, int n, NmsWs* out) {
+    NmsWs w;
+    w.keys = ws.take<uint32_t>(n);
+    w.order = ws.take<int32_t>(n);
+    w.n_sel = ws.take<int32_t>(1);
+    w.sorted = ws.take<float>((size_t)n * 4);
+    w.keep = ws.take<int32_t>(n);
+    w.topk_bytes = frcnn_topk_workspace_bytes(1, n);
+    w.topk_ws = ws.take<char>(w.topk_bytes);
+    w.nms_bytes = frcnn_nms_sorted_workspace_bytes(1, n, n, 0);
+    w.nms_ws = ws.take<char>(w.nms_bytes);
+    if (out) *out = w;
+    return ws.off;
+}
+
+size_t frcnn_nms_workspace_bytes(int32_t n) {
+    if (n <= 0) return 256;
+    Workspace ws(nullptr, 0);
+    return nms_layout(ws, n, nullptr);
+}
+
+int frcnn_nms(const float* boxes, const float* scores, int32_t n, double thresh, int64_t* keep,
+              int32_t* n_keep, void* workspace, size_t workspace_bytes, frcnn_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FRCNN_CHECK_ARG(n >= 0 && n_keep, "frcnn_nms: bad arguments");
+    if (n == 0) {
+        FRCNN_CUDA(cudaMemsetAsync(n_keep, 0, sizeof(int32_t), stream));
+        return FRCNN_OK;
+    }
+    FRCNN_CHECK_ARG(boxes && scores && keep, "frcnn_nms: null pointer");
+    Workspace ws(workspace, workspace_bytes);
+    NmsWs w;
+    nms_layout(ws, n, &w);
+    if (!ws.ok()) {
+        set_error("frcnn_nms: workspace too small or misaligned (%zu needed, %zu given)", ws.off, workspace_bytes);
+        return FRCNN_ERR_WORKSPACE;
+    }
+    scores_to_keys_kernel<<<cdiv(n, 256), 256, 0, stream>>>(scores, n, w.keys);
+    FRCNN_LAUNCH_CHECK();
+    int rc = run_topk(w.keys, boxes, 1, n, n, w.order, w.n_sel, w.sorted, w.topk_ws, w.topk_bytes, stream);
+    if (rc) return rc;
+    rc = run_nms_sorted(w.sorted, w.n_sel, 1, n, thresh, n, 0, w.keep, n_keep, w.nms_ws, w.nms_bytes, stream);
+    if (rc) return rc;
+    keep_to_index_kernel<<<cdiv(n, 256), 256, 0, stream>>>(w.keep, n_keep, w.order, keep);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,658 @@
+// roi_ops.cu -- RoI feature gathering for the classifier head (nets/classify.py:29-43):
+// torchvision RoIPool / roi_align forward (+ backward) as sm_100a kernels.
+//
+// Data flow of the forward kernels: RoIs are bucketed per image on the device; one CTA owns
+// (image, channel slab, RoI group), stages the slab's full H x W feature planes into shared memory
+// with TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP), then every thread produces output
+// elements from shared memory and stores them coalesced along the contiguous [C,P,P] axis of the
+// RoI.  Features are read from L2/HBM once per (slab, group); the dominant HBM traffic is the
+// K*C*P*P*4 B output write.
+#include <float.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace frcnn {
+
+// ---------------------------------------------------------------------------------------------
+// nets/classify.py:33-38
+// ---------------------------------------------------------------------------------------------
+__global__ void roi_head_coords_kernel(const float4* __restrict__ rois, const int* __restrict__ idx, int total,
+                                       int per_image, float d0, float d1, float fh, float fw,
+                                       float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float4 r = __ldg(rois + i);
+    float* o = out + (size_t)i * 5;
+    o[0] = (float)__ldg(idx + i / per_image);
+    o[1] = (r.x / d1) * fw;
+    o[2] = (r.y / d0) * fh;
+    o[3] = (r.z / d1) * fw;
+    o[4] = (r.w / d0) * fh;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bucket RoIs by image: perm[offs[b] .. offs[b+1]) = RoI ids of image b
+// ---------------------------------------------------------------------------------------------
+constexpr int BUCKET_THREADS = 1024;
+
+__global__ void __launch_bounds__(BUCKET_THREADS)
+roi_bucket_kernel(const float* __restrict__ rois5, int K, int B, int* __restrict__ perm, int* __restrict__ offs) {
+    extern __shared__ int sb[];  // cnt[B], cur[B]
+    int* cnt = sb;
+    int* cur = sb + B;
+    __shared__ int chunk_tot[BUCKET_THREADS];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < B; i += BUCKET_THREADS) cnt[i] = 0;
+    __syncthreads();
+    for (int k = tid; k < K; k += BUCKET_THREADS) {
+        int b = (int)__ldg(rois5 + (size_t)k * 5);
+        if (b >= 0 && b < B) atomicAdd(&cnt[b], 1);
+    }
+    __syncthreads();
+    // exclusive scan: each thread owns a contiguous chunk of images
+    int per = (B + BUCKET_THREADS - 1) / BUCKET_THREADS;
+    int lo = tid * per, hi = min(lo + per, B);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += cnt[i];
+    chunk_tot[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int i = 0; i < BUCKET_THREADS; ++i) {
+            int t = chunk_tot[i];
+            chunk_tot[i] = run;
+            run += t;
+        }
+        offs[B] = run;
+    }
+    __syncthreads();
+    int run = chunk_tot[tid];
+    for (int i = lo; i < hi; ++i) {
+        cur[i] = run;
+        offs[i] = run;
+        run += cnt[i];
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += BUCKET_THREADS) {
+        int b = (int)__ldg(rois5 + (size_t)k * 5);
+        if (b >= 0 && b < B) perm[atomicAdd(&cur[b], 1)] = k;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA bulk-copy helpers (1-D cp.async.bulk global -> shared, completion on an mbarrier)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Stage `count` floats (contiguous in global memory) into shared memory.  TMA path when the source
+// is 16-byte aligned and the size a multiple of 16 bytes; plain coalesced loads otherwise.
+__device__ __forceinline__ void stage_slab(float* sdst, const float* gsrc, int count, uint64_t* bar) {
+    const bool tma_ok = ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0) && ((count & 3) == 0);
+    if (tma_ok) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t bytes = (uint32_t)count * 4u;
+            mbar_expect_tx(bar, bytes);
+            const uint32_t chunk = 32768u;
+            for (uint32_t off = 0; off < bytes; off += chunk) {
+                uint32_t nb = min(chunk, bytes - off);
+                bulk_g2s(reinterpret_cast<char*>(sdst) + off, reinterpret_cast<const char*>(gsrc) + off, nb, bar);
+            }
+        }
+        mbar_wait(bar, 0);
+    } else {
+        for (int i = threadIdx.x; i < count; i += blockDim.x) sdst[i] = __ldg(gsrc + i);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RoIPool forward
+// ---------------------------------------------------------------------------------------------
+constexpr int ROI_THREADS = 512;
+constexpr int ROI_NB = 8;        // RoIs per inner batch (one table build + one sync per batch)
+constexpr int ROI_MAX_P = 32;    // largest pooled size served by the staged kernels
+
+struct RoiArgs {
+    const float* feat;
+    const float* rois5;
+    const int* perm;
+    const int* offs;
+    int B, C, H, W, K, PH, PW;
+    float scale;
+    int CS;          // channels per slab
+    int groups;      // RoI groups per image
+    float* out;
+    int* argmax;
+    int sampling_ratio, aligned;
+};
+
+__device__ __forceinline__ int round_half_away(float v) { return (int)roundf(v); }
+
+template <int P, bool WITH_ARGMAX>
+__global__ void __launch_bounds__(ROI_THREADS, 2) roi_pool_staged_kernel(RoiArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int s_roi[ROI_NB];
+    __shared__ int th[ROI_NB][ROI_MAX_P];  // hstart | hend << 16
+    __shared__ int tw[ROI_NB][ROI_MAX_P];  // wstart | wend << 16
+    float* sfeat = reinterpret_cast<float*>(smem_raw);
+    const int PH = P > 0 ? P : a.PH, PW = P > 0 ? P : a.PW;
+    const int PP = PH * PW;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * a.CS;
+    const int cs = min(a.CS, a.C - c0);
+    const int HW = a.H * a.W;
+    const int r_begin = a.offs[b], r_end = a.offs[b + 1];
+    const int first = r_begin + blockIdx.x;
+    if (first >= r_end) return;
+    stage_slab(sfeat, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
+
+    const int per_roi = cs * PP;
+    for (int rb = first; rb < r_end; rb += a.groups * ROI_NB) {
+        // RoIs of this batch: rb, rb+groups, ...  (strided so groups stay balanced)
+        int nb = 0;
+        for (int j = 0; j < ROI_NB; ++j)
+            if (rb + j * a.groups < r_end) nb = j + 1;
+        __syncthreads();  // previous batch done with the tables
+        if (threadIdx.x < nb * (PH + PW)) {
+            int j = threadIdx.x / (PH + PW), e = threadIdx.x % (PH + PW);
+            int k = a.perm[rb + j * a.groups];
+            const float* r = a.rois5 + (size_t)k * 5;
+            if (e == 0) s_roi[j] = k;
+            if (e < PH) {
+                int sh = round_half_away(__ldg(r + 2) * a.scale), eh = round_half_away(__ldg(r + 4) * a.scale);
+                int rh = max(eh - sh + 1, 1);
+                float bin = (float)rh / (float)PH;
+                int hs = (int)floorf((float)e * bin), he = (int)ceilf((float)(e + 1) * bin);
+                hs = min(max(hs + sh, 0), a.H);
+                he = min(max(he + sh, 0), a.H);
+                th[j][e] = hs | (he << 16);
+            } else {
+                int p = e - PH;
+                int sw = round_half_away(__ldg(r + 1) * a.scale), ew = round_half_away(__ldg(r + 3) * a.scale);
+                int rw = max(ew - sw + 1, 1);
+                float bin = (float)rw / (float)PW;
+                int ws = (int)floorf((float)p * bin), we = (int)ceilf((float)(p + 1) * bin);
+                ws = min(max(ws + sw, 0), a.W);
+                we = min(max(we + sw, 0), a.W);
+                tw[j][p] = ws | (we << 16);
+            }
+        }
+        __syncthreads();
+        const int total = nb * per_roi;
+        for (int it = threadIdx.x; it < total; it += ROI_THREADS) {
+            int j = it / per_roi, rem = it - j * per_roi;
+            int c = rem / PP, bin = rem - c * PP;
+            int ph = bin / PW, pw = bin - ph * PW;
+            int hh = th[j][ph], ww = tw[j][pw];
+            int hs = hh & 0xFFFF, he = hh >> 16, ws = ww & 0xFFFF, we = ww >> 16;
+            const float* plane = sfeat + c * HW;
+            bool empty = (he <= hs) || (we <= ws);
+            float best = empty ? 0.f : -FLT_MAX;
+            int besti = -1;
+            for (int h = hs; h < he; ++h) {
+                const float* row = plane + h * a.W;
+                for (int w = ws; w < we; ++w) {
+                    float v = row[w];
+                    if (WITH_ARGMAX) {
+                        if (v > best) {
+                            best = v;
+                            besti = h * a.W + w;
+                        }
+                    } else {
+                        best = v > best ? v : best;
+                    }
+                }
+            }
+            size_t o = ((size_t)s_roi[j] * a.C + c0) * PP + rem;
+            a.out[o] = best;
+            if (WITH_ARGMAX) a.argmax[o] = besti;
+        }
+    }
+}
+
+// Fallback for feature planes too large to stage: one thread per output, straight from global.
+template <bool WITH_ARGMAX>
+__global__ void roi_pool_direct_kernel(RoiArgs a) {
+    size_t total = (size_t)a.K * a.C * a.PH * a.PW;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+        int pw = o % a.PW, ph = (o / a.PW) % a.PH;
+        int c = (o / ((size_t)a.PW * a.PH)) % a.C;
+        int k = o / ((size_t)a.PW * a.PH * a.C);
+        const float* r = a.rois5 + (size_t)k * 5;
+        int b = (int)r[0];
+        float best = 0.f;
+        int besti = -1;
+        if (b >= 0 && b < a.B) {
+            int sw = round_half_away(r[1] * a.scale), sh = round_half_away(r[2] * a.scale);
+            int ew = round_half_away(r[3] * a.scale), eh = round_half_away(r[4] * a.scale);
+            int rw = max(ew - sw + 1, 1), rh = max(eh - sh + 1, 1);
+            float bh = (float)rh / (float)a.PH, bw = (float)rw / (float)a.PW;
+            int hs = min(max((int)floorf((float)ph * bh) + sh, 0), a.H);
+            int he = min(max((int)ceilf((float)(ph + 1) * bh) + sh, 0), a.H);
+            int ws = min(max((int)floorf((float)pw * bw) + sw, 0), a.W);
+            int we = min(max((int)ceilf((float)(pw + 1) * bw) + sw, 0), a.W);
+            bool empty = (he <= hs) || (we <= ws);
+            best = empty ? 0.f : -FLT_MAX;
+            const float* plane = a.feat + ((size_t)b * a.C + c) * a.H * a.W;
+            for (int h = hs; h < he; ++h)
+                for (int w = ws; w < we; ++w) {
+                    float v = __ldg(plane + h * a.W + w);
+                    if (v > best) {
+                        best = v;
+                        besti = h * a.W + w;
+                    }
+                }
+        }
+        a.out[o] = best;
+        if (WITH_ARGMAX) a.argmax[o] = besti;
+    }
+}
+
+__global__ void roi_pool_backward_kernel(const float* __restrict__ go, const int* __restrict__ argmax,
+                                         const float* __restrict__ rois5, size_t total, int C, int HW, int PP,
+                                         float* __restrict__ gi) {
+    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= total) return;
+    int am = __ldg(argmax + o);
+    if (am < 0) return;
+    size_t kc = o / PP;
+    int c = kc % C;
+    size_t k = kc / C;
+    int b = (int)__ldg(rois5 + k * 5);
+    atomicAdd(gi + ((size_t)b * C + c) * HW + am, __ldg(go + o));
+}
+
+// ---------------------------------------------------------------------------------------------
+// RoIAlign forward (torchvision roi_align)
+// ---------------------------------------------------------------------------------------------
+struct AlignRoi {
+    float sx, sy, bin_w, bin_h, count;
+    int gw, gh, k;
+};
+
+__device__ __forceinline__ AlignRoi make_align_roi(const float* r, int k, float scale, int PH, int PW,
+                                                   int sampling_ratio, int aligned) {
+    AlignRoi q;
+    float off = aligned ? 0.5f : 0.f;
+    q.sx = r[1] * scale - off;
+    q.sy = r[2] * scale - off;
+    float ex = r[3] * scale - off, ey = r[4] * scale - off;
+    float rw = ex - q.sx, rh = ey - q.sy;
+    if (!aligned) {
+        rw = fmaxf(rw, 1.f);
+        rh = fmaxf(rh, 1.f);
+    }
+    q.bin_h = rh / (float)PH;
+    q.bin_w = rw / (float)PW;
+    q.gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rh / (float)PH);
+    q.gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rw / (float)PW);
+    q.count = (float)max(q.gh * q.gw, 1);
+    q.k = k;
+    return q;
+}
+
+// one output element; `plane` may point to shared or global memory
+__device__ __forceinline__ float align_one(const float* plane, const AlignRoi& q, int ph, int pw, int H, int W) {
+    float acc = 0.f;
+    for (int iy = 0; iy < q.gh; ++iy) {
+        float yy = q.sy + (float)ph * q.bin_h;
+        yy = yy + ((float)iy + .5f) * q.bin_h / (float)q.gh;
+        for (int ix = 0; ix < q.gw; ++ix) {
+            float xx = q.sx + (float)pw * q.bin_w;
+            xx = xx + ((float)ix + .5f) * q.bin_w / (float)q.gw;
+            float y = yy, x = xx;
+            if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) continue;
+            if (y <= 0.f) y = 0.f;
+            if (x <= 0.f) x = 0.f;
+            int yl = (int)y, xl = (int)x, yh, xh;
+            if (yl >= H - 1) {
+                yh = yl = H - 1;
+                y = (float)yl;
+            } else {
+                yh = yl + 1;
+            }
+            if (xl >= W - 1) {
+                xh = xl = W - 1;
+                x = (float)xl;
+            } else {
+                xh = xl + 1;
+            }
+            float ly = y - (float)yl, lx = x - (float)xl;
+            float hy = 1.f - ly, hx = 1.f - lx;
+            float t = (hy * hx) * plane[yl * W + xl];
+            t = t + (hy * lx) * plane[yl * W + xh];
+            t = t + (ly * hx) * plane[yh * W + xl];
+            t = t + (ly * lx) * plane[yh * W + xh];
+            acc = acc + t;
+        }
+    }
+    return acc / q.count;
+}
+
+__global__ void __launch_bounds__(ROI_THREADS, 2) roi_align_staged_kernel(RoiArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ AlignRoi sq[ROI_NB];
+    float* sfeat = reinterpret_cast<float*>(smem_raw);
+    const int PH = a.PH, PW = a.PW, PP = PH * PW;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * a.CS;
+    const int cs = min(a.CS, a.C - c0);
+    const int HW = a.H * a.W;
+    const int r_begin = a.offs[b], r_end = a.offs[b + 1];
+    const int first = r_begin + blockIdx.x;
+    if (first >= r_end) return;
+    stage_slab(sfeat, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
+    const int per_roi = cs * PP;
+    for (int rb = first; rb < r_end; rb += a.groups * ROI_NB) {
+        int nb = 0;
+        for (int j = 0; j < ROI_NB; ++j)
+            if (rb + j * a.groups < r_end) nb = j + 1;
+        __syncthreads();
+        if (threadIdx.x < nb) {
+            int k = a.perm[rb + threadIdx.x * a.groups];
+            sq[threadIdx.x] = make_align_roi(a.rois5 + (size_t)k * 5, k, a.scale, PH, PW, a.sampling_ratio, a.aligned);
+        }
+        __syncthreads();
+        const int total = nb * per_roi;
+        for (int it = threadIdx.x; it < total; it += ROI_THREADS) {
+            int j = it / per_roi, rem = it - j * per_roi;
+            int c = rem / PP, bin = rem - c * PP;
+            int ph = bin / PW, pw = bin - ph * PW;
+            const AlignRoi q = sq[j];
+            a.out[((size_t)q.k * a.C + c0) * PP + rem] = align_one(sfeat + c * HW, q, ph, pw, a.H, a.W);
+        }
+    }
+}
+
+__global__ void roi_align_direct_kernel(RoiArgs a) {
+    size_t total = (size_t)a.K * a.C * a.PH * a.PW;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+        int pw = o % a.PW, ph = (o / a.PW) % a.PH;
+        int c = (o / ((size_t)a.PW * a.PH)) % a.C;
+        int k = o / ((size_t)a.PW * a.PH * a.C);
+        const float* r = a.rois5 + (size_t)k * 5;
+        int b = (int)r[0];
+        float v = 0.f;
+        if (b >= 0 && b < a.B) {
+            AlignRoi q = make_align_roi(r, k, a.scale, a.PH, a.PW, a.sampling_ratio, a.aligned);
+            v = align_one(a.feat + ((size_t)b * a.C + c) * a.H * a.W, q, ph, pw, a.H, a.W);
+        }
+        a.out[o] = v;
+    }
+}
+
+__global__ void roi_align_backward_kernel(const float* __restrict__ go, RoiArgs a, float* __restrict__ gi) {
+    size_t total = (size_t)a.K * a.C * a.PH * a.PW;
+    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= total) return;
+    int pw = o % a.PW, ph = (o / a.PW) % a.PH;
+    int c = (o / ((size_t)a.PW * a.PH)) % a.C;
+    int k = o / ((size_t)a.PW * a.PH * a.C);
+    const float* r = a.rois5 + (size_t)k * 5;
+    int b = (int)r[0];
+    if (b < 0 || b >= a.B) return;
+    AlignRoi q = make_align_roi(r, k, a.scale, a.PH, a.PW, a.sampling_ratio, a.aligned);
+    float g = __ldg(go + o) / q.count;
+    float* plane = gi + ((size_t)b * a.C + c) * a.H * a.W;
+    const int H = a.H, W = a.W;
+    for (int iy = 0; iy < q.gh; ++iy) {
+        float yy = q.sy + (float)ph * q.bin_h;
+        yy = yy + ((float)iy + .5f) * q.bin_h / (float)q.gh;
+        for (int ix = 0; ix < q.gw; ++ix) {
+            float xx = q.sx + (float)pw * q.bin_w;
+            xx = xx + ((float)ix + .5f) * q.bin_w / (float)q.gw;
+            float y = yy, x = xx;
+            if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) continue;
+            if (y <= 0.f) y = 0.f;
+            if (x <= 0.f) x = 0.f;
+            int yl = (int)y, xl = (int)x, yh, xh;
+            if (yl >= H - 1) {
+                yh = yl = H - 1;
+                y = (float)yl;
+            } else {
+                yh = yl + 1;
+            }
+            if (xl >= W - 1) {
+                xh = xl = W - 1;
+                x = (float)xl;
+            } else {
+                xh = xl + 1;
+            }
+            float ly = y - (float)yl, lx = x - (float)xl;
+            float hy = 1.f - ly, hx = 1.f - lx;
+            atomicAdd(plane + yl * W + xl, g * (hy * hx));
+            atomicAdd(plane + yl * W + xh, g * (hy * lx));
+            atomicAdd(plane + yh * W + xl, g * (ly * hx));
+            atomicAdd(plane + yh * W + xh, g * (ly * lx));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct RoiWs {
+    int* perm;
+    int* offs;
+};
+
+static size_t roi_layout(Workspace& ws, int batch, int num_rois, RoiWs* out) {
+    RoiWs w;
+    w.perm = ws.take<int>(num_rois > 0 ? num_rois : 1);
+    w.offs = ws.take<int>(batch + 1);
+    if (out) *out = w;
+    return ws.off;
+}
+
+constexpr size_t ROI_SMEM_TARGET = 100 * 1024;  // two CTAs per SM
+constexpr size_t ROI_SMEM_MAX = 200 * 1024;
+
+// channels per slab: largest power of two whose planes fit the shared-memory target
+static int pick_slab(int C, int HW) {
+    size_t plane = (size_t)HW * 4;
+    if (plane > ROI_SMEM_MAX) return 0;  // cannot stage
+    int cs = 1;
+    while (cs * 2 <= C && (size_t)(cs * 2) * plane <= ROI_SMEM_TARGET && cs * 2 <= 64) cs *= 2;
+    return cs;
+}
+
+static int pick_groups(int K, int B, int slabs) {
+    // enough CTAs for >= 4 waves of 2 CTAs/SM, but at least ~2*ROI_NB RoIs per CTA
+    int per_image = (K + B - 1) / B;
+    int g = (per_image + 2 * ROI_NB - 1) / (2 * ROI_NB);
+    int want = (8 * sm_count() + B * slabs - 1) / (B * slabs);
+    if (g > want) g = want;
+    if (g < 1) g = 1;
+    return g;
+}
+
+static int check_roi_common(const float* feat, int B, int C, int H, int W, const float* rois5, int K, int PH,
+                            int PW, const float* out, const char* who) {
+    FRCNN_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && K >= 0 && PH > 0 && PW > 0, "%s: bad shape", who);
+    FRCNN_CHECK_ARG(H < 32768 && W < 32768, "%s: feature map too large", who);
+    FRCNN_CHECK_ARG(K == 0 || (feat && rois5 && out), "%s: null pointer", who);
+    return FRCNN_OK;
+}
+
+template <typename KernelT>
+static int launch_staged(KernelT kernel, const RoiArgs& a, size_t smem, cudaStream_t stream) {
+    FRCNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int slabs = cdiv(a.C, a.CS);
+    FRCNN_CHECK_ARG(slabs <= 65535 && a.B <= 65535, "roi op: too many channel slabs / images");
+    dim3 grid(a.groups, slabs, a.B);
+    kernel<<<grid, ROI_THREADS, smem, stream>>>(a);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
+}  // namespace frcnn
+
+using namespace frcnn;
+
+extern "C" {
+
+int frcnn_roi_head_coords(const float* rois, const int32_t* roi_indices, int32_t n_images, int32_t per_image,
+                          float d0, float d1, int32_t fh, int32_t fw, float* rois5, frcnn_stream_t stream) {
+    FRCNN_CHECK_ARG(n_images >= 0 && per_image >= 0, "frcnn_roi_head_coords: bad shape");
+    int total = n_images * per_image;
+    if (total == 0) return FRCNN_OK;
+    FRCNN_CHECK_ARG(rois && roi_indices && rois5, "frcnn_roi_head_coords: null pointer");
+    roi_head_coords_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)rois, roi_indices, total, per_image, d0, d1, (float)fh, (float)fw, rois5);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
+size_t frcnn_roi_workspace_bytes(int32_t batch, int32_t num_rois) {
+    Workspace ws(nullptr, 0);
+    return roi_layout(ws, batch > 0 ? batch : 1, num_rois, nullptr);
+}
+
+static int roi_forward_common(bool align, const float* feat, int B, int C, int H, int W, const float* rois5,
+                              int K, int PH, int PW, float scale, int sampling_ratio, int aligned, float* out,
+                              int32_t* argmax, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                              const char* who) {
+    int rc = check_roi_common(feat, B, C, H, W, rois5, K, PH, PW, out, who);
+    if (rc) return rc;
+    if (K == 0) return FRCNN_OK;
+    RoiArgs a;
+    memset(&a, 0, sizeof(a));
+    a.feat = feat;
+    a.rois5 = rois5;
+    a.B = B;
+    a.C = C;
+    a.H = H;
+    a.W = W;
+    a.K = K;
+    a.PH = PH;
+    a.PW = PW;
+    a.scale = scale;
+    a.out = out;
+    a.argmax = argmax;
+    a.sampling_ratio = sampling_ratio;
+    a.aligned = aligned;
+    int cs = pick_slab(C, H * W);
+    bool staged = cs > 0 && PH <= ROI_MAX_P && PW <= ROI_MAX_P && B <= 4096;
+    if (!staged) {
+        size_t total = (size_t)K * C * PH * PW;
+        int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 32);
+        if (align) roi_align_direct_kernel<<<blocks, 256, 0, stream>>>(a);
+        else if (argmax) roi_pool_direct_kernel<true><<<blocks, 256, 0, stream>>>(a);
+        else roi_pool_direct_kernel<false><<<blocks, 256, 0, stream>>>(a);
+        FRCNN_LAUNCH_CHECK();
+        return FRCNN_OK;
+    }
+    Workspace ws(workspace, workspace_bytes);
+    RoiWs w;
+    roi_layout(ws, B, K, &w);
+    if (!ws.ok()) {
+        set_error("%s: workspace too small or misaligned (%zu needed, %zu given)", who, ws.off, workspace_bytes);
+        return FRCNN_ERR_WORKSPACE;
+    }
+    roi_bucket_kernel<<<1, BUCKET_THREADS, 2 * B * sizeof(int), stream>>>(rois5, K, B, w.perm, w.offs);
+    FRCNN_LAUNCH_CHECK();
+    a.perm = w.perm;
+    a.offs = w.offs;
+    a.CS = cs;
+    a.groups = pick_groups(K, B, cdiv(C, cs));
+    size_t smem = (size_t)cs * H * W * 4;
+    if (align) return launch_staged(roi_align_staged_kernel, a, smem, stream);
+    if (PH == PW && PH == 7)
+        return argmax ? launch_staged(roi_pool_staged_kernel<7, true>, a, smem, stream)
+                      : launch_staged(roi_pool_staged_kernel<7, false>, a, smem, stream);
+    if (PH == PW && PH == 14)
+        return argmax ? launch_staged(roi_pool_staged_kernel<14, true>, a, smem, stream)
+                      : launch_staged(roi_pool_staged_kernel<14, false>, a, smem, stream);
+    return argmax ? launch_staged(roi_pool_staged_kernel<0, true>, a, smem, stream)
+                  : launch_staged(roi_pool_staged_kernel<0, false>, a, smem, stream);
+}
+
+int frcnn_roi_pool_forward(const float* feat, int32_t B, int32_t C, int32_t H, int32_t W, const float* rois5,
+                           int32_t K, int32_t PH, int32_t PW, float scale, float* out, int32_t* argmax,
+                           void* workspace, size_t workspace_bytes, frcnn_stream_t stream) {
+    return roi_forward_common(false, feat, B, C, H, W, rois5, K, PH, PW, scale, 0, 0, out, argmax, workspace,
+                              workspace_bytes, (cudaStream_t)stream, "frcnn_roi_pool_forward");
+}
+
+int frcnn_roi_align_forward(const float* feat, int32_t B, int32_t C, int32_t H, int32_t W, const float* rois5,
+                            int32_t K, int32_t PH, int32_t PW, float scale, int32_t sampling_ratio,
+                            int32_t aligned, float* out, void* workspace, size_t workspace_bytes,
+                            frcnn_stream_t stream) {
+    return roi_forward_common(true, feat, B, C, H, W, rois5, K, PH, PW, scale, sampling_ratio, aligned, out,
+                              nullptr, workspace, workspace_bytes, (cudaStream_t)stream, "frcnn_roi_align_forward");
+}
+
+int frcnn_roi_pool_backward(const float* grad_out, const int32_t* argmax, const float* rois5, int32_t K,
+                            int32_t C, int32_t H, int32_t W, int32_t PH, int32_t PW, float* grad_in,
+                            frcnn_stream_t stream) {
+    FRCNN_CHECK_ARG(K >= 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0, "frcnn_roi_pool_backward: bad shape");
+    if (K == 0) return FRCNN_OK;
+    FRCNN_CHECK_ARG(grad_out && argmax && rois5 && grad_in, "frcnn_roi_pool_backward: null pointer");
+    size_t total = (size_t)K * C * PH * PW;
+    roi_pool_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        grad_out, argmax, rois5, total, C, H * W, PH * PW, grad_in);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
+int frcnn_roi_align_backward(const float* grad_out, const float* rois5, int32_t K, int32_t C, int32_t H,
+                             int32_t W, int32_t PH, int32_t PW, float scale, int32_t sampling_ratio,
+                             int32_t aligned, float* grad_in, frcnn_stream_t stream) {
+    FRCNN_CHECK_ARG(K >= 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0, "frcnn_roi_align_backward: bad shape");
+    if (K == 0) return FRCNN_OK;
+    FRCNN_CHECK_ARG(grad_out && rois5 && grad_in, "frcnn_roi_align_backward: null pointer");
+    RoiArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rois5 = rois5;
+    a.B = 1 << 30;
+    a.C = C;
+    a.H = H;
+    a.W = W;
+    a.K = K;
+    a.PH = PH;
+    a.PW = PW;
+    a.scale = scale;
+    a.sampling_ratio = sampling_ratio;
+    a.aligned = aligned;
+    size_t total = (size_t)K * C * PH * PW;
+    roi_align_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grad_out, a,
+                                                                                                  grad_in);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+"""Drop-in for the reference's nets/classify.py: the RoI head.  The RoI -> feature-map coordinate map
+and the RoIPool / RoIAlign gather run in csrc/roi_ops.cu; the classifier module and the two Linear
+layers stay PyTorch, with the reference's parameter names (``cls_loc``, ``score``)."""
+from __future__ import annotations
+
+from torch import nn
+
+from .. import functional as F
+
+
+class RoIPool(nn.Module):
+    """torchvision.ops.RoIPool stand-in (nets/classify.py:4,17): (input [B,C,H,W], rois [K,5])."""
+
+    def __init__(self, output_size, spatial_scale):
+        super().__init__()
+        self.output_size = output_size
+        self.spatial_scale = spatial_scale
+
+    def forward(self, input, rois):
+        return F.roi_pool(input, rois, self.output_size, self.spatial_scale)
+
+
+class RoIAlign(nn.Module):
+    """torchvision.ops.RoIAlign stand-in (the BASELINE RoIAlign 7x7 configuration)."""
+
+    def __init__(self, output_size, spatial_scale, sampling_ratio=-1, aligned=False):
+        super().__init__()
+        self.output_size = output_size
+        self.spatial_scale = spatial_scale
+        self.sampling_ratio = sampling_ratio
+        self.aligned = aligned
+
+    def forward(self, input, rois):
+        return F.roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio, self.aligned)
+
+
+class HarNetRoIHead(nn.Module):
+    """nets/classify.py:8-56.  forward(x [n,C,H,W], rois [n,R,4], roi_indices [n], img_size) ->
+    (roi_cls_locs [n,R,4*n_class], roi_scores [n,R,n_class]).
+
+    Differences from the reference, all opt-in or supersets: any R per image (the reference
+    hard-codes 128 in an expand), ``in_features`` other than 512, and ``roi_op="align"``."""
+
+    def __init__(self, n_class, roi_size, spatial_scale, classifier, in_features=512, roi_op="pool",
+                 sampling_ratio=-1, aligned=False):
+        super().__init__()
+        self.classifier = classifier
+        self.cls_loc = nn.Linear(in_features, n_class * 4)
+        self.score = nn.Linear(in_features, n_class)
+        if roi_op == "pool":
+            self.roi = RoIPool((roi_size, roi_size), spatial_scale)
+        elif roi_op == "align":
+            self.roi = RoIAlign((roi_size, roi_size), spatial_scale, sampling_ratio, aligned)
+        else:
+            raise ValueError("roi_op must be 'pool' or 'align'")
+
+    def gather(self, x, rois, roi_indices, img_size):
+        """The hot part: coordinate map + index concat + RoI gather -> [n*R, C, P, P]."""
+        indices_and_rois = F.roi_head_coords(rois.view(x.shape[0], -1, 4), roi_indices, img_size,
+                                             (x.size()[2], x.size()[3]))
+        return self.roi(x, indices_and_rois)
+
+    def forward(self, x, rois, roi_indices, img_size):
+        n = x.shape[0]
+        pool = self.gather(x, rois, roi_indices, img_size)
+        fc7 = self.classifier(pool)
+        roi_cls_locs = self.cls_loc(fc7)
+        roi_scores = self.score(fc7)
+        roi_cls_locs = roi_cls_locs.view(n, -1, roi_cls_locs.size(1))
+        roi_scores = roi_scores.view(n, -1, roi_scores.size(1))
+        return roi_cls_locs, roi_scores
