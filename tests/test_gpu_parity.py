@@ -379,6 +379,8 @@ def test_roi_head_dropin(F):
 def test_rpn_forward_dropin(F):
     from two_stage_object_detection_b200.nets import ProposalCreator, RegionProposalNetwork
     g = load_golden("rpn_forward")
+    torch.backends.cudnn.allow_tf32 = False  # the golden conv outputs are fp32 (CPU)
+    torch.backends.cuda.matmul.allow_tf32 = False
     rpn = RegionProposalNetwork(in_channels=16, mode="test").to(DEV)
     rpn.proposal_layer = ProposalCreator("test", n_test_pre_nms=500, n_test_post_nms=40)
     with torch.no_grad():

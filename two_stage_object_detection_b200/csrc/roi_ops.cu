@@ -243,6 +243,153 @@ __global__ void __launch_bounds__(ROI_THREADS, 2) roi_pool_staged_kernel(RoiArgs
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// RoIPool forward, table kernel (inference: no argmax).
+//
+// A bin's max over [hs,he) x [ws,we) is the max of four lookups into 2-D "sparse max tables":
+//   T[a][b][y][x] = max of the a x b window anchored at (y,x),  a,b in {1,2}
+// because any window up to 4 x 4 is covered by the (at most) four a x b windows placed in its corners
+// (max is idempotent, overlaps do not matter).  The CTA builds the four tables once for its 4-channel
+// slab -- channel-interleaved, one float4 per pixel, so one LDS.128 serves four channels -- and then
+// every bin costs 4 LDS.128 + 12 FMNMX instead of a data-dependent double loop.  RoIs with a bin
+// larger than 4 in either direction take a loop path over T[1][1].  Values are first clamped with
+// fmaxf(v, -FLT_MAX), which reproduces the reference's `v > best` scan exactly (NaN / -inf never win).
+//
+// smem: 4 tables x HWp float4 (HW=38x38: 92 KB, two CTAs per SM).  The raw NCHW planes are TMA-staged
+// into the region that later holds T[2][2], the last table built.
+// Thread mapping: LPW (16 or 8) consecutive lanes serve one RoI, lane = output column pw; each thread
+// walks the P output rows for all four channels.
+// ---------------------------------------------------------------------------------------------
+constexpr int TAB_THREADS = 512;
+constexpr int TAB_WARPS = TAB_THREADS / 32;
+constexpr int TAB_CS = 4;
+
+__device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
+    return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
+template <int P>
+__global__ void __launch_bounds__(TAB_THREADS, 2) roi_pool_tab_kernel(RoiArgs a) {
+    constexpr int LPW = P <= 8 ? 8 : 16;  // lanes per RoI
+    constexpr int GPW = 32 / LPW;         // RoIs per warp
+    constexpr int PP = P * P;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int2 s_th[TAB_WARPS][GPW][16];  // per output row: table offsets of the two corner rows
+    __shared__ int s_hh[TAB_WARPS][GPW][16];   // per output row: hstart | hend << 16 (loop path)
+    float4* tab = reinterpret_cast<float4*>(smem_raw);
+    const int H = a.H, W = a.W, HW = H * W, HWp = (HW + 3) & ~3;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * TAB_CS;
+    const int cs = min(TAB_CS, a.C - c0);
+    const int r_begin = a.offs[b], r_end = a.offs[b + 1];
+    const int slot0 = blockIdx.x * (TAB_WARPS * GPW);
+    if (r_begin + slot0 >= r_end) return;
+    const int tid = threadIdx.x;
+
+    float* raw = reinterpret_cast<float*>(tab + 3 * HWp);  // [cs][HW], lives where T22 will be
+    stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
+    for (int p = tid; p < HW; p += TAB_THREADS) {
+        float4 v;
+        v.x = fmaxf(raw[p], -FLT_MAX);
+        v.y = cs > 1 ? fmaxf(raw[HW + p], -FLT_MAX) : -FLT_MAX;
+        v.z = cs > 2 ? fmaxf(raw[2 * HW + p], -FLT_MAX) : -FLT_MAX;
+        v.w = cs > 3 ? fmaxf(raw[3 * HW + p], -FLT_MAX) : -FLT_MAX;
+        tab[p] = v;
+    }
+    __syncthreads();
+    for (int p = tid; p < HW; p += TAB_THREADS) {
+        int y = p / W, x = p - y * W;
+        int pr = x + 1 < W ? p + 1 : p, pd = y + 1 < H ? p + W : p;
+        float4 v = tab[p];
+        tab[HWp + p] = max4(v, tab[pr]);      // 1 x 2
+        tab[2 * HWp + p] = max4(v, tab[pd]);  // 2 x 1
+    }
+    __syncthreads();
+    for (int p = tid; p < HW; p += TAB_THREADS) {
+        int y = p / W;
+        int pd = y + 1 < H ? p + W : p;
+        tab[3 * HWp + p] = max4(tab[HWp + p], tab[HWp + pd]);  // 2 x 2
+    }
+    __syncthreads();
+
+    const int warp = tid >> 5, lane = tid & 31, grp = lane / LPW, pw = lane % LPW;
+    const bool active = pw < P;
+    const int pi = active ? pw : P - 1;
+    const unsigned gmask = (LPW == 16 ? 0xFFFFu : 0xFFu) << (grp * LPW);
+    const int stride = a.groups * TAB_WARPS * GPW;
+    for (int r = r_begin + slot0 + warp * GPW + grp;; r += stride) {
+        const bool has = r < r_end;
+        if (!__any_sync(0xFFFFFFFFu, has)) break;
+        const int k = has ? a.perm[r] : a.perm[r_begin];
+        const float* rp = a.rois5 + (size_t)k * 5;
+        const int sw = round_half_away(__ldg(rp + 1) * a.scale), sh = round_half_away(__ldg(rp + 2) * a.scale);
+        const int ew = round_half_away(__ldg(rp + 3) * a.scale), eh = round_half_away(__ldg(rp + 4) * a.scale);
+        const float bw = (float)max(ew - sw + 1, 1) / (float)P, bh = (float)max(eh - sh + 1, 1) / (float)P;
+        const int ws = min(max((int)floorf((float)pi * bw) + sw, 0), W);
+        const int we = min(max((int)ceilf((float)(pi + 1) * bw) + sw, 0), W);
+        const int hs = min(max((int)floorf((float)pi * bh) + sh, 0), H);
+        const int he = min(max((int)ceilf((float)(pi + 1) * bh) + sh, 0), H);
+        const int wlen = we - ws, hlen = he - hs;
+        // RoIs with a bin larger than 4 or an empty bin (RoI partly outside the map) take the loop path
+        const unsigned odd = __ballot_sync(0xFFFFFFFFu, has && (wlen > 4 || hlen > 4 || wlen <= 0 || hlen <= 0));
+        const bool loop_path = (odd & gmask) != 0;
+        if (active) {
+            const int aa = min(max(hlen, 1), 2);
+            // byte offsets of the two corner rows inside table T[aa][.]
+            s_th[warp][grp][pw] = make_int2(((aa - 1) * 2 * HWp + hs * W) * 16, ((aa - 1) * 2 * HWp + (he - aa) * W) * 16);
+            s_hh[warp][grp][pw] = hs | (he << 16);
+        }
+        __syncwarp();
+        const bool wempty = wlen <= 0;
+        const int bb = min(max(wlen, 1), 2);
+        const int ix1 = ((bb - 1) * HWp + ws) * 16;
+        const int ix2 = ((bb - 1) * HWp + (we - bb)) * 16;
+        float* ob = a.out + ((size_t)k * a.C + c0) * PP + pw;
+        if (has && active) {
+            if (!loop_path) {
+                const unsigned char* t1 = smem_raw + ix1;
+                const unsigned char* t2 = smem_raw + ix2;
+#pragma unroll
+                for (int ph = 0; ph < P; ++ph) {
+                    const int2 t = s_th[warp][grp][ph];
+                    const float4 v = max4(max4(*reinterpret_cast<const float4*>(t1 + t.x),
+                                               *reinterpret_cast<const float4*>(t2 + t.x)),
+                                          max4(*reinterpret_cast<const float4*>(t1 + t.y),
+                                               *reinterpret_cast<const float4*>(t2 + t.y)));
+                    float* o = ob + ph * P;
+                    if (cs == TAB_CS) {
+                        o[0] = v.x;
+                        o[PP] = v.y;
+                        o[2 * PP] = v.z;
+                        o[3 * PP] = v.w;
+                    } else {
+                        o[0] = v.x;
+                        if (cs > 1) o[PP] = v.y;
+                        if (cs > 2) o[2 * PP] = v.z;
+                    }
+                }
+            } else {
+                for (int ph = 0; ph < P; ++ph) {
+                    const int hh = s_hh[warp][grp][ph];
+                    const int hs2 = hh & 0xFFFF, he2 = hh >> 16;
+                    const bool empty = (he2 <= hs2) || wempty;
+                    float4 v = empty ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                     : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+                    for (int h = hs2; h < he2; ++h)
+                        for (int w = ws; w < we; ++w) v = max4(v, tab[h * W + w]);
+                    float* o = ob + ph * P;
+                    o[0] = v.x;
+                    if (cs > 1) o[PP] = v.y;
+                    if (cs > 2) o[2 * PP] = v.z;
+                    if (cs > 3) o[3 * PP] = v.w;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Fallback for feature planes too large to stage: one thread per output, straight from global.
 template <bool WITH_ARGMAX>
 __global__ void roi_pool_direct_kernel(RoiArgs a) {
@@ -519,6 +666,17 @@ static int launch_staged(KernelT kernel, const RoiArgs& a, size_t smem, cudaStre
     return FRCNN_OK;
 }
 
+template <typename KernelT>
+static int launch_tab(KernelT kernel, const RoiArgs& a, size_t smem, cudaStream_t stream) {
+    FRCNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int slabs = cdiv(a.C, TAB_CS);
+    FRCNN_CHECK_ARG(slabs <= 65535 && a.B <= 65535, "roi op: too many channel slabs / images");
+    dim3 grid(a.groups, slabs, a.B);
+    kernel<<<grid, TAB_THREADS, smem, stream>>>(a);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
 }  // namespace frcnn
 
 using namespace frcnn;
@@ -591,6 +749,19 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
     a.groups = pick_groups(K, B, cdiv(C, cs));
     size_t smem = (size_t)cs * H * W * 4;
     if (align) return launch_staged(roi_align_staged_kernel, a, smem, stream);
+    // inference RoIPool: sparse max-table kernel when the four tables of a 4-channel slab fit
+    size_t tab_smem = (size_t)4 * ((H * W + 3) & ~3) * sizeof(float4);
+    if (!argmax && PH == PW && (PH == 7 || PH == 14) && tab_smem <= ROI_SMEM_MAX) {
+        a.CS = TAB_CS;
+        int per_pass = TAB_WARPS * (PH <= 8 ? 4 : 2);
+        int slabs = cdiv(C, TAB_CS);
+        int per_image = cdiv(K, B);
+        int g = cdiv(per_image, 4 * per_pass);  // >= 4 passes per CTA amortise the table build
+        int want = cdiv(8 * sm_count(), B * slabs);
+        a.groups = std::max(1, std::min(g, want));
+        return PH == 7 ? launch_tab(roi_pool_tab_kernel<7>, a, tab_smem, stream)
+                       : launch_tab(roi_pool_tab_kernel<14>, a, tab_smem, stream);
+    }
     if (PH == PW && PH == 7)
         return argmax ? launch_staged(roi_pool_staged_kernel<7, true>, a, smem, stream)
                       : launch_staged(roi_pool_staged_kernel<7, false>, a, smem, stream);
