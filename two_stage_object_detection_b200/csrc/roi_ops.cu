@@ -8,6 +8,7 @@
 // RoI.  Features are read from L2/HBM once per (slab, group); the dominant HBM traffic is the
 // K*C*P*P*4 B output write.
 #include <float.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -250,42 +251,93 @@ __global__ void __launch_bounds__(ROI_THREADS, 2) roi_pool_staged_kernel(RoiArgs
 //   T[a][b][y][x] = max of the a x b window anchored at (y,x),  a,b in {1,2}
 // because any window up to 4 x 4 is covered by the (at most) four a x b windows placed in its corners
 // (max is idempotent, overlaps do not matter).  The CTA builds the four tables once for its 4-channel
-// slab -- channel-interleaved, one float4 per pixel, so one LDS.128 serves four channels -- and then
-// every bin costs 4 LDS.128 + 12 FMNMX instead of a data-dependent double loop.  RoIs with a bin
-// larger than 4 in either direction take a loop path over T[1][1].  Values are first clamped with
-// fmaxf(v, -FLT_MAX), which reproduces the reference's `v > best` scan exactly (NaN / -inf never win).
+// slab -- channel-interleaved, one float4 per pixel, so one LDS.128 serves four channels -- and then a
+// bin costs 1-4 LDS.128 + FMNMX instead of a data-dependent double loop.  Bins larger than 4 in either
+// direction take a loop path over T[1][1].  Values are first clamped with fmaxf(v, -FLT_MAX), which
+// reproduces the reference's `v > best` scan exactly (NaN / -inf never win); empty bins give 0.
 //
 // smem: 4 tables x HWp float4 (HW=38x38: 92 KB, two CTAs per SM).  The raw NCHW planes are TMA-staged
 // into the region that later holds T[2][2], the last table built.
-// Thread mapping: LPW (16 or 8) consecutive lanes serve one RoI, lane = output column pw; each thread
-// walks the P output rows for all four channels.
+//
+// Thread mapping: TAB_THREADS = 784 = 4 * 14*14 = 16 * 7*7.  A thread owns ONE output bin (ph,pw) for
+// good and walks the CTA's RoIs; consecutive threads are consecutive bins of the same RoI, so every
+// warp-level store is a contiguous 128-byte run of the [K,C,P,P] output (measured: the store pattern,
+// not the lookups, bounds this kernel).  Per-RoI bin geometry is precomputed for a batch of RoIs into
+// shared-memory tables (one entry per thread), and the next batch's RoI boxes are prefetched.
 // ---------------------------------------------------------------------------------------------
-constexpr int TAB_THREADS = 512;
-constexpr int TAB_WARPS = TAB_THREADS / 32;
 constexpr int TAB_CS = 4;
+constexpr int TAB_NE_BIT = 0x80000000;   // entry .y bit 31: bin row / column is non-empty
+constexpr int TAB_BIG_BIT = 0x40000000;  // entry .y bit 30: longer than 4 -> loop path
+constexpr int TAB_OFF_MASK = 0x3FFFFFFF;
 
 __device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
     return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
 
-template <int P>
+struct RoiBox {
+    int k;
+    float x1, y1, x2, y2;
+};
+
+__device__ __forceinline__ RoiBox load_roi(const RoiArgs& a, int r, int r_end) {
+    RoiBox q;
+    q.k = -1;
+    q.x1 = q.y1 = q.x2 = q.y2 = 0.f;
+    if (r < r_end) {
+        q.k = a.perm[r];
+        const float* rp = a.rois5 + (size_t)q.k * 5;
+        q.x1 = __ldg(rp + 1);
+        q.y1 = __ldg(rp + 2);
+        q.x2 = __ldg(rp + 3);
+        q.y2 = __ldg(rp + 4);
+    }
+    return q;
+}
+
+// One axis of the bin grid: [lo,hi) of bin `i`, as (offset of first corner, offset of second corner
+// | flags); `unit` = table elements per step along this axis (W for rows, 1 for columns), `tsel` =
+// table stride selected by a 2-long window along this axis.
+__device__ __forceinline__ int2 tab_entry(int i, int P, float c1, float c2, float scale, int limit, int unit,
+                                          int tsel, int* raw) {
+    const int s = round_half_away(c1 * scale), e = round_half_away(c2 * scale);
+    const float bin = (float)max(e - s + 1, 1) / (float)P;
+    const int lo = min(max((int)floorf((float)i * bin) + s, 0), limit);
+    const int hi = min(max((int)ceilf((float)(i + 1) * bin) + s, 0), limit);
+    const int len = hi - lo;
+    *raw = lo | (hi << 16);
+    const bool empty = len <= 0;
+    const int a = min(max(len, 1), 2);
+    const int lo_ = empty ? 0 : lo, hi_ = empty ? a : hi;
+    int2 r;
+    r.x = ((a - 1) * tsel + lo_ * unit) * 16;
+    r.y = (((a - 1) * tsel + (hi_ - a) * unit) * 16) | (empty ? 0 : TAB_NE_BIT) | (len > 4 ? TAB_BIG_BIT : 0);
+    return r;
+}
+
+template <int P, int TAB_THREADS>
 __global__ void __launch_bounds__(TAB_THREADS, 2) roi_pool_tab_kernel(RoiArgs a) {
-    constexpr int LPW = P <= 8 ? 8 : 16;  // lanes per RoI
-    constexpr int GPW = 32 / LPW;         // RoIs per warp
-    constexpr int PP = P * P;
+    constexpr int BINS = P * P;
+    constexpr int RPI = TAB_THREADS / BINS;      // RoIs per iteration (4 or 16)
+    constexpr int NB = TAB_THREADS / (2 * P);    // RoIs per batch: one table entry per thread (28 or 56)
+    static_assert(RPI * BINS == TAB_THREADS && NB * 2 * P == TAB_THREADS, "thread mapping");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int2 s_th[TAB_WARPS][GPW][16];  // per output row: table offsets of the two corner rows
-    __shared__ int s_hh[TAB_WARPS][GPW][16];   // per output row: hstart | hend << 16 (loop path)
+    __shared__ int2 s_th[NB][P], s_tw[NB][P];  // per RoI: row / column corner offsets + flags
+    __shared__ int s_hraw[NB][P], s_wraw[NB][P];
+    __shared__ int s_k[NB];
     float4* tab = reinterpret_cast<float4*>(smem_raw);
     const int H = a.H, W = a.W, HW = H * W, HWp = (HW + 3) & ~3;
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * TAB_CS;
     const int cs = min(TAB_CS, a.C - c0);
     const int r_begin = a.offs[b], r_end = a.offs[b + 1];
-    const int slot0 = blockIdx.x * (TAB_WARPS * GPW);
-    if (r_begin + slot0 >= r_end) return;
+    const int stride = a.groups * NB;
+    int r0 = r_begin + blockIdx.x * NB;  // first RoI of this CTA's current batch
+    if (r0 >= r_end) return;
     const int tid = threadIdx.x;
+    // table-entry role: RoI tj of the batch, axis entry ti (rows first, then columns)
+    const int tj = tid / (2 * P), ti = tid % (2 * P);
+    RoiBox nxt = load_roi(a, r0 + tj, r_end);  // in flight while the tables are built
 
     float* raw = reinterpret_cast<float*>(tab + 3 * HWp);  // [cs][HW], lives where T22 will be
     stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
@@ -311,82 +363,51 @@ __global__ void __launch_bounds__(TAB_THREADS, 2) roi_pool_tab_kernel(RoiArgs a)
         int pd = y + 1 < H ? p + W : p;
         tab[3 * HWp + p] = max4(tab[HWp + p], tab[HWp + pd]);  // 2 x 2
     }
-    __syncthreads();
 
-    const int warp = tid >> 5, lane = tid & 31, grp = lane / LPW, pw = lane % LPW;
-    const bool active = pw < P;
-    const int pi = active ? pw : P - 1;
-    const unsigned gmask = (LPW == 16 ? 0xFFFFu : 0xFFu) << (grp * LPW);
-    const int stride = a.groups * TAB_WARPS * GPW;
-    for (int r = r_begin + slot0 + warp * GPW + grp;; r += stride) {
-        const bool has = r < r_end;
-        if (!__any_sync(0xFFFFFFFFu, has)) break;
-        const int k = has ? a.perm[r] : a.perm[r_begin];
-        const float* rp = a.rois5 + (size_t)k * 5;
-        const int sw = round_half_away(__ldg(rp + 1) * a.scale), sh = round_half_away(__ldg(rp + 2) * a.scale);
-        const int ew = round_half_away(__ldg(rp + 3) * a.scale), eh = round_half_away(__ldg(rp + 4) * a.scale);
-        const float bw = (float)max(ew - sw + 1, 1) / (float)P, bh = (float)max(eh - sh + 1, 1) / (float)P;
-        const int ws = min(max((int)floorf((float)pi * bw) + sw, 0), W);
-        const int we = min(max((int)ceilf((float)(pi + 1) * bw) + sw, 0), W);
-        const int hs = min(max((int)floorf((float)pi * bh) + sh, 0), H);
-        const int he = min(max((int)ceilf((float)(pi + 1) * bh) + sh, 0), H);
-        const int wlen = we - ws, hlen = he - hs;
-        // RoIs with a bin larger than 4 or an empty bin (RoI partly outside the map) take the loop path
-        const unsigned odd = __ballot_sync(0xFFFFFFFFu, has && (wlen > 4 || hlen > 4 || wlen <= 0 || hlen <= 0));
-        const bool loop_path = (odd & gmask) != 0;
-        if (active) {
-            const int aa = min(max(hlen, 1), 2);
-            // byte offsets of the two corner rows inside table T[aa][.]
-            s_th[warp][grp][pw] = make_int2(((aa - 1) * 2 * HWp + hs * W) * 16, ((aa - 1) * 2 * HWp + (he - aa) * W) * 16);
-            s_hh[warp][grp][pw] = hs | (he << 16);
-        }
-        __syncwarp();
-        const bool wempty = wlen <= 0;
-        const int bb = min(max(wlen, 1), 2);
-        const int ix1 = ((bb - 1) * HWp + ws) * 16;
-        const int ix2 = ((bb - 1) * HWp + (we - bb)) * 16;
-        float* ob = a.out + ((size_t)k * a.C + c0) * PP + pw;
-        if (has && active) {
-            if (!loop_path) {
-                const unsigned char* t1 = smem_raw + ix1;
-                const unsigned char* t2 = smem_raw + ix2;
-#pragma unroll
-                for (int ph = 0; ph < P; ++ph) {
-                    const int2 t = s_th[warp][grp][ph];
-                    const float4 v = max4(max4(*reinterpret_cast<const float4*>(t1 + t.x),
-                                               *reinterpret_cast<const float4*>(t2 + t.x)),
-                                          max4(*reinterpret_cast<const float4*>(t1 + t.y),
-                                               *reinterpret_cast<const float4*>(t2 + t.y)));
-                    float* o = ob + ph * P;
-                    if (cs == TAB_CS) {
-                        o[0] = v.x;
-                        o[PP] = v.y;
-                        o[2 * PP] = v.z;
-                        o[3 * PP] = v.w;
-                    } else {
-                        o[0] = v.x;
-                        if (cs > 1) o[PP] = v.y;
-                        if (cs > 2) o[2 * PP] = v.z;
-                    }
+    // compute role: bin e = (ph,pw) of the (tid / BINS)-th RoI of each iteration
+    const int e = tid % BINS, ej = tid / BINS;
+    const int ph = e / P, pw = e % P;
+    for (; r0 < r_end; r0 += stride) {
+        const RoiBox q = nxt;
+        __syncthreads();  // previous batch's table reads (and, first time, the T22 build) are done
+        if (ti < P) s_th[tj][ti] = tab_entry(ti, P, q.y1, q.y2, a.scale, H, W, 2 * HWp, &s_hraw[tj][ti]);
+        else s_tw[tj][ti - P] = tab_entry(ti - P, P, q.x1, q.x2, a.scale, W, 1, HWp, &s_wraw[tj][ti - P]);
+        if (ti == 0) s_k[tj] = q.k;
+        nxt = load_roi(a, r0 + stride + tj, r_end);  // prefetch the next batch's boxes
+        __syncthreads();
+        const int nb = min(NB, r_end - r0);
+#pragma unroll 2
+        for (int j = ej; j < nb; j += RPI) {
+            const int2 h = s_th[j][ph], w = s_tw[j][pw];
+            const int flags = h.y & w.y;
+            const bool big = ((h.y | w.y) & TAB_BIG_BIT) != 0;
+            const int hy = h.y & TAB_OFF_MASK, wy = w.y & TAB_OFF_MASK;
+            const unsigned char* t1 = smem_raw + w.x;
+            const unsigned char* t2 = smem_raw + wy;
+            float4 v;
+            if (!big) {
+                // lookups that coincide are skipped when no lane of the warp needs them
+                const bool wide = __any_sync(__activemask(), w.x != wy);
+                const bool tall = __any_sync(__activemask(), h.x != hy);
+                v = *reinterpret_cast<const float4*>(t1 + h.x);
+                if (wide) v = max4(v, *reinterpret_cast<const float4*>(t2 + h.x));
+                if (tall) {
+                    v = max4(v, *reinterpret_cast<const float4*>(t1 + hy));
+                    if (wide) v = max4(v, *reinterpret_cast<const float4*>(t2 + hy));
                 }
             } else {
-                for (int ph = 0; ph < P; ++ph) {
-                    const int hh = s_hh[warp][grp][ph];
-                    const int hs2 = hh & 0xFFFF, he2 = hh >> 16;
-                    const bool empty = (he2 <= hs2) || wempty;
-                    float4 v = empty ? make_float4(0.f, 0.f, 0.f, 0.f)
-                                     : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-                    for (int h = hs2; h < he2; ++h)
-                        for (int w = ws; w < we; ++w) v = max4(v, tab[h * W + w]);
-                    float* o = ob + ph * P;
-                    o[0] = v.x;
-                    if (cs > 1) o[PP] = v.y;
-                    if (cs > 2) o[2 * PP] = v.z;
-                    if (cs > 3) o[3 * PP] = v.w;
-                }
+                const int hr = s_hraw[j][ph], wr = s_wraw[j][pw];
+                v = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+                for (int y = hr & 0xFFFF; y < (hr >> 16); ++y)
+                    for (int x = wr & 0xFFFF; x < (wr >> 16); ++x) v = max4(v, tab[y * W + x]);
             }
+            const unsigned m = (unsigned)(flags >> 31);  // all ones iff the bin is non-empty
+            float* o = a.out + ((size_t)s_k[j] * a.C + c0) * BINS + e;
+            o[0] = __uint_as_float(__float_as_uint(v.x) & m);
+            if (cs > 1) o[BINS] = __uint_as_float(__float_as_uint(v.y) & m);
+            if (cs > 2) o[2 * BINS] = __uint_as_float(__float_as_uint(v.z) & m);
+            if (cs > 3) o[3 * BINS] = __uint_as_float(__float_as_uint(v.w) & m);
         }
-        __syncwarp();
     }
 }
 
@@ -667,12 +688,12 @@ static int launch_staged(KernelT kernel, const RoiArgs& a, size_t smem, cudaStre
 }
 
 template <typename KernelT>
-static int launch_tab(KernelT kernel, const RoiArgs& a, size_t smem, cudaStream_t stream) {
+static int launch_tab(KernelT kernel, const RoiArgs& a, size_t smem, int threads, cudaStream_t stream) {
     FRCNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int slabs = cdiv(a.C, TAB_CS);
     FRCNN_CHECK_ARG(slabs <= 65535 && a.B <= 65535, "roi op: too many channel slabs / images");
     dim3 grid(a.groups, slabs, a.B);
-    kernel<<<grid, TAB_THREADS, smem, stream>>>(a);
+    kernel<<<grid, threads, smem, stream>>>(a);
     FRCNN_LAUNCH_CHECK();
     return FRCNN_OK;
 }
@@ -753,14 +774,17 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
     size_t tab_smem = (size_t)4 * ((H * W + 3) & ~3) * sizeof(float4);
     if (!argmax && PH == PW && (PH == 7 || PH == 14) && tab_smem <= ROI_SMEM_MAX) {
         a.CS = TAB_CS;
-        int per_pass = TAB_WARPS * (PH <= 8 ? 4 : 2);
+        static int tab_threads = getenv("FRCNN_TAB_THREADS") ? atoi(getenv("FRCNN_TAB_THREADS")) : 392;
+        int per_batch = tab_threads / (2 * PH);
         int slabs = cdiv(C, TAB_CS);
         int per_image = cdiv(K, B);
-        int g = cdiv(per_image, 4 * per_pass);  // >= 4 passes per CTA amortise the table build
+        int g = cdiv(per_image, 4 * per_batch);  // >= 4 batches per CTA amortise the table build
         int want = cdiv(8 * sm_count(), B * slabs);
         a.groups = std::max(1, std::min(g, want));
-        return PH == 7 ? launch_tab(roi_pool_tab_kernel<7>, a, tab_smem, stream)
-                       : launch_tab(roi_pool_tab_kernel<14>, a, tab_smem, stream);
+        if (PH == 7) return launch_tab(roi_pool_tab_kernel<7, 784>, a, tab_smem, 784, stream);
+        if (tab_threads == 588) return launch_tab(roi_pool_tab_kernel<14, 588>, a, tab_smem, 588, stream);
+        if (tab_threads == 392) return launch_tab(roi_pool_tab_kernel<14, 392>, a, tab_smem, 392, stream);
+        return launch_tab(roi_pool_tab_kernel<14, 784>, a, tab_smem, 784, stream);
     }
     if (PH == PW && PH == 7)
         return argmax ? launch_staged(roi_pool_staged_kernel<7, true>, a, smem, stream)
