@@ -8,7 +8,6 @@
 // RoI.  Features are read from L2/HBM once per (slab, group); the dominant HBM traffic is the
 // K*C*P*P*4 B output write.
 #include <float.h>
-#include <stdlib.h>
 
 #include <algorithm>
 
@@ -314,17 +313,27 @@ __device__ __forceinline__ int2 tab_entry(int i, int P, float c1, float c2, floa
     return r;
 }
 
+// Loop path for one bin longer than 4 in some direction (kept out of line: it is rare and would
+// otherwise bloat the unrolled fast path).
+__device__ __noinline__ float4 tab_big_bin(const float4* tab, int hr, int wr, int W) {
+    float4 v = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (int y = hr & 0xFFFF; y < (hr >> 16); ++y)
+        for (int x = wr & 0xFFFF; x < (wr >> 16); ++x) v = max4(v, tab[y * W + x]);
+    return v;
+}
+
 template <int P, int TAB_THREADS>
 __global__ void __launch_bounds__(TAB_THREADS, 2) roi_pool_tab_kernel(RoiArgs a) {
     constexpr int BINS = P * P;
-    constexpr int RPI = TAB_THREADS / BINS;      // RoIs per iteration (4 or 16)
-    constexpr int NB = TAB_THREADS / (2 * P);    // RoIs per batch: one table entry per thread (28 or 56)
-    static_assert(RPI * BINS == TAB_THREADS && NB * 2 * P == TAB_THREADS, "thread mapping");
+    constexpr int RPI = TAB_THREADS / BINS;      // RoIs per iteration (2 or 8)
+    constexpr int NB = TAB_THREADS / P;          // RoIs per batch: two table entries per thread (28 or 56)
+    constexpr int ITERS = NB / RPI;
+    static_assert(RPI * BINS == TAB_THREADS && NB * P == TAB_THREADS && ITERS * RPI == NB, "thread mapping");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int2 s_th[NB][P], s_tw[NB][P];  // per RoI: row / column corner offsets + flags
-    __shared__ int s_hraw[NB][P], s_wraw[NB][P];
-    __shared__ int s_k[NB];
+    __shared__ int2 s_th[2][NB][P], s_tw[2][NB][P];  // per RoI: row / column corner offsets + flags
+    __shared__ int s_hraw[2][NB][P], s_wraw[2][NB][P];
+    __shared__ size_t s_ob[2][NB];                   // per RoI: byte offset of its [4,P,P] output block
     float4* tab = reinterpret_cast<float4*>(smem_raw);
     const int H = a.H, W = a.W, HW = H * W, HWp = (HW + 3) & ~3;
     const int b = blockIdx.z;
@@ -335,9 +344,9 @@ __global__ void __launch_bounds__(TAB_THREADS, 2) roi_pool_tab_kernel(RoiArgs a)
     int r0 = r_begin + blockIdx.x * NB;  // first RoI of this CTA's current batch
     if (r0 >= r_end) return;
     const int tid = threadIdx.x;
-    // table-entry role: RoI tj of the batch, axis entry ti (rows first, then columns)
+    // table-entry role: axis entry ti (rows first, then columns) of RoIs tj and tj + NB/2 of the batch
     const int tj = tid / (2 * P), ti = tid % (2 * P);
-    RoiBox nxt = load_roi(a, r0 + tj, r_end);  // in flight while the tables are built
+    RoiBox nx0 = load_roi(a, r0 + tj, r_end), nx1 = load_roi(a, r0 + tj + NB / 2, r_end);
 
     float* raw = reinterpret_cast<float*>(tab + 3 * HWp);  // [cs][HW], lives where T22 will be
     stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
@@ -367,46 +376,63 @@ __global__ void __launch_bounds__(TAB_THREADS, 2) roi_pool_tab_kernel(RoiArgs a)
     // compute role: bin e = (ph,pw) of the (tid / BINS)-th RoI of each iteration
     const int e = tid % BINS, ej = tid / BINS;
     const int ph = e / P, pw = e % P;
-    for (; r0 < r_end; r0 += stride) {
-        const RoiBox q = nxt;
-        __syncthreads();  // previous batch's table reads (and, first time, the T22 build) are done
-        if (ti < P) s_th[tj][ti] = tab_entry(ti, P, q.y1, q.y2, a.scale, H, W, 2 * HWp, &s_hraw[tj][ti]);
-        else s_tw[tj][ti - P] = tab_entry(ti - P, P, q.x1, q.x2, a.scale, W, 1, HWp, &s_wraw[tj][ti - P]);
-        if (ti == 0) s_k[tj] = q.k;
-        nxt = load_roi(a, r0 + stride + tj, r_end);  // prefetch the next batch's boxes
-        __syncthreads();
+    auto fill_tables = [&](int buf, int j, const RoiBox& q) {
+        if (ti < P) s_th[buf][j][ti] = tab_entry(ti, P, q.y1, q.y2, a.scale, H, W, 2 * HWp, &s_hraw[buf][j][ti]);
+        else s_tw[buf][j][ti - P] = tab_entry(ti - P, P, q.x1, q.x2, a.scale, W, 1, HWp, &s_wraw[buf][j][ti - P]);
+        if (ti == 0)
+            s_ob[buf][j] = (((size_t)max(q.k, 0) * a.C + c0) * BINS) * sizeof(float);
+    };
+    fill_tables(0, tj, nx0);
+    fill_tables(0, tj + NB / 2, nx1);
+    nx0 = load_roi(a, r0 + stride + tj, r_end);
+    nx1 = load_roi(a, r0 + stride + tj + NB / 2, r_end);
+    int cur = 0;
+    for (; r0 < r_end; r0 += stride, cur ^= 1) {
+        __syncthreads();  // tables[cur] (and, first time, T22) complete; tables[cur^1] no longer read
+        fill_tables(cur ^ 1, tj, nx0);  // geometry of the next batch
+        fill_tables(cur ^ 1, tj + NB / 2, nx1);
+        nx0 = load_roi(a, r0 + 2 * stride + tj, r_end);  // boxes of the batch after that
+        nx1 = load_roi(a, r0 + 2 * stride + tj + NB / 2, r_end);
         const int nb = min(NB, r_end - r0);
-#pragma unroll 2
-        for (int j = ej; j < nb; j += RPI) {
-            const int2 h = s_th[j][ph], w = s_tw[j][pw];
-            const int flags = h.y & w.y;
-            const bool big = ((h.y | w.y) & TAB_BIG_BIT) != 0;
+        // one bin (this thread's ph,pw) of RoI j of the batch, all four channels
+        auto one_bin = [&](int j, bool full4, bool valid) {
+            const int2 h = s_th[cur][j][ph], w = s_tw[cur][j][pw];
             const int hy = h.y & TAB_OFF_MASK, wy = w.y & TAB_OFF_MASK;
-            const unsigned char* t1 = smem_raw + w.x;
-            const unsigned char* t2 = smem_raw + wy;
-            float4 v;
-            if (!big) {
-                // lookups that coincide are skipped when no lane of the warp needs them
-                const bool wide = __any_sync(__activemask(), w.x != wy);
-                const bool tall = __any_sync(__activemask(), h.x != hy);
-                v = *reinterpret_cast<const float4*>(t1 + h.x);
-                if (wide) v = max4(v, *reinterpret_cast<const float4*>(t2 + h.x));
-                if (tall) {
-                    v = max4(v, *reinterpret_cast<const float4*>(t1 + hy));
-                    if (wide) v = max4(v, *reinterpret_cast<const float4*>(t2 + hy));
-                }
-            } else {
-                const int hr = s_hraw[j][ph], wr = s_wraw[j][pw];
-                v = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-                for (int y = hr & 0xFFFF; y < (hr >> 16); ++y)
-                    for (int x = wr & 0xFFFF; x < (wr >> 16); ++x) v = max4(v, tab[y * W + x]);
+            // lookups that coincide are skipped when no lane of the warp needs them
+            const bool wide = __any_sync(0xFFFFFFFFu, w.x != wy);
+            const bool tall = __any_sync(0xFFFFFFFFu, h.x != hy);
+            float4 v = *reinterpret_cast<const float4*>(smem_raw + (w.x + h.x));
+            if (wide) v = max4(v, *reinterpret_cast<const float4*>(smem_raw + (wy + h.x)));
+            if (tall) {
+                v = max4(v, *reinterpret_cast<const float4*>(smem_raw + (w.x + hy)));
+                if (wide) v = max4(v, *reinterpret_cast<const float4*>(smem_raw + (wy + hy)));
             }
-            const unsigned m = (unsigned)(flags >> 31);  // all ones iff the bin is non-empty
-            float* o = a.out + ((size_t)s_k[j] * a.C + c0) * BINS + e;
-            o[0] = __uint_as_float(__float_as_uint(v.x) & m);
-            if (cs > 1) o[BINS] = __uint_as_float(__float_as_uint(v.y) & m);
-            if (cs > 2) o[2 * BINS] = __uint_as_float(__float_as_uint(v.z) & m);
-            if (cs > 3) o[3 * BINS] = __uint_as_float(__float_as_uint(v.w) & m);
+            const bool big = ((h.y | w.y) & TAB_BIG_BIT) != 0;
+            if (__any_sync(0xFFFFFFFFu, big)) {
+                if (big) v = tab_big_bin(tab, s_hraw[cur][j][ph], s_wraw[cur][j][pw], W);
+            }
+            const unsigned m = (unsigned)((h.y & w.y) >> 31);  // all ones iff the bin is non-empty
+            float* o = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.out) + s_ob[cur][j]) + e;
+            if (full4) {
+                o[0] = __uint_as_float(__float_as_uint(v.x) & m);
+                o[BINS] = __uint_as_float(__float_as_uint(v.y) & m);
+                o[2 * BINS] = __uint_as_float(__float_as_uint(v.z) & m);
+                o[3 * BINS] = __uint_as_float(__float_as_uint(v.w) & m);
+            } else if (valid) {
+                o[0] = __uint_as_float(__float_as_uint(v.x) & m);
+                if (cs > 1) o[BINS] = __uint_as_float(__float_as_uint(v.y) & m);
+                if (cs > 2) o[2 * BINS] = __uint_as_float(__float_as_uint(v.z) & m);
+                if (cs > 3) o[3 * BINS] = __uint_as_float(__float_as_uint(v.w) & m);
+            }
+        };
+        if (nb == NB && cs == TAB_CS) {
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) one_bin(it * RPI + ej, true, true);
+        } else {
+            for (int it = 0; it * RPI < nb; ++it) {
+                const int j = it * RPI + ej;
+                one_bin(j < nb ? j : 0, false, j < nb);
+            }
         }
     }
 }
@@ -774,17 +800,15 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
     size_t tab_smem = (size_t)4 * ((H * W + 3) & ~3) * sizeof(float4);
     if (!argmax && PH == PW && (PH == 7 || PH == 14) && tab_smem <= ROI_SMEM_MAX) {
         a.CS = TAB_CS;
-        static int tab_threads = getenv("FRCNN_TAB_THREADS") ? atoi(getenv("FRCNN_TAB_THREADS")) : 392;
-        int per_batch = tab_threads / (2 * PH);
+        const int tab_threads = 392;  // 2*14*14 = 8*7*7; measured best (784/588 are register-starved)
+        int per_batch = tab_threads / PH;
         int slabs = cdiv(C, TAB_CS);
         int per_image = cdiv(K, B);
         int g = cdiv(per_image, 4 * per_batch);  // >= 4 batches per CTA amortise the table build
         int want = cdiv(8 * sm_count(), B * slabs);
         a.groups = std::max(1, std::min(g, want));
-        if (PH == 7) return launch_tab(roi_pool_tab_kernel<7, 784>, a, tab_smem, 784, stream);
-        if (tab_threads == 588) return launch_tab(roi_pool_tab_kernel<14, 588>, a, tab_smem, 588, stream);
-        if (tab_threads == 392) return launch_tab(roi_pool_tab_kernel<14, 392>, a, tab_smem, 392, stream);
-        return launch_tab(roi_pool_tab_kernel<14, 784>, a, tab_smem, 784, stream);
+        if (PH == 7) return launch_tab(roi_pool_tab_kernel<7, 392>, a, tab_smem, tab_threads, stream);
+        return launch_tab(roi_pool_tab_kernel<14, 392>, a, tab_smem, tab_threads, stream);
     }
     if (PH == PW && PH == 7)
         return argmax ? launch_staged(roi_pool_staged_kernel<7, true>, a, smem, stream)
