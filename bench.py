@@ -148,9 +148,9 @@ def run_ours(args):
         rois5 = F.roi_head_coords(rois, idx, (S, S), (H, W))
         ev["r0"][i].record()
         if cfg["op"] == "pool":
-            F.roi_pool_forward(feat, rois5, P, 1.0, out=pooled)
+            F.roi_pool_forward(feat, rois5, P, 1.0, out=pooled, rois_per_image=n_post)
         else:
-            F.roi_align_forward(feat, rois5, P, 1.0, 2, False, out=pooled)
+            F.roi_align_forward(feat, rois5, P, 1.0, 2, False, out=pooled, rois_per_image=n_post)
         ev["r1"][i].record()
         if world > 1:
             dist.all_gather_into_tensor(gathered, rois)
@@ -196,7 +196,7 @@ def run_ours(args):
         rois, _, _, st = creator.batched(loc, logits, (3, S, S), 1.0, base=base, feat_stride=16, feat_hw=(H, W),
                                          score_is_logits=True)
         with torch.no_grad():
-            cls_locs, scores = head(feat, rois, idx, (S, S))
+            cls_locs, scores = head(feat, rois, None, (S, S))
         outs = [rois.cpu(), cls_locs.cpu(), scores.cpu(), st.cpu()]
         d2h = sum(o.numel() * o.element_size() for o in outs)
         return outs
@@ -219,8 +219,10 @@ def run_ours(args):
     peak, peak_src = peaks()
     alg_bytes = K * C * P * P * 4 + K * 20 + B * C * H * W * 4
     achieved = alg_bytes / (roi_ms * 1e-3) / 1e9
-    n_sb = -(-min(cfg["n_pre"], N) // 2048)
-    launches = 1 + 1 + 2 * n_sb + 1 + 1 + 1 + 1  # decode, topk, nms(mask+scan)*sb, finalize, coords, bucket, gather
+    rows = min(cfg["n_pre"], N)
+    sblock = min(max(-(-2 * n_post // 256) * 256, 256), 2048, -(-rows // 256) * 256)  # csrc/proposals.cu
+    n_sb = -(-rows // sblock)
+    launches = 1 + 1 + 2 * n_sb + 1 + 1 + 1  # decode, topk, nms(mask+scan)*sb, finalize, coords, gather
 
     out = {
         "metric": "images/sec (RPN proposals + RoI gather hot path)", "value": world * B / (ms_step * 1e-3),

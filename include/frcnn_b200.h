@@ -178,11 +178,14 @@ int frcnn_roi_head_coords(const float* rois, const int32_t* roi_indices, int32_t
                           int32_t feat_w, float* rois5, frcnn_stream_t stream);
 
 /* torchvision RoIPool forward (nets/classify.py:17,43).  feat [B,C,H,W]; rois5 [K,5];
- * out [K,C,PH,PW]; argmax [K,C,PH,PW] int32 (nullable; needed only for backward).               */
+ * out [K,C,PH,PW]; argmax [K,C,PH,PW] int32 (nullable; needed only for backward).
+ * rois_per_image: 0 = RoIs in any order (bucketed by their batch index on the device); R > 0 = the
+ * caller guarantees K == B*R and rows [b*R,(b+1)*R) belong to image b, as the head builds them
+ * (nets/classify.py:38), which skips the bucketing pass.                                         */
 size_t frcnn_roi_workspace_bytes(int32_t batch, int32_t num_rois);
 int frcnn_roi_pool_forward(const float* feat, int32_t batch, int32_t channels, int32_t height,
-                           int32_t width, const float* rois5, int32_t num_rois, int32_t pooled_h,
-                           int32_t pooled_w, float spatial_scale, float* out, int32_t* argmax,
+                           int32_t width, const float* rois5, int32_t num_rois, int32_t rois_per_image,
+                           int32_t pooled_h, int32_t pooled_w, float spatial_scale, float* out, int32_t* argmax,
                            void* workspace, size_t workspace_bytes, frcnn_stream_t stream);
 /* grad_in [B,C,H,W] must be zero-initialised by the caller.                                     */
 int frcnn_roi_pool_backward(const float* grad_out, const int32_t* argmax, const float* rois5,
@@ -190,8 +193,8 @@ int frcnn_roi_pool_backward(const float* grad_out, const int32_t* argmax, const 
                             int32_t pooled_h, int32_t pooled_w, float* grad_in, frcnn_stream_t stream);
 /* torchvision roi_align forward (BASELINE.json RoIAlign 7x7 configuration).                      */
 int frcnn_roi_align_forward(const float* feat, int32_t batch, int32_t channels, int32_t height,
-                            int32_t width, const float* rois5, int32_t num_rois, int32_t pooled_h,
-                            int32_t pooled_w, float spatial_scale, int32_t sampling_ratio,
+                            int32_t width, const float* rois5, int32_t num_rois, int32_t rois_per_image,
+                            int32_t pooled_h, int32_t pooled_w, float spatial_scale, int32_t sampling_ratio,
                             int32_t aligned, float* out, void* workspace, size_t workspace_bytes,
                             frcnn_stream_t stream);
 int frcnn_roi_align_backward(const float* grad_out, const float* rois5, int32_t num_rois,

@@ -59,7 +59,7 @@ def test_host_side_argument_checks_need_no_gpu():
     assert rc == -1 and b"bad shape" in lib.frcnn_last_error()
     rc = lib.frcnn_proposals(ctypes.byref(p), None, None, None, None, None, None, None, None, 0, None)
     assert rc == -1
-    rc = lib.frcnn_roi_pool_forward(None, 0, 1, 1, 1, None, 0, 7, 7, 1.0, None, None, None, 0, None)
+    rc = lib.frcnn_roi_pool_forward(None, 0, 1, 1, 1, None, 0, 0, 7, 7, 1.0, None, None, None, 0, None)
     assert rc == -1
 
 

@@ -351,6 +351,23 @@ def test_roi_ops_vs_oracle(F, O, shape):
         assert np.array_equal(N(F.roi_align(T(feat), T(rois), P, 1.0, sr, al)), O.roi_align(feat, rois, P, 1.0, sr, al))
 
 
+def test_roi_grouped_path_equals_bucketed(F):
+    """rois_per_image promise (no bucketing pass) gives the same bits as the general path."""
+    rng = np.random.default_rng(77)
+    B, Cc, H, W, R = 3, 12, 38, 38, 50
+    feat = T(rng.standard_normal((B, Cc, H, W)).astype(np.float32))
+    c = rng.uniform(0, W, (B * R, 2))
+    wh = rng.uniform(1, 30, (B * R, 2))
+    rois = np.concatenate([np.repeat(np.arange(B), R)[:, None], c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    for P in (7, 14):
+        a = F.roi_pool_forward(feat, T(rois), P, 1.0)
+        b = F.roi_pool_forward(feat, T(rois), P, 1.0, rois_per_image=R)
+        assert torch.equal(a, b)
+    a = F.roi_align_forward(feat, T(rois), 7, 1.0, 2, False)
+    b = F.roi_align_forward(feat, T(rois), 7, 1.0, 2, False, rois_per_image=R)
+    assert torch.equal(a, b)
+
+
 def test_roi_head_dropin(F):
     from two_stage_object_detection_b200.nets import HarNetRoIHead
     from two_stage_object_detection_b200.nets.frcnn import GlobalAvgClassifier
@@ -368,6 +385,7 @@ def test_roi_head_dropin(F):
         r5 = F.roi_head_coords(rois, idx, img, (x.shape[2], x.shape[3]))
         assert np.array_equal(N(r5), g[f"{tag}_rois5"]), tag
         pool = head.gather(x, rois, idx, img)
+        assert torch.equal(pool, head.gather(x, rois, None, img))
         assert np.array_equal(N(pool[:16, :32]), g[f"{tag}_pool_head"]), tag
         assert np.allclose(N(pool).astype(np.float64).sum((2, 3)), g[f"{tag}_pool_sum"], rtol=0, atol=1e-9)
         with torch.no_grad():

@@ -2,12 +2,15 @@
 // torchvision.ops.nms), batched over images, no host synchronisation anywhere.
 //
 //   decode_clip_key   one thread per anchor: loc2bbox, clamp, min-size test, score -> sortable key
-//   topk_sort         one CTA per image: stable LSD radix sort of (~key) with warp-match ranking;
-//                     emits anchor indices in (score desc, index asc) order + gathered boxes
+//   topk_sort         one 8-CTA cluster per image: stable LSD radix sort of (~key), histograms
+//                     exchanged over distributed shared memory, warp-match ranking; emits anchor
+//                     indices in (score desc, index asc) order + gathered boxes
 //   nms_mask          super-block S of sorted candidates: warp-ballot IoU>thr bitmask tiles
 //                     (upper triangle only) + suppression by boxes kept in earlier super-blocks
 //   nms_scan          one CTA per image: resolves 32 candidates per step, early exit at keep_cap
 //   finalize          pad-with-arange / truncate / gather (nets/rpn.py:65-69)
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace frcnn {
@@ -71,40 +74,59 @@ __global__ void scores_to_keys_kernel(const float* __restrict__ s, int n, uint32
 
 // ---------------------------------------------------------------------------------------------
 // per-image stable radix sort (descending key, ascending index on ties)
+//
+// One thread-block CLUSTER of 8 CTAs per image (16 images -> 128 SMs instead of 16).  CTA r owns the
+// r-th contiguous eighth of the keys in their current order.  Per 8-bit pass:
+//   1. every CTA histograms its segment (warp-match aggregated shared-memory atomics);
+//   2. cluster barrier; each CTA reads the eight histograms through distributed shared memory and
+//      derives, per digit, the global base + the count in lower-ranked CTAs = its own running offset;
+//   3. stable scatter of the segment into the other global ping-pong buffer (chunks in order, ranks
+//      from __match_any_sync + a scan of per-warp digit counts);
+//   4. cluster barrier (release/acquire: the scatter is visible to the whole cluster).
+// Sorting ~key ascending gives key descending; LSD stability gives index-ascending ties; filtered
+// anchors (key 0) sort last.  Passes whose digit is identical for all keys are skipped.
 // ---------------------------------------------------------------------------------------------
-constexpr int TOPK_THREADS = 1024;
-constexpr int TOPK_WARPS = TOPK_THREADS / 32;
+constexpr int TK_CL = 8;
+constexpr int TK_THREADS = 512;
+constexpr int TK_WARPS = TK_THREADS / 32;
 
-__global__ void __launch_bounds__(TOPK_THREADS)
+__global__ void __cluster_dims__(TK_CL, 1, 1) __launch_bounds__(TK_THREADS)
 topk_sort_kernel(const uint32_t* __restrict__ keys_all, const float4* __restrict__ boxes_all, int n,
                  int k_cap, uint32_t* __restrict__ ws_keys, uint32_t* __restrict__ ws_idx,
                  int* __restrict__ order_all, int* __restrict__ n_sel_all,
                  float4* __restrict__ sorted_all) {
-    __shared__ uint32_t hist[256];
-    __shared__ uint32_t warp_cnt[TOPK_WARPS][256];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ uint32_t hist[256];  // this CTA's digit counts (read by the whole cluster)
+    __shared__ uint32_t offs[256];  // running destination offsets of this CTA
+    __shared__ uint32_t warp_cnt[TK_WARPS][256];
     __shared__ uint32_t warp_tot[8];
-    __shared__ uint32_t s_nzero;
+    __shared__ uint32_t s_nzero;    // filtered (key == 0) anchors in this CTA's segment
 
-    const int b = blockIdx.x;
+    const int crank = (int)cluster.block_rank();
+    const int b = blockIdx.x / TK_CL;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* keys = keys_all + (size_t)b * n;
-    uint32_t* bufK[2] = {ws_keys + (size_t)b * 2 * n, ws_keys + (size_t)b * 2 * n + n};
-    uint32_t* bufI[2] = {ws_idx + (size_t)b * 2 * n, ws_idx + (size_t)b * 2 * n + n};
+    uint32_t* bufK0 = ws_keys + (size_t)b * 2 * n;
+    uint32_t* bufI0 = ws_idx + (size_t)b * 2 * n;
     const uint32_t lt = lanemask_lt();
+    const int seg = (n + TK_CL - 1) / TK_CL;
+    const int lo = min(crank * seg, n), hi = min(lo + seg, n);
 
     if (tid == 0) s_nzero = 0;
     int cur = -1;  // -1: data still in `keys` (identity permutation)
 
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 8 * pass;
+        const uint32_t* srcK = cur < 0 ? nullptr : bufK0 + (size_t)cur * n;
+        const uint32_t* srcI = cur < 0 ? nullptr : bufI0 + (size_t)cur * n;
         if (tid < 256) hist[tid] = 0;
         __syncthreads();
-        // digit histogram, warp-aggregated
-        for (int base = 0; base < n; base += TOPK_THREADS) {
+        for (int base = lo; base < hi; base += TK_THREADS) {
             int i = base + tid;
-            bool valid = i < n;
+            bool valid = i < hi;
             uint32_t k = 0;
-            if (valid) k = (cur < 0) ? ~__ldg(keys + i) : bufK[cur][i];
+            if (valid) k = srcK ? __ldcg(srcK + i) : ~__ldg(keys + i);
             uint32_t d = valid ? ((k >> shift) & 255u) : 256u;
             uint32_t m = __match_any_sync(0xFFFFFFFFu, d);
             if (valid && (m & lt) == 0) atomicAdd(&hist[d], (uint32_t)__popc(m));
@@ -113,14 +135,24 @@ topk_sort_kernel(const uint32_t* __restrict__ keys_all, const float4* __restrict
                 if (lane == 0 && z) atomicAdd(&s_nzero, (uint32_t)__popc(z));
             }
         }
-        __syncthreads();
-        int trivial = __syncthreads_or(tid < 256 && hist[tid] == (uint32_t)n);
-        if (trivial) continue;  // every key shares this digit: pass is the identity
-        // exclusive scan of hist -> running base offsets
-        uint32_t v = 0, incl = 0;
+        cluster.sync();  // all eight histograms complete
+        uint32_t total = 0, pre = 0;
         if (tid < 256) {
-            v = hist[tid];
-            incl = v;
+#pragma unroll
+            for (int c = 0; c < TK_CL; ++c) {
+                uint32_t v = cluster.map_shared_rank(hist, c)[tid];
+                pre += c < crank ? v : 0u;
+                total += v;
+            }
+        }
+        // identical in every CTA of the cluster, so the whole cluster takes the same branch
+        int trivial = __syncthreads_or(tid < 256 && total == (uint32_t)n);
+        if (trivial) {
+            cluster.sync();  // remote reads of hist are done before the next pass clears it
+            continue;
+        }
+        uint32_t incl = total;
+        if (tid < 256) {
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -130,22 +162,24 @@ topk_sort_kernel(const uint32_t* __restrict__ keys_all, const float4* __restrict
         }
         __syncthreads();
         if (tid < 256) {
-            uint32_t pre = 0;
-            for (int w = 0; w < warp; ++w) pre += warp_tot[w];
-            hist[tid] = pre + incl - v;
+            uint32_t before = 0;
+            for (int w = 0; w < warp; ++w) before += warp_tot[w];
+            offs[tid] = before + incl - total + pre;
         }
         __syncthreads();
-        const int dst = (cur < 0) ? 0 : (cur ^ 1);
-        for (int base = 0; base < n; base += TOPK_THREADS) {
+        const int dst = cur < 0 ? 0 : (cur ^ 1);
+        uint32_t* dstK = bufK0 + (size_t)dst * n;
+        uint32_t* dstI = bufI0 + (size_t)dst * n;
+        for (int base = lo; base < hi; base += TK_THREADS) {
             int i = base + tid;
-            bool valid = i < n;
+            bool valid = i < hi;
             uint32_t k = 0, id = (uint32_t)i;
             if (valid) {
-                if (cur < 0) {
-                    k = ~__ldg(keys + i);
+                if (srcK) {  // written by other SMs in the previous pass: read through L2
+                    k = __ldcg(srcK + i);
+                    id = __ldcg(srcI + i);
                 } else {
-                    k = bufK[cur][i];
-                    id = bufI[cur][i];
+                    k = ~__ldg(keys + i);
                 }
             }
             uint32_t d = valid ? ((k >> shift) & 255u) : 256u;
@@ -157,33 +191,36 @@ topk_sort_kernel(const uint32_t* __restrict__ keys_all, const float4* __restrict
             if (valid && rank == 0) warp_cnt[warp][d] = __popc(m);
             __syncthreads();
             if (tid < 256) {
-                uint32_t run = hist[tid];
-#pragma unroll 8
-                for (int w = 0; w < TOPK_WARPS; ++w) {
+                uint32_t run = offs[tid];
+#pragma unroll
+                for (int w = 0; w < TK_WARPS; ++w) {
                     uint32_t c = warp_cnt[w][tid];
                     warp_cnt[w][tid] = run;
                     run += c;
                 }
-                hist[tid] = run;
+                offs[tid] = run;
             }
             __syncthreads();
             if (valid) {
                 uint32_t pos = warp_cnt[warp][d] + rank;
-                bufK[dst][pos] = k;
-                bufI[dst][pos] = id;
+                dstK[pos] = k;
+                dstI[pos] = id;
             }
         }
-        __syncthreads();  // scatter visible to the whole CTA before the next pass reads it
+        cluster.sync();  // scatter visible cluster-wide; hist may be cleared again
         cur = dst;
     }
-    __syncthreads();
-    const int n_valid = n - (int)s_nzero;
+    uint32_t nzero = 0;
+#pragma unroll
+    for (int c = 0; c < TK_CL; ++c) nzero += *cluster.map_shared_rank(&s_nzero, c);
+    const int n_valid = n - (int)nzero;
     const int n_sel = n_valid < k_cap ? n_valid : k_cap;
-    if (tid == 0) n_sel_all[b] = n_sel;
+    if (crank == 0 && tid == 0) n_sel_all[b] = n_sel;
     int* order = order_all + (size_t)b * k_cap;
-    for (int j = tid; j < k_cap; j += TOPK_THREADS) {
+    const uint32_t* finI = cur < 0 ? nullptr : bufI0 + (size_t)cur * n;
+    for (int j = crank * TK_THREADS + tid; j < k_cap; j += TK_CL * TK_THREADS) {
         int id = -1;
-        if (j < n_sel) id = (cur < 0) ? j : (int)bufI[cur][j];
+        if (j < n_sel) id = finI ? (int)__ldcg(finI + j) : j;
         order[j] = id;
         if (sorted_all) {
             float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -191,6 +228,7 @@ topk_sort_kernel(const uint32_t* __restrict__ keys_all, const float4* __restrict
             sorted_all[(size_t)b * k_cap + j] = bx;
         }
     }
+    cluster.sync();  // nobody exits while its shared memory may still be read remotely
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -452,9 +490,14 @@ static float float_threshold(double thr) {
     return t;
 }
 
-static int pick_superblock(int requested, int n_rows) {
-    int S = requested > 0 ? requested : 2048;
+static int pick_superblock(int requested, int n_rows, int keep_cap) {
+    // default: about twice the number of boxes wanted, so that the first super-block usually
+    // finishes the job and little of the IoU mask is computed for nothing (measured on cfg2: a
+    // 2048-wide block spent 97 us on a mask of which ~430 columns were needed)
+    int S = requested > 0 ? requested : 2 * keep_cap;
     S = (S + NMS_CB - 1) / NMS_CB * NMS_CB;
+    if (S < NMS_CB) S = NMS_CB;
+    if (S > 2048 && requested <= 0) S = 2048;
     if (S > NMS_MAX_WORDS * 32) S = NMS_MAX_WORDS * 32;
     int need = (n_rows + NMS_CB - 1) / NMS_CB * NMS_CB;
     if (need < NMS_CB) need = NMS_CB;
@@ -469,7 +512,7 @@ struct NmsLayout {
 
 static size_t nms_ws_layout(Workspace& ws, int batch, int n_rows, int keep_cap, int superblock,
                             NmsArgs* a) {
-    int S = pick_superblock(superblock, n_rows);
+    int S = pick_superblock(superblock, n_rows, keep_cap);
     uint32_t* mask = ws.take<uint32_t>((size_t)batch * (S / 32) * S);
     // state + removed are cleared together by one memset
     size_t clear_bytes = align_up((size_t)batch * sizeof(NmsState)) + align_up((size_t)batch * (S / 32) * 4);
@@ -530,8 +573,8 @@ static int run_topk(const uint32_t* keys, const float* boxes, int batch, int n, 
         set_error("topk: workspace too small or misaligned (%zu needed, %zu given)", ws.off, workspace_bytes);
         return FRCNN_ERR_WORKSPACE;
     }
-    topk_sort_kernel<<<batch, TOPK_THREADS, 0, stream>>>(keys, (const float4*)boxes, n, k_cap, wk, wi, order,
-                                                         n_sel, (float4*)sorted_boxes);
+    topk_sort_kernel<<<batch * TK_CL, TK_THREADS, 0, stream>>>(keys, (const float4*)boxes, n, k_cap, wk, wi, order,
+                                                               n_sel, (float4*)sorted_boxes);
     FRCNN_LAUNCH_CHECK();
     return FRCNN_OK;
 }

@@ -156,9 +156,22 @@ struct RoiArgs {
     float* out;
     int* argmax;
     int sampling_ratio, aligned;
+    int per_image;   // > 0: RoIs are grouped, rows [b*per_image, (b+1)*per_image) belong to image b
 };
 
 __device__ __forceinline__ int round_half_away(float v) { return (int)roundf(v); }
+
+// RoI rows of image b, and the RoI id stored at row r (identity when the caller grouped the RoIs)
+__device__ __forceinline__ void roi_range(const RoiArgs& a, int b, int& r_begin, int& r_end) {
+    if (a.per_image > 0) {
+        r_begin = b * a.per_image;
+        r_end = r_begin + a.per_image;
+    } else {
+        r_begin = a.offs[b];
+        r_end = a.offs[b + 1];
+    }
+}
+__device__ __forceinline__ int roi_at(const RoiArgs& a, int r) { return a.per_image > 0 ? r : a.perm[r]; }
 
 template <int P, bool WITH_ARGMAX>
 __global__ void __launch_bounds__(ROI_THREADS, 2) roi_pool_staged_kernel(RoiArgs a) {
@@ -174,7 +187,8 @@ __global__ void __launch_bounds__(ROI_THREADS, 2) roi_pool_staged_kernel(RoiArgs
     const int c0 = blockIdx.y * a.CS;
     const int cs = min(a.CS, a.C - c0);
     const int HW = a.H * a.W;
-    const int r_begin = a.offs[b], r_end = a.offs[b + 1];
+    int r_begin, r_end;
+    roi_range(a, b, r_begin, r_end);
     const int first = r_begin + blockIdx.x;
     if (first >= r_end) return;
     stage_slab(sfeat, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
@@ -188,7 +202,7 @@ __global__ void __launch_bounds__(ROI_THREADS, 2) roi_pool_staged_kernel(RoiArgs
         __syncthreads();  // previous batch done with the tables
         if (threadIdx.x < nb * (PH + PW)) {
             int j = threadIdx.x / (PH + PW), e = threadIdx.x % (PH + PW);
-            int k = a.perm[rb + j * a.groups];
+            int k = roi_at(a, rb + j * a.groups);
             const float* r = a.rois5 + (size_t)k * 5;
             if (e == 0) s_roi[j] = k;
             if (e < PH) {
@@ -283,7 +297,7 @@ __device__ __forceinline__ RoiBox load_roi(const RoiArgs& a, int r, int r_end) {
     q.k = -1;
     q.x1 = q.y1 = q.x2 = q.y2 = 0.f;
     if (r < r_end) {
-        q.k = a.perm[r];
+        q.k = roi_at(a, r);
         const float* rp = a.rois5 + (size_t)q.k * 5;
         q.x1 = __ldg(rp + 1);
         q.y1 = __ldg(rp + 2);
@@ -339,7 +353,8 @@ __global__ void __launch_bounds__(TAB_THREADS, 2) roi_pool_tab_kernel(RoiArgs a)
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * TAB_CS;
     const int cs = min(TAB_CS, a.C - c0);
-    const int r_begin = a.offs[b], r_end = a.offs[b + 1];
+    int r_begin, r_end;
+    roi_range(a, b, r_begin, r_end);
     const int stride = a.groups * NB;
     int r0 = r_begin + blockIdx.x * NB;  // first RoI of this CTA's current batch
     if (r0 >= r_end) return;
@@ -566,7 +581,8 @@ __global__ void __launch_bounds__(ROI_THREADS, 2) roi_align_staged_kernel(RoiArg
     const int c0 = blockIdx.y * a.CS;
     const int cs = min(a.CS, a.C - c0);
     const int HW = a.H * a.W;
-    const int r_begin = a.offs[b], r_end = a.offs[b + 1];
+    int r_begin, r_end;
+    roi_range(a, b, r_begin, r_end);
     const int first = r_begin + blockIdx.x;
     if (first >= r_end) return;
     stage_slab(sfeat, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
@@ -577,7 +593,7 @@ __global__ void __launch_bounds__(ROI_THREADS, 2) roi_align_staged_kernel(RoiArg
             if (rb + j * a.groups < r_end) nb = j + 1;
         __syncthreads();
         if (threadIdx.x < nb) {
-            int k = a.perm[rb + threadIdx.x * a.groups];
+            int k = roi_at(a, rb + threadIdx.x * a.groups);
             sq[threadIdx.x] = make_align_roi(a.rois5 + (size_t)k * 5, k, a.scale, PH, PW, a.sampling_ratio, a.aligned);
         }
         __syncthreads();
@@ -748,7 +764,7 @@ size_t frcnn_roi_workspace_bytes(int32_t batch, int32_t num_rois) {
 }
 
 static int roi_forward_common(bool align, const float* feat, int B, int C, int H, int W, const float* rois5,
-                              int K, int PH, int PW, float scale, int sampling_ratio, int aligned, float* out,
+                              int K, int per_image, int PH, int PW, float scale, int sampling_ratio, int aligned, float* out,
                               int32_t* argmax, void* workspace, size_t workspace_bytes, cudaStream_t stream,
                               const char* who) {
     int rc = check_roi_common(feat, B, C, H, W, rois5, K, PH, PW, out, who);
@@ -781,17 +797,22 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
         FRCNN_LAUNCH_CHECK();
         return FRCNN_OK;
     }
-    Workspace ws(workspace, workspace_bytes);
-    RoiWs w;
-    roi_layout(ws, B, K, &w);
-    if (!ws.ok()) {
-        set_error("%s: workspace too small or misaligned (%zu needed, %zu given)", who, ws.off, workspace_bytes);
-        return FRCNN_ERR_WORKSPACE;
+    if (per_image > 0) {
+        FRCNN_CHECK_ARG((int64_t)per_image * B == K, "%s: rois_per_image * batch != num_rois", who);
+        a.per_image = per_image;  // caller guarantees grouping: no bucketing pass
+    } else {
+        Workspace ws(workspace, workspace_bytes);
+        RoiWs w;
+        roi_layout(ws, B, K, &w);
+        if (!ws.ok()) {
+            set_error("%s: workspace too small or misaligned (%zu needed, %zu given)", who, ws.off, workspace_bytes);
+            return FRCNN_ERR_WORKSPACE;
+        }
+        roi_bucket_kernel<<<1, BUCKET_THREADS, 2 * B * sizeof(int), stream>>>(rois5, K, B, w.perm, w.offs);
+        FRCNN_LAUNCH_CHECK();
+        a.perm = w.perm;
+        a.offs = w.offs;
     }
-    roi_bucket_kernel<<<1, BUCKET_THREADS, 2 * B * sizeof(int), stream>>>(rois5, K, B, w.perm, w.offs);
-    FRCNN_LAUNCH_CHECK();
-    a.perm = w.perm;
-    a.offs = w.offs;
     a.CS = cs;
     a.groups = pick_groups(K, B, cdiv(C, cs));
     size_t smem = (size_t)cs * H * W * 4;
@@ -821,17 +842,17 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
 }
 
 int frcnn_roi_pool_forward(const float* feat, int32_t B, int32_t C, int32_t H, int32_t W, const float* rois5,
-                           int32_t K, int32_t PH, int32_t PW, float scale, float* out, int32_t* argmax,
-                           void* workspace, size_t workspace_bytes, frcnn_stream_t stream) {
-    return roi_forward_common(false, feat, B, C, H, W, rois5, K, PH, PW, scale, 0, 0, out, argmax, workspace,
+                           int32_t K, int32_t per_image, int32_t PH, int32_t PW, float scale, float* out,
+                           int32_t* argmax, void* workspace, size_t workspace_bytes, frcnn_stream_t stream) {
+    return roi_forward_common(false, feat, B, C, H, W, rois5, K, per_image, PH, PW, scale, 0, 0, out, argmax, workspace,
                               workspace_bytes, (cudaStream_t)stream, "frcnn_roi_pool_forward");
 }
 
 int frcnn_roi_align_forward(const float* feat, int32_t B, int32_t C, int32_t H, int32_t W, const float* rois5,
-                            int32_t K, int32_t PH, int32_t PW, float scale, int32_t sampling_ratio,
-                            int32_t aligned, float* out, void* workspace, size_t workspace_bytes,
-                            frcnn_stream_t stream) {
-    return roi_forward_common(true, feat, B, C, H, W, rois5, K, PH, PW, scale, sampling_ratio, aligned, out,
+                            int32_t K, int32_t per_image, int32_t PH, int32_t PW, float scale,
+                            int32_t sampling_ratio, int32_t aligned, float* out, void* workspace,
+                            size_t workspace_bytes, frcnn_stream_t stream) {
+    return roi_forward_common(true, feat, B, C, H, W, rois5, K, per_image, PH, PW, scale, sampling_ratio, aligned, out,
                               nullptr, workspace, workspace_bytes, (cudaStream_t)stream, "frcnn_roi_align_forward");
 }
 

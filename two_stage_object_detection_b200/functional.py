@@ -348,7 +348,7 @@ def _pair(v):
     return (int(v), int(v)) if isinstance(v, int) else (int(v[0]), int(v[1]))
 
 
-def roi_pool_forward(feat, rois5, output_size, spatial_scale=1.0, with_argmax=False, out=None):
+def roi_pool_forward(feat, rois5, output_size, spatial_scale=1.0, with_argmax=False, out=None, rois_per_image=0):
     lib = _lib.load()
     dev = _lib.require_cuda(feat, rois5)
     f, r = f32c(feat), f32c(rois5).view(-1, 5)
@@ -361,13 +361,14 @@ def roi_pool_forward(feat, rois5, output_size, spatial_scale=1.0, with_argmax=Fa
     nbytes = lib.frcnn_roi_workspace_bytes(B, K)
     with torch.cuda.device(dev):
         ws = _lib.workspace(dev, nbytes)
-        check(lib.frcnn_roi_pool_forward(f.data_ptr(), B, Cc, H, W, r.data_ptr(), K, ph, pw,
+        check(lib.frcnn_roi_pool_forward(f.data_ptr(), B, Cc, H, W, r.data_ptr(), K, int(rois_per_image), ph, pw,
                                          float(spatial_scale), out.data_ptr(), ptr(am), ws.data_ptr(),
                                          ws.numel(), _lib.stream_ptr(dev)), "frcnn_roi_pool_forward")
     return (out, am) if with_argmax else out
 
 
-def roi_align_forward(feat, rois5, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=False, out=None):
+def roi_align_forward(feat, rois5, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=False, out=None,
+                      rois_per_image=0):
     lib = _lib.load()
     dev = _lib.require_cuda(feat, rois5)
     f, r = f32c(feat), f32c(rois5).view(-1, 5)
@@ -379,7 +380,7 @@ def roi_align_forward(feat, rois5, output_size, spatial_scale=1.0, sampling_rati
     nbytes = lib.frcnn_roi_workspace_bytes(B, K)
     with torch.cuda.device(dev):
         ws = _lib.workspace(dev, nbytes)
-        check(lib.frcnn_roi_align_forward(f.data_ptr(), B, Cc, H, W, r.data_ptr(), K, ph, pw,
+        check(lib.frcnn_roi_align_forward(f.data_ptr(), B, Cc, H, W, r.data_ptr(), K, int(rois_per_image), ph, pw,
                                           float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
                                           out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)),
               "frcnn_roi_align_forward")
@@ -388,9 +389,10 @@ def roi_align_forward(feat, rois5, output_size, spatial_scale=1.0, sampling_rati
 
 class _RoIPoolFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feat, rois5, output_size, spatial_scale):
+    def forward(ctx, feat, rois5, output_size, spatial_scale, rois_per_image):
         need = feat.requires_grad
-        res = roi_pool_forward(feat, rois5, output_size, spatial_scale, with_argmax=need)
+        res = roi_pool_forward(feat, rois5, output_size, spatial_scale, with_argmax=need,
+                               rois_per_image=rois_per_image)
         if need:
             out, am = res
             ctx.save_for_backward(am, f32c(rois5).view(-1, 5))
@@ -411,13 +413,14 @@ class _RoIPoolFn(torch.autograd.Function):
             check(lib.frcnn_roi_pool_backward(go.data_ptr(), am.data_ptr(), r.data_ptr(), r.shape[0], Cc, H, W,
                                               ctx.ps[0], ctx.ps[1], gi.data_ptr(), _lib.stream_ptr(dev)),
                   "frcnn_roi_pool_backward")
-        return gi, None, None, None
+        return gi, None, None, None, None
 
 
 class _RoIAlignFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feat, rois5, output_size, spatial_scale, sampling_ratio, aligned):
-        out = roi_align_forward(feat, rois5, output_size, spatial_scale, sampling_ratio, aligned)
+    def forward(ctx, feat, rois5, output_size, spatial_scale, sampling_ratio, aligned, rois_per_image):
+        out = roi_align_forward(feat, rois5, output_size, spatial_scale, sampling_ratio, aligned,
+                                rois_per_image=rois_per_image)
         if feat.requires_grad:
             ctx.save_for_backward(f32c(rois5).view(-1, 5))
             ctx.cfg = (tuple(feat.shape), _pair(output_size), float(spatial_scale), int(sampling_ratio),
@@ -436,18 +439,20 @@ class _RoIAlignFn(torch.autograd.Function):
             check(lib.frcnn_roi_align_backward(go.data_ptr(), r.data_ptr(), r.shape[0], Cc, H, W, ph, pw, scale,
                                                sr, al, gi.data_ptr(), _lib.stream_ptr(dev)),
                   "frcnn_roi_align_backward")
-        return gi, None, None, None, None, None
+        return gi, None, None, None, None, None, None
 
 
-def roi_pool(feat, rois5, output_size, spatial_scale=1.0):
-    """torchvision.ops.roi_pool equivalent with autograd w.r.t. ``feat``."""
+def roi_pool(feat, rois5, output_size, spatial_scale=1.0, rois_per_image=0):
+    """torchvision.ops.roi_pool equivalent with autograd w.r.t. ``feat``.  ``rois_per_image=R`` promises
+    that rows [b*R,(b+1)*R) of rois5 belong to image b (skips the device-side bucketing pass)."""
     if feat.requires_grad and torch.is_grad_enabled():
-        return _RoIPoolFn.apply(feat, rois5, output_size, spatial_scale)
-    return roi_pool_forward(feat, rois5, output_size, spatial_scale)
+        return _RoIPoolFn.apply(feat, rois5, output_size, spatial_scale, rois_per_image)
+    return roi_pool_forward(feat, rois5, output_size, spatial_scale, rois_per_image=rois_per_image)
 
 
-def roi_align(feat, rois5, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=False):
+def roi_align(feat, rois5, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=False, rois_per_image=0):
     """torchvision.ops.roi_align equivalent with autograd w.r.t. ``feat``."""
     if feat.requires_grad and torch.is_grad_enabled():
-        return _RoIAlignFn.apply(feat, rois5, output_size, spatial_scale, sampling_ratio, aligned)
-    return roi_align_forward(feat, rois5, output_size, spatial_scale, sampling_ratio, aligned)
+        return _RoIAlignFn.apply(feat, rois5, output_size, spatial_scale, sampling_ratio, aligned, rois_per_image)
+    return roi_align_forward(feat, rois5, output_size, spatial_scale, sampling_ratio, aligned,
+                             rois_per_image=rois_per_image)

@@ -3,6 +3,7 @@ and the RoIPool / RoIAlign gather run in csrc/roi_ops.cu; the classifier module 
 layers stay PyTorch, with the reference's parameter names (``cls_loc``, ``score``)."""
 from __future__ import annotations
 
+import torch
 from torch import nn
 
 from .. import functional as F
@@ -16,8 +17,8 @@ class RoIPool(nn.Module):
         self.output_size = output_size
         self.spatial_scale = spatial_scale
 
-    def forward(self, input, rois):
-        return F.roi_pool(input, rois, self.output_size, self.spatial_scale)
+    def forward(self, input, rois, rois_per_image=0):
+        return F.roi_pool(input, rois, self.output_size, self.spatial_scale, rois_per_image)
 
 
 class RoIAlign(nn.Module):
@@ -30,8 +31,9 @@ class RoIAlign(nn.Module):
         self.sampling_ratio = sampling_ratio
         self.aligned = aligned
 
-    def forward(self, input, rois):
-        return F.roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio, self.aligned)
+    def forward(self, input, rois, rois_per_image=0):
+        return F.roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio, self.aligned,
+                           rois_per_image)
 
 
 class HarNetRoIHead(nn.Module):
@@ -39,7 +41,9 @@ class HarNetRoIHead(nn.Module):
     (roi_cls_locs [n,R,4*n_class], roi_scores [n,R,n_class]).
 
     Differences from the reference, all opt-in or supersets: any R per image (the reference
-    hard-codes 128 in an expand), ``in_features`` other than 512, and ``roi_op="align"``."""
+    hard-codes 128 in an expand), ``in_features`` other than 512, ``roi_op="align"``, and
+    ``roi_indices=None`` meaning "RoI row i belongs to image i" (what the reference's callers always
+    pass, frcnn_training.py:290), which lets the gather skip its per-image bucketing pass."""
 
     def __init__(self, n_class, roi_size, spatial_scale, classifier, in_features=512, roi_op="pool",
                  sampling_ratio=-1, aligned=False):
@@ -56,9 +60,13 @@ class HarNetRoIHead(nn.Module):
 
     def gather(self, x, rois, roi_indices, img_size):
         """The hot part: coordinate map + index concat + RoI gather -> [n*R, C, P, P]."""
-        indices_and_rois = F.roi_head_coords(rois.view(x.shape[0], -1, 4), roi_indices, img_size,
-                                             (x.size()[2], x.size()[3]))
-        return self.roi(x, indices_and_rois)
+        rois = rois.view(x.shape[0], -1, 4)
+        grouped = 0
+        if roi_indices is None:
+            roi_indices = torch.arange(x.shape[0], dtype=torch.int32, device=x.device)
+            grouped = rois.shape[1]
+        indices_and_rois = F.roi_head_coords(rois, roi_indices, img_size, (x.size()[2], x.size()[3]))
+        return self.roi(x, indices_and_rois, grouped)
 
     def forward(self, x, rois, roi_indices, img_size):
         n = x.shape[0]

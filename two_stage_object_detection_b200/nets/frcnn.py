@@ -54,6 +54,8 @@ class FasterRCNN(nn.Module):
     @staticmethod
     def _image_index(roi_indices):
         # the RPN hands back one index per RoI [n,R]; the head wants one per image [n]
+        if roi_indices is None:
+            return None
         return roi_indices[:, 0].to(torch.int32) if roi_indices.dim() == 2 else roi_indices
 
     def forward(self, x, scale=1., mode="forward"):
@@ -62,7 +64,8 @@ class FasterRCNN(nn.Module):
             base_feature = self.extractor(x)
             # the proposal layer indexes img_size[1], img_size[2] (nets/rpn.py:47-48)
             _, _, rois, roi_indices, _ = self.rpn.forward(base_feature, (x.shape[1],) + tuple(img_size), scale)
-            roi_cls_locs, roi_scores = self.head.forward(base_feature, rois, self._image_index(roi_indices), img_size)
+            # our own RPN emits image i's RoIs in row i: tell the head (None) so it skips the bucketing pass
+            roi_cls_locs, roi_scores = self.head.forward(base_feature, rois, None, img_size)
             return roi_cls_locs, roi_scores, rois, roi_indices
         elif mode == "extractor":
             return self.extractor.forward(x)
