@@ -413,14 +413,19 @@ __global__ void __launch_bounds__(TAB_THREADS, 2) roi_pool_tab_kernel(RoiArgs a)
         auto one_bin = [&](int j, bool full4, bool valid) {
             const int2 h = s_th[cur][j][ph], w = s_tw[cur][j][pw];
             const int hy = h.y & TAB_OFF_MASK, wy = w.y & TAB_OFF_MASK;
-            // lookups that coincide are skipped when no lane of the warp needs them
-            const bool wide = __any_sync(0xFFFFFFFFu, w.x != wy);
-            const bool tall = __any_sync(0xFFFFFFFFu, h.x != hy);
+            // lookups that coincide with the first one are skipped: warp-uniformly when no lane needs
+            // them (saves the issue slots), per lane otherwise (idle lanes cost no LSU wavefronts)
+            const bool wide = w.x != wy, tall = h.x != hy;
+            const bool any_wide = __any_sync(0xFFFFFFFFu, wide), any_tall = __any_sync(0xFFFFFFFFu, tall);
             float4 v = *reinterpret_cast<const float4*>(smem_raw + (w.x + h.x));
-            if (wide) v = max4(v, *reinterpret_cast<const float4*>(smem_raw + (wy + h.x)));
-            if (tall) {
-                v = max4(v, *reinterpret_cast<const float4*>(smem_raw + (w.x + hy)));
-                if (wide) v = max4(v, *reinterpret_cast<const float4*>(smem_raw + (wy + hy)));
+            if (any_wide) {
+                if (wide) v = max4(v, *reinterpret_cast<const float4*>(smem_raw + (wy + h.x)));
+            }
+            if (any_tall) {
+                if (tall) v = max4(v, *reinterpret_cast<const float4*>(smem_raw + (w.x + hy)));
+                if (any_wide) {
+                    if (wide && tall) v = max4(v, *reinterpret_cast<const float4*>(smem_raw + (wy + hy)));
+                }
             }
             const bool big = ((h.y | w.y) & TAB_BIG_BIT) != 0;
             if (__any_sync(0xFFFFFFFFu, big)) {
