@@ -264,10 +264,14 @@ def run_ours(args):
     alg_bytes = K * C * P * P * 4 + K * 20 + B * C * H * W * 4
     achieved = alg_bytes / (roi_ms * 1e-3) / 1e9
     rows = min(cfg["n_pre"], N)
-    sblock = min(max(-(-2 * n_post // 256) * 256, 256), 2048, -(-rows // 256) * 256)  # csrc/proposals.cu
-    n_sb = -(-rows // sblock)
+    # NMS super-block schedule of csrc/proposals.cu (run_nms_sorted): first block ~2*n_post, then doubling
+    need = -(-rows // 256) * 256
+    s0 = min(max(-(-2 * n_post // 256) * 256, 256), 2048, need)
+    smax = max(s0, min(2048, need))
+    n_sb, c0, ln = 0, 0, s0
+    while c0 < rows:
+        n_sb, c0, ln = n_sb + 1, c0 + ln, min(2 * ln, smax)
     launches = 1 + 1 + 2 * n_sb + 1 + 1 + 1  # decode, topk, nms(mask+scan)*sb, finalize, coords, gather
-
     kernel_name = "roi_pool_tab_kernel<14,392>" if (cfg["op"], P) == ("pool", 14) else (
         "roi_pool_tab_kernel<7,392>" if cfg["op"] == "pool" else "roi_align_staged_kernel")
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from one ncu --set full capture

@@ -11,6 +11,8 @@
 //   finalize          pad-with-arange / truncate / gather (nets/rpn.py:65-69)
 #include <cooperative_groups.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace frcnn {
@@ -89,6 +91,9 @@ __global__ void scores_to_keys_kernel(const float* __restrict__ s, int n, uint32
 constexpr int TK_CL = 8;
 constexpr int TK_THREADS = 512;
 constexpr int TK_WARPS = TK_THREADS / 32;
+constexpr int TK_E = 4;                          // keys per thread per round
+constexpr int TK_ROUND = TK_E * TK_THREADS;      // keys per CTA per round (2048)
+constexpr size_t TK_SMEM = sizeof(uint32_t) * TK_E * TK_WARPS * 256;  // per-(chunk,warp) digit counters
 
 __global__ void __cluster_dims__(TK_CL, 1, 1) __launch_bounds__(TK_THREADS)
 topk_sort_kernel(const uint32_t* __restrict__ keys_all, const float4* __restrict__ boxes_all, int n,
@@ -97,11 +102,11 @@ topk_sort_kernel(const uint32_t* __restrict__ keys_all, const float4* __restrict
                  float4* __restrict__ sorted_all) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    __shared__ uint32_t hist[256];  // this CTA's digit counts (read by the whole cluster)
-    __shared__ uint32_t offs[256];  // running destination offsets of this CTA
-    __shared__ uint32_t warp_cnt[TK_WARPS][256];
+    extern __shared__ uint32_t cnt[];  // [TK_E][TK_WARPS][256]: digit counts, then exclusive prefixes
+    __shared__ uint32_t hist[256];     // this CTA's digit totals (read by the whole cluster)
+    __shared__ uint32_t offs[256];     // running destination offsets of this CTA
     __shared__ uint32_t warp_tot[8];
-    __shared__ uint32_t s_nzero;    // filtered (key == 0) anchors in this CTA's segment
+    __shared__ uint32_t s_nzero;       // filtered (key == 0) anchors in this CTA's segment
 
     const int crank = (int)cluster.block_rank();
     const int b = blockIdx.x / TK_CL;
@@ -112,27 +117,98 @@ topk_sort_kernel(const uint32_t* __restrict__ keys_all, const float4* __restrict
     const uint32_t lt = lanemask_lt();
     const int seg = (n + TK_CL - 1) / TK_CL;
     const int lo = min(crank * seg, n), hi = min(lo + seg, n);
+    const int rounds = (seg + TK_ROUND - 1) / TK_ROUND;  // same in every CTA of the cluster
 
     if (tid == 0) s_nzero = 0;
     int cur = -1;  // -1: data still in `keys` (identity permutation)
+
+    uint32_t k[TK_E], id[TK_E], rank[TK_E];
+    bool valid[TK_E];
+    // one round = TK_E chunks of TK_THREADS consecutive keys; order inside the CTA = (chunk, warp, lane)
+    auto load_round = [&](int r0, const uint32_t* srcK, const uint32_t* srcI) {
+#pragma unroll
+        for (int e = 0; e < TK_E; ++e) {
+            const int i = r0 + e * TK_THREADS + tid;
+            valid[e] = i < hi;
+            k[e] = 0;
+            id[e] = (uint32_t)i;
+            if (valid[e]) {
+                if (srcK) {  // written by other SMs in the previous pass: read through L2
+                    k[e] = __ldcg(srcK + i);
+                    id[e] = __ldcg(srcI + i);
+                } else {
+                    k[e] = ~__ldg(keys + i);
+                }
+            }
+        }
+    };
+    // per-(chunk,warp) digit counts into cnt, per-key rank among equal digits of its warp
+    auto count_round = [&](int shift) {
+        for (int j = lane; j < TK_E * 256; j += 32) cnt[((j >> 8) * TK_WARPS + warp) * 256 + (j & 255)] = 0;
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < TK_E; ++e) {
+            const uint32_t d = valid[e] ? ((k[e] >> shift) & 255u) : 256u;
+            const uint32_t m = __match_any_sync(0xFFFFFFFFu, d);
+            rank[e] = __popc(m & lt);
+            if (valid[e] && rank[e] == 0) cnt[(e * TK_WARPS + warp) * 256 + d] = __popc(m);
+        }
+    };
+    // thread d < 256: turn the counts of digit d into exclusive prefixes, return their sum
+    auto scan_round = [&]() -> uint32_t {
+        uint32_t run = 0;
+#pragma unroll 16
+        for (int j = 0; j < TK_E * TK_WARPS; ++j) {
+            const uint32_t c = cnt[j * 256 + tid];
+            cnt[j * 256 + tid] = run;
+            run += c;
+        }
+        return run;
+    };
+    auto scatter_round = [&](int shift, uint32_t* dstK, uint32_t* dstI) {
+#pragma unroll
+        for (int e = 0; e < TK_E; ++e) {
+            if (valid[e]) {
+                const uint32_t d = (k[e] >> shift) & 255u;
+                const uint32_t pos = offs[d] + cnt[(e * TK_WARPS + warp) * 256 + d] + rank[e];
+                dstK[pos] = k[e];
+                dstI[pos] = id[e];
+            }
+        }
+    };
 
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 8 * pass;
         const uint32_t* srcK = cur < 0 ? nullptr : bufK0 + (size_t)cur * n;
         const uint32_t* srcI = cur < 0 ? nullptr : bufI0 + (size_t)cur * n;
-        if (tid < 256) hist[tid] = 0;
-        __syncthreads();
-        for (int base = lo; base < hi; base += TK_THREADS) {
-            int i = base + tid;
-            bool valid = i < hi;
-            uint32_t k = 0;
-            if (valid) k = srcK ? __ldcg(srcK + i) : ~__ldg(keys + i);
-            uint32_t d = valid ? ((k >> shift) & 255u) : 256u;
-            uint32_t m = __match_any_sync(0xFFFFFFFFu, d);
-            if (valid && (m & lt) == 0) atomicAdd(&hist[d], (uint32_t)__popc(m));
+        // ---- this CTA's digit histogram ----
+        if (rounds == 1) {
+            load_round(lo, srcK, srcI);
+            count_round(shift);
             if (pass == 0) {
-                uint32_t z = __ballot_sync(0xFFFFFFFFu, valid && k == 0xFFFFFFFFu);
-                if (lane == 0 && z) atomicAdd(&s_nzero, (uint32_t)__popc(z));
+#pragma unroll
+                for (int e = 0; e < TK_E; ++e) {
+                    uint32_t z = __ballot_sync(0xFFFFFFFFu, valid[e] && k[e] == 0xFFFFFFFFu);
+                    if (lane == 0 && z) atomicAdd(&s_nzero, (uint32_t)__popc(z));
+                }
+            }
+            __syncthreads();
+            if (tid < 256) hist[tid] = scan_round();
+        } else {
+            if (tid < 256) hist[tid] = 0;
+            __syncthreads();
+            for (int r = 0; r < rounds; ++r) {
+                load_round(lo + r * TK_ROUND, srcK, srcI);
+#pragma unroll
+                for (int e = 0; e < TK_E; ++e) {
+                    const uint32_t d = valid[e] ? ((k[e] >> shift) & 255u) : 256u;
+                    const uint32_t m = __match_any_sync(0xFFFFFFFFu, d);
+                    if (valid[e] && (m & lt) == 0) atomicAdd(&hist[d], (uint32_t)__popc(m));
+                    if (pass == 0) {
+                        uint32_t z = __ballot_sync(0xFFFFFFFFu, valid[e] && k[e] == 0xFFFFFFFFu);
+                        if (lane == 0 && z) atomicAdd(&s_nzero, (uint32_t)__popc(z));
+                    }
+                }
             }
         }
         cluster.sync();  // all eight histograms complete
@@ -148,7 +224,7 @@ topk_sort_kernel(const uint32_t* __restrict__ keys_all, const float4* __restrict
         // identical in every CTA of the cluster, so the whole cluster takes the same branch
         int trivial = __syncthreads_or(tid < 256 && total == (uint32_t)n);
         if (trivial) {
-            cluster.sync();  // remote reads of hist are done before the next pass clears it
+            cluster.sync();  // remote reads of hist are done before the next pass rewrites it
             continue;
         }
         uint32_t incl = total;
@@ -167,47 +243,27 @@ topk_sort_kernel(const uint32_t* __restrict__ keys_all, const float4* __restrict
             offs[tid] = before + incl - total + pre;
         }
         __syncthreads();
+        // ---- stable scatter into the other ping-pong buffer ----
         const int dst = cur < 0 ? 0 : (cur ^ 1);
         uint32_t* dstK = bufK0 + (size_t)dst * n;
         uint32_t* dstI = bufI0 + (size_t)dst * n;
-        for (int base = lo; base < hi; base += TK_THREADS) {
-            int i = base + tid;
-            bool valid = i < hi;
-            uint32_t k = 0, id = (uint32_t)i;
-            if (valid) {
-                if (srcK) {  // written by other SMs in the previous pass: read through L2
-                    k = __ldcg(srcK + i);
-                    id = __ldcg(srcI + i);
-                } else {
-                    k = ~__ldg(keys + i);
-                }
-            }
-            uint32_t d = valid ? ((k >> shift) & 255u) : 256u;
-            __syncwarp();
-            for (int j = lane; j < 256; j += 32) warp_cnt[warp][j] = 0;
-            __syncwarp();
-            uint32_t m = __match_any_sync(0xFFFFFFFFu, d);
-            uint32_t rank = __popc(m & lt);
-            if (valid && rank == 0) warp_cnt[warp][d] = __popc(m);
-            __syncthreads();
-            if (tid < 256) {
-                uint32_t run = offs[tid];
-#pragma unroll
-                for (int w = 0; w < TK_WARPS; ++w) {
-                    uint32_t c = warp_cnt[w][tid];
-                    warp_cnt[w][tid] = run;
-                    run += c;
-                }
-                offs[tid] = run;
-            }
-            __syncthreads();
-            if (valid) {
-                uint32_t pos = warp_cnt[warp][d] + rank;
-                dstK[pos] = k;
-                dstI[pos] = id;
+        if (rounds == 1) {
+            scatter_round(shift, dstK, dstI);  // keys, ranks and prefixes are still live
+        } else {
+            for (int r = 0; r < rounds; ++r) {
+                load_round(lo + r * TK_ROUND, srcK, srcI);
+                __syncthreads();  // previous round's scatter has read cnt / offs
+                count_round(shift);
+                __syncthreads();
+                uint32_t run = 0;
+                if (tid < 256) run = scan_round();
+                __syncthreads();
+                scatter_round(shift, dstK, dstI);
+                __syncthreads();
+                if (tid < 256) offs[tid] += run;
             }
         }
-        cluster.sync();  // scatter visible cluster-wide; hist may be cleared again
+        cluster.sync();  // scatter visible cluster-wide; hist may be rewritten
         cur = dst;
     }
     uint32_t nzero = 0;
@@ -219,12 +275,12 @@ topk_sort_kernel(const uint32_t* __restrict__ keys_all, const float4* __restrict
     int* order = order_all + (size_t)b * k_cap;
     const uint32_t* finI = cur < 0 ? nullptr : bufI0 + (size_t)cur * n;
     for (int j = crank * TK_THREADS + tid; j < k_cap; j += TK_CL * TK_THREADS) {
-        int id = -1;
-        if (j < n_sel) id = finI ? (int)__ldcg(finI + j) : j;
-        order[j] = id;
+        int idx = -1;
+        if (j < n_sel) idx = finI ? (int)__ldcg(finI + j) : j;
+        order[j] = idx;
         if (sorted_all) {
             float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (id >= 0) bx = __ldg(boxes_all + (size_t)b * n + id);
+            if (idx >= 0) bx = __ldg(boxes_all + (size_t)b * n + idx);
             sorted_all[(size_t)b * k_cap + j] = bx;
         }
     }
@@ -258,7 +314,9 @@ __device__ __forceinline__ bool nms_suppresses(const float4& r, float ra, const 
 struct NmsArgs {
     const float4* boxes;   // [B,row_stride]
     const int* n_sel;      // [B]
-    int row_stride, S, sb, keep_cap;
+    int row_stride, keep_cap;
+    int S;                 // mask row stride = largest super-block
+    int c0, len;           // current super-block: sorted positions [c0, c0+len)
     float thr;
     uint32_t* mask;        // [B][S/32][S]
     uint32_t* removed;     // [B][S/32]
@@ -276,9 +334,9 @@ __global__ void __launch_bounds__(NMS_CB) nms_mask_kernel(NmsArgs a) {
     const NmsState st = a.state[b];
     if (st.done) return;
     const int n = a.n_sel[b];
-    const int c0 = a.sb * a.S;
+    const int c0 = a.c0;
     if (c0 >= n) return;
-    const int c1 = min(c0 + a.S, n);
+    const int c1 = min(c0 + a.len, n);
     const float4* boxes = a.boxes + (size_t)b * a.row_stride;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int t = blockIdx.x;
@@ -314,7 +372,7 @@ __global__ void __launch_bounds__(NMS_CB) nms_mask_kernel(NmsArgs a) {
     } else {
         // suppression by boxes kept in earlier super-blocks
         t -= a.tri_tiles;
-        int ncb = a.S / NMS_CB;
+        int ncb = a.len / NMS_CB;
         int cb = t % ncb, kc = t / ncb;
         int k0 = kc * NMS_KC;
         if (k0 >= st.n_kept) return;
@@ -341,68 +399,65 @@ __global__ void __launch_bounds__(NMS_CB) nms_mask_kernel(NmsArgs a) {
     }
 }
 
-constexpr int NMS_SCAN_THREADS = 512;
 constexpr int NMS_MAX_WORDS = 256;  // S <= 8192
 
-__global__ void __launch_bounds__(NMS_SCAN_THREADS) nms_scan_kernel(NmsArgs a) {
-    __shared__ uint32_t R[NMS_MAX_WORDS];      // removed bits of this super-block
-    __shared__ uint32_t Kb[NMS_MAX_WORDS];     // kept bits of this super-block
-    __shared__ uint32_t partial[NMS_SCAN_THREADS / 32];
+// One CTA per image, one thread per 32-candidate column word t of the super-block.  Step u resolves
+// the 32 candidates of block u in warp 0 (serial over the 32 bits, diagonal mask word per lane), then
+// every thread t > u ORs the mask rows of the newly kept candidates into its removed word R[t].  The
+// 32 mask words thread t needs for step u+1 (M[t][32(u+1)..]) do not depend on the outcome of step u,
+// so they are loaded one step ahead and their latency hides behind the resolve.
+__global__ void __launch_bounds__(NMS_MAX_WORDS) nms_scan_kernel(NmsArgs a) {
+    __shared__ uint32_t R[NMS_MAX_WORDS];  // removed bits of this super-block
+    __shared__ uint32_t s_kb;
     __shared__ int s_nkept, s_done;
     const int b = blockIdx.x;
     NmsState st = a.state[b];
     if (st.done) return;
     const int n = a.n_sel[b];
-    const int c0 = a.sb * a.S;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = a.c0;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (c0 >= n) {
-        if (tid == 0) {
+        if (t == 0) {
             a.state[b].done = 1;
             a.n_keep[b] = st.n_kept;
         }
         return;
     }
-    const int c1 = min(c0 + a.S, n);
+    const int c1 = min(c0 + a.len, n);
     const int ncol = c1 - c0, nw = (ncol + 31) / 32;
     const float4* boxes = a.boxes + (size_t)b * a.row_stride;
     uint32_t* removed = a.removed + (size_t)b * (a.S / 32);
     const uint32_t* mask = a.mask + (size_t)b * (a.S / 32) * a.S;
-    for (int j = tid; j < a.S / 32; j += NMS_SCAN_THREADS) {
-        uint32_t v = removed[j];
-        removed[j] = 0;  // ready for the next super-block
-        if (j == nw - 1 && (ncol & 31)) v |= ~0u << (ncol & 31);
-        R[j] = v;
-        Kb[j] = 0;
+    if (t < a.S / 32) {
+        uint32_t v = removed[t];
+        removed[t] = 0;  // ready for the next super-block
+        if (t == nw - 1 && (ncol & 31)) v |= ~0u << (ncol & 31);
+        R[t] = v;
     }
-    if (tid == 0) {
+    if (t == 0) {
         s_nkept = st.n_kept;
         s_done = 0;
     }
-    __syncthreads();
-    // software pipeline: the column-w words M[w][0..32w) are loaded one step ahead
-    const int rows_per_iter = NMS_SCAN_THREADS * 4;
-    for (int w = 0; w < nw; ++w) {
-        // (1) R[w] |= OR over kept rows r < 32w of M[w][r]
-        uint32_t acc = 0;
-        const uint32_t* mcol = mask + (size_t)w * a.S;
-        for (int r4 = tid * 4; r4 < 32 * w; r4 += rows_per_iter) {
-            uint4 m = *reinterpret_cast<const uint4*>(mcol + r4);
-            uint32_t sel = Kb[r4 >> 5] >> (r4 & 31);
-            acc |= (sel & 1u) ? m.x : 0u;
-            acc |= (sel & 2u) ? m.y : 0u;
-            acc |= (sel & 4u) ? m.z : 0u;
-            acc |= (sel & 8u) ? m.w : 0u;
+    const uint32_t* mine = mask + (size_t)t * a.S;  // rows of my column word
+    uint4 m[8];
+    auto prefetch = [&](int u) {
+        if (t > u && t < nw) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) m[q] = __ldcg(reinterpret_cast<const uint4*>(mine + 32 * u) + q);
         }
-        acc = __reduce_or_sync(0xFFFFFFFFu, acc);
-        if (lane == 0) partial[warp] = acc;
-        __syncthreads();
-        // (2) warp 0 resolves the 32 candidates of block w
+    };
+    auto diag = [&](int u) -> uint32_t {  // warp 0: which later candidates of block u does row 32u+lane suppress
+        int row = 32 * u + lane;
+        uint32_t d = (u < nw && row < ncol) ? __ldcg(mask + (size_t)u * a.S + row) : 0u;
+        return d & ~((2u << lane) - 1u);
+    };
+    prefetch(0);
+    uint32_t D = warp == 0 ? diag(0) : 0u;
+    __syncthreads();
+    for (int u = 0; u < nw; ++u) {
         if (warp == 0) {
-            uint32_t pv = lane < NMS_SCAN_THREADS / 32 ? partial[lane] : 0u;
-            uint32_t rw = R[w] | __reduce_or_sync(0xFFFFFFFFu, pv);
-            int row = 32 * w + lane;
-            uint32_t D = (row < ncol) ? mcol[row] : 0u;
-            D &= ~((2u << lane) - 1u);  // only later candidates can be suppressed
+            const uint32_t Dn = diag(u + 1);  // in flight during the resolve
+            uint32_t rw = R[u];
             uint32_t kb = 0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -412,6 +467,7 @@ __global__ void __launch_bounds__(NMS_SCAN_THREADS) nms_scan_kernel(NmsArgs a) {
                     rw |= di;
                 }
             }
+            D = Dn;
             int nk = s_nkept;
             int room = a.keep_cap - nk;
             int cnt = __popc(kb);
@@ -423,19 +479,34 @@ __global__ void __launch_bounds__(NMS_SCAN_THREADS) nms_scan_kernel(NmsArgs a) {
             }
             if ((kb >> lane) & 1u) {
                 int pos = nk + __popc(kb & ((1u << lane) - 1u));
-                a.keep[(size_t)b * a.keep_cap + pos] = c0 + row;
-                a.kept_box[(size_t)b * a.keep_cap + pos] = __ldg(boxes + c0 + row);
+                int row = c0 + 32 * u + lane;
+                a.keep[(size_t)b * a.keep_cap + pos] = row;
+                a.kept_box[(size_t)b * a.keep_cap + pos] = __ldg(boxes + row);
             }
             if (lane == 0) {
-                Kb[w] = kb;
+                s_kb = kb;
                 s_nkept = nk + cnt;
                 if (done) s_done = 1;
             }
         }
         __syncthreads();
         if (s_done) break;
+        if (t > u && t < nw) {
+            const uint32_t kb = s_kb;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                acc |= ((kb >> (4 * q)) & 1u) ? m[q].x : 0u;
+                acc |= ((kb >> (4 * q + 1)) & 1u) ? m[q].y : 0u;
+                acc |= ((kb >> (4 * q + 2)) & 1u) ? m[q].z : 0u;
+                acc |= ((kb >> (4 * q + 3)) & 1u) ? m[q].w : 0u;
+            }
+            R[t] |= acc;
+        }
+        prefetch(u + 1);
+        __syncthreads();
     }
-    if (tid == 0) {
+    if (t == 0) {
         int done = s_done || (c1 >= n);
         a.state[b].n_kept = s_nkept;
         a.state[b].done = done;
@@ -510,9 +581,16 @@ struct NmsLayout {
     size_t mask_words, removed_words;
 };
 
+static int max_superblock(int requested, int n_rows, int keep_cap) {
+    int s0 = pick_superblock(requested, n_rows, keep_cap);
+    if (requested > 0) return s0;
+    int need = (n_rows + NMS_CB - 1) / NMS_CB * NMS_CB;
+    return std::max(s0, std::min(2048, need));
+}
+
 static size_t nms_ws_layout(Workspace& ws, int batch, int n_rows, int keep_cap, int superblock,
                             NmsArgs* a) {
-    int S = pick_superblock(superblock, n_rows, keep_cap);
+    int S = max_superblock(superblock, n_rows, keep_cap);
     uint32_t* mask = ws.take<uint32_t>((size_t)batch * (S / 32) * S);
     // state + removed are cleared together by one memset
     size_t clear_bytes = align_up((size_t)batch * sizeof(NmsState)) + align_up((size_t)batch * (S / 32) * 4);
@@ -548,17 +626,23 @@ static int run_nms_sorted(const float* sorted_boxes, const int32_t* n_sel, int b
     a.keep = keep;
     a.n_keep = n_keep;
     FRCNN_CUDA(cudaMemsetAsync(a.state, 0, clear_bytes, stream));
-    int ncb = a.S / NMS_CB;
-    a.tri_tiles = 2 * ncb * (ncb + 1);
-    int n_sb = cdiv(row_stride, a.S);
-    int prev_tiles = ncb * cdiv(keep_cap, NMS_KC);
-    for (int sb = 0; sb < n_sb; ++sb) {
-        a.sb = sb;
-        dim3 grid(a.tri_tiles + (sb > 0 ? prev_tiles : 0), batch);
+    // super-block schedule: the first block is sized for keep_cap (pick_superblock); later blocks double
+    // up to the mask stride, so a run that finishes early launches few no-op kernels
+    const int s0 = pick_superblock(superblock, row_stride, keep_cap);
+    int c0 = 0, len = s0;
+    while (c0 < row_stride) {
+        a.c0 = c0;
+        a.len = len;
+        int ncb = len / NMS_CB;
+        a.tri_tiles = 2 * ncb * (ncb + 1);
+        int prev_tiles = c0 > 0 ? ncb * cdiv(keep_cap, NMS_KC) : 0;
+        dim3 grid(a.tri_tiles + prev_tiles, batch);
         nms_mask_kernel<<<grid, NMS_CB, 0, stream>>>(a);
         FRCNN_LAUNCH_CHECK();
-        nms_scan_kernel<<<batch, NMS_SCAN_THREADS, 0, stream>>>(a);
+        nms_scan_kernel<<<batch, std::max(32, (len / 32 + 31) / 32 * 32), 0, stream>>>(a);
         FRCNN_LAUNCH_CHECK();
+        c0 += len;
+        if (superblock <= 0) len = std::min(2 * len, a.S);
     }
     return FRCNN_OK;
 }
@@ -573,8 +657,9 @@ static int run_topk(const uint32_t* keys, const float* boxes, int batch, int n, 
         set_error("topk: workspace too small or misaligned (%zu needed, %zu given)", ws.off, workspace_bytes);
         return FRCNN_ERR_WORKSPACE;
     }
-    topk_sort_kernel<<<batch * TK_CL, TK_THREADS, 0, stream>>>(keys, (const float4*)boxes, n, k_cap, wk, wi, order,
-                                                               n_sel, (float4*)sorted_boxes);
+    FRCNN_CUDA(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TK_SMEM));
+    topk_sort_kernel<<<batch * TK_CL, TK_THREADS, TK_SMEM, stream>>>(keys, (const float4*)boxes, n, k_cap, wk, wi,
+                                                                     order, n_sel, (float4*)sorted_boxes);
     FRCNN_LAUNCH_CHECK();
     return FRCNN_OK;
 }
