@@ -12,7 +12,7 @@ import threading
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libfrcnn_b200.so")
+LIB_PATH = os.environ.get("FRCNN_B200_LIB") or os.path.join(_PKG, "libfrcnn_b200.so")
 ABI_VERSION = 1
 MAX_BASE_ANCHORS = 64
 

@@ -278,13 +278,53 @@ __global__ void __launch_bounds__(ROI_THREADS, 2) roi_pool_staged_kernel(RoiArgs
 // not the lookups, bounds this kernel).  Per-RoI bin geometry is precomputed for a batch of RoIs into
 // shared-memory tables (one entry per thread), and the next batch's RoI boxes are prefetched.
 // ---------------------------------------------------------------------------------------------
-constexpr int TAB_CS = 4;
 constexpr int TAB_NE_BIT = 0x80000000;   // entry .y bit 31: bin row / column is non-empty
 constexpr int TAB_BIG_BIT = 0x40000000;  // entry .y bit 30: longer than 4 -> loop path
 constexpr int TAB_OFF_MASK = 0x3FFFFFFF;
 
-__device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
+// CS channel-interleaved floats per pixel: float4 (LDS.128) for CS = 4, float2 (LDS.64) for CS = 2.
+// Native vector types on purpose: a struct-of-array wrapper made ptxas split the predicated loads.
+template <int CS>
+struct VecT;
+template <>
+struct VecT<4> {
+    typedef float4 type;
+};
+template <>
+struct VecT<2> {
+    typedef float2 type;
+};
+__device__ __forceinline__ float4 vmax(const float4& a, const float4& b) {
     return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+__device__ __forceinline__ float2 vmax(const float2& a, const float2& b) {
+    return make_float2(fmaxf(a.x, b.x), fmaxf(a.y, b.y));
+}
+__device__ __forceinline__ void vsplat(float4& v, float x) { v = make_float4(x, x, x, x); }
+__device__ __forceinline__ void vsplat(float2& v, float x) { v = make_float2(x, x); }
+// planes -> interleaved pixel, clamped with fmaxf(., -FLT_MAX); channels >= cs read as -FLT_MAX
+__device__ __forceinline__ void vgather(float4& v, const float* raw, int HW, int p, int cs) {
+    v.x = fmaxf(raw[p], -FLT_MAX);
+    v.y = cs > 1 ? fmaxf(raw[HW + p], -FLT_MAX) : -FLT_MAX;
+    v.z = cs > 2 ? fmaxf(raw[2 * HW + p], -FLT_MAX) : -FLT_MAX;
+    v.w = cs > 3 ? fmaxf(raw[3 * HW + p], -FLT_MAX) : -FLT_MAX;
+}
+__device__ __forceinline__ void vgather(float2& v, const float* raw, int HW, int p, int cs) {
+    v.x = fmaxf(raw[p], -FLT_MAX);
+    v.y = cs > 1 ? fmaxf(raw[HW + p], -FLT_MAX) : -FLT_MAX;
+}
+// masked store of the channels of one bin (stride = P*P floats between channels)
+template <bool FULL>
+__device__ __forceinline__ void vstore(float* o, int stride, const float4& v, unsigned m, int cs) {
+    o[0] = __uint_as_float(__float_as_uint(v.x) & m);
+    if (FULL || cs > 1) o[stride] = __uint_as_float(__float_as_uint(v.y) & m);
+    if (FULL || cs > 2) o[2 * stride] = __uint_as_float(__float_as_uint(v.z) & m);
+    if (FULL || cs > 3) o[3 * stride] = __uint_as_float(__float_as_uint(v.w) & m);
+}
+template <bool FULL>
+__device__ __forceinline__ void vstore(float* o, int stride, const float2& v, unsigned m, int cs) {
+    o[0] = __uint_as_float(__float_as_uint(v.x) & m);
+    if (FULL || cs > 1) o[stride] = __uint_as_float(__float_as_uint(v.y) & m);
 }
 
 struct RoiBox {
@@ -307,11 +347,11 @@ __device__ __forceinline__ RoiBox load_roi(const RoiArgs& a, int r, int r_end) {
     return q;
 }
 
-// One axis of the bin grid: [lo,hi) of bin `i`, as (offset of first corner, offset of second corner
-// | flags); `unit` = table elements per step along this axis (W for rows, 1 for columns), `tsel` =
-// table stride selected by a 2-long window along this axis.
+// One axis of the bin grid: [lo,hi) of bin `i`, as (byte offset of first corner, byte offset of second
+// corner | flags); `unit` = table elements per step along this axis (W for rows, 1 for columns), `tsel`
+// = table stride selected by a 2-long window along this axis, `esz` = bytes per table element.
 __device__ __forceinline__ int2 tab_entry(int i, int P, float c1, float c2, float scale, int limit, int unit,
-                                          int tsel, int* raw) {
+                                          int tsel, int esz, int* raw) {
     const int s = round_half_away(c1 * scale), e = round_half_away(c2 * scale);
     const float bin = (float)max(e - s + 1, 1) / (float)P;
     const int lo = min(max((int)floorf((float)i * bin) + s, 0), limit);
@@ -322,22 +362,26 @@ __device__ __forceinline__ int2 tab_entry(int i, int P, float c1, float c2, floa
     const int a = min(max(len, 1), 2);
     const int lo_ = empty ? 0 : lo, hi_ = empty ? a : hi;
     int2 r;
-    r.x = ((a - 1) * tsel + lo_ * unit) * 16;
-    r.y = (((a - 1) * tsel + (hi_ - a) * unit) * 16) | (empty ? 0 : TAB_NE_BIT) | (len > 4 ? TAB_BIG_BIT : 0);
+    r.x = ((a - 1) * tsel + lo_ * unit) * esz;
+    r.y = (((a - 1) * tsel + (hi_ - a) * unit) * esz) | (empty ? 0 : TAB_NE_BIT) | (len > 4 ? TAB_BIG_BIT : 0);
     return r;
 }
 
-// Loop path for one bin longer than 4 in some direction (kept out of line: it is rare and would
-// otherwise bloat the unrolled fast path).
-__device__ __noinline__ float4 tab_big_bin(const float4* tab, int hr, int wr, int W) {
-    float4 v = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+// Loop path for one bin longer than 4 in some direction.  Deliberately tiny and out of line: the call
+// sits inside the unrolled fast loop, and a larger callee (e.g. one tiling the bin with 2 x 2 table
+// windows) raises the register pressure at every call site enough to cost the fast path 6 % (measured).
+template <typename V>
+__device__ __noinline__ V tab_big_bin(const V* tab, int hr, int wr, int W) {
+    V v;
+    vsplat(v, -FLT_MAX);
     for (int y = hr & 0xFFFF; y < (hr >> 16); ++y)
-        for (int x = wr & 0xFFFF; x < (wr >> 16); ++x) v = max4(v, tab[y * W + x]);
+        for (int x = wr & 0xFFFF; x < (wr >> 16); ++x) v = vmax(v, tab[y * W + x]);
     return v;
 }
 
-template <int P, int TAB_THREADS>
-__global__ void __launch_bounds__(TAB_THREADS, 2) roi_pool_tab_kernel(RoiArgs a) {
+template <int P, int TAB_THREADS, int CS, int MINB>
+__global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs a) {
+    typedef typename VecT<CS>::type V;
     constexpr int BINS = P * P;
     constexpr int RPI = TAB_THREADS / BINS;      // RoIs per iteration (2 or 8)
     constexpr int NB = TAB_THREADS / P;          // RoIs per batch: two table entries per thread (28 or 56)
@@ -347,12 +391,12 @@ __global__ void __launch_bounds__(TAB_THREADS, 2) roi_pool_tab_kernel(RoiArgs a)
     __shared__ __align__(8) uint64_t bar;
     __shared__ int2 s_th[2][NB][P], s_tw[2][NB][P];  // per RoI: row / column corner offsets + flags
     __shared__ int s_hraw[2][NB][P], s_wraw[2][NB][P];
-    __shared__ size_t s_ob[2][NB];                   // per RoI: byte offset of its [4,P,P] output block
-    float4* tab = reinterpret_cast<float4*>(smem_raw);
+    __shared__ size_t s_ob[2][NB];                   // per RoI: byte offset of its [CS,P,P] output block
+    V* tab = reinterpret_cast<V*>(smem_raw);
     const int H = a.H, W = a.W, HW = H * W, HWp = (HW + 3) & ~3;
     const int b = blockIdx.z;
-    const int c0 = blockIdx.y * TAB_CS;
-    const int cs = min(TAB_CS, a.C - c0);
+    const int c0 = blockIdx.y * CS;
+    const int cs = min(CS, a.C - c0);
     int r_begin, r_end;
     roi_range(a, b, r_begin, r_end);
     const int stride = a.groups * NB;
@@ -366,34 +410,34 @@ __global__ void __launch_bounds__(TAB_THREADS, 2) roi_pool_tab_kernel(RoiArgs a)
     float* raw = reinterpret_cast<float*>(tab + 3 * HWp);  // [cs][HW], lives where T22 will be
     stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
     for (int p = tid; p < HW; p += TAB_THREADS) {
-        float4 v;
-        v.x = fmaxf(raw[p], -FLT_MAX);
-        v.y = cs > 1 ? fmaxf(raw[HW + p], -FLT_MAX) : -FLT_MAX;
-        v.z = cs > 2 ? fmaxf(raw[2 * HW + p], -FLT_MAX) : -FLT_MAX;
-        v.w = cs > 3 ? fmaxf(raw[3 * HW + p], -FLT_MAX) : -FLT_MAX;
+        V v;
+        vgather(v, raw, HW, p, cs);
         tab[p] = v;
     }
     __syncthreads();
     for (int p = tid; p < HW; p += TAB_THREADS) {
         int y = p / W, x = p - y * W;
         int pr = x + 1 < W ? p + 1 : p, pd = y + 1 < H ? p + W : p;
-        float4 v = tab[p];
-        tab[HWp + p] = max4(v, tab[pr]);      // 1 x 2
-        tab[2 * HWp + p] = max4(v, tab[pd]);  // 2 x 1
+        V v = tab[p];
+        tab[HWp + p] = vmax(v, tab[pr]);      // 1 x 2
+        tab[2 * HWp + p] = vmax(v, tab[pd]);  // 2 x 1
     }
     __syncthreads();
     for (int p = tid; p < HW; p += TAB_THREADS) {
         int y = p / W;
         int pd = y + 1 < H ? p + W : p;
-        tab[3 * HWp + p] = max4(tab[HWp + p], tab[HWp + pd]);  // 2 x 2
+        tab[3 * HWp + p] = vmax(tab[HWp + p], tab[HWp + pd]);  // 2 x 2
     }
 
     // compute role: bin e = (ph,pw) of the (tid / BINS)-th RoI of each iteration
     const int e = tid % BINS, ej = tid / BINS;
     const int ph = e / P, pw = e % P;
     auto fill_tables = [&](int buf, int j, const RoiBox& q) {
-        if (ti < P) s_th[buf][j][ti] = tab_entry(ti, P, q.y1, q.y2, a.scale, H, W, 2 * HWp, &s_hraw[buf][j][ti]);
-        else s_tw[buf][j][ti - P] = tab_entry(ti - P, P, q.x1, q.x2, a.scale, W, 1, HWp, &s_wraw[buf][j][ti - P]);
+        if (ti < P)
+            s_th[buf][j][ti] = tab_entry(ti, P, q.y1, q.y2, a.scale, H, W, 2 * HWp, sizeof(V), &s_hraw[buf][j][ti]);
+        else
+            s_tw[buf][j][ti - P] = tab_entry(ti - P, P, q.x1, q.x2, a.scale, W, 1, HWp, sizeof(V),
+                                             &s_wraw[buf][j][ti - P]);
         if (ti == 0)
             s_ob[buf][j] = (((size_t)max(q.k, 0) * a.C + c0) * BINS) * sizeof(float);
     };
@@ -409,43 +453,34 @@ __global__ void __launch_bounds__(TAB_THREADS, 2) roi_pool_tab_kernel(RoiArgs a)
         nx0 = load_roi(a, r0 + 2 * stride + tj, r_end);  // boxes of the batch after that
         nx1 = load_roi(a, r0 + 2 * stride + tj + NB / 2, r_end);
         const int nb = min(NB, r_end - r0);
-        // one bin (this thread's ph,pw) of RoI j of the batch, all four channels
-        auto one_bin = [&](int j, bool full4, bool valid) {
+        // one bin (this thread's ph,pw) of RoI j of the batch, all CS channels
+        auto one_bin = [&](int j, bool full, bool valid) {
             const int2 h = s_th[cur][j][ph], w = s_tw[cur][j][pw];
             const int hy = h.y & TAB_OFF_MASK, wy = w.y & TAB_OFF_MASK;
             // lookups that coincide with the first one are skipped: warp-uniformly when no lane needs
             // them (saves the issue slots), per lane otherwise (idle lanes cost no LSU wavefronts)
             const bool wide = w.x != wy, tall = h.x != hy;
             const bool any_wide = __any_sync(0xFFFFFFFFu, wide), any_tall = __any_sync(0xFFFFFFFFu, tall);
-            float4 v = *reinterpret_cast<const float4*>(smem_raw + (w.x + h.x));
+            V v = *reinterpret_cast<const V*>(smem_raw + (w.x + h.x));
             if (any_wide) {
-                if (wide) v = max4(v, *reinterpret_cast<const float4*>(smem_raw + (wy + h.x)));
+                if (wide) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (wy + h.x)));
             }
             if (any_tall) {
-                if (tall) v = max4(v, *reinterpret_cast<const float4*>(smem_raw + (w.x + hy)));
+                if (tall) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (w.x + hy)));
                 if (any_wide) {
-                    if (wide && tall) v = max4(v, *reinterpret_cast<const float4*>(smem_raw + (wy + hy)));
+                    if (wide && tall) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (wy + hy)));
                 }
             }
             const bool big = ((h.y | w.y) & TAB_BIG_BIT) != 0;
             if (__any_sync(0xFFFFFFFFu, big)) {
-                if (big) v = tab_big_bin(tab, s_hraw[cur][j][ph], s_wraw[cur][j][pw], W);
+                if (big) v = tab_big_bin<V>(tab, s_hraw[cur][j][ph], s_wraw[cur][j][pw], W);
             }
             const unsigned m = (unsigned)((h.y & w.y) >> 31);  // all ones iff the bin is non-empty
             float* o = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.out) + s_ob[cur][j]) + e;
-            if (full4) {
-                o[0] = __uint_as_float(__float_as_uint(v.x) & m);
-                o[BINS] = __uint_as_float(__float_as_uint(v.y) & m);
-                o[2 * BINS] = __uint_as_float(__float_as_uint(v.z) & m);
-                o[3 * BINS] = __uint_as_float(__float_as_uint(v.w) & m);
-            } else if (valid) {
-                o[0] = __uint_as_float(__float_as_uint(v.x) & m);
-                if (cs > 1) o[BINS] = __uint_as_float(__float_as_uint(v.y) & m);
-                if (cs > 2) o[2 * BINS] = __uint_as_float(__float_as_uint(v.z) & m);
-                if (cs > 3) o[3 * BINS] = __uint_as_float(__float_as_uint(v.w) & m);
-            }
+            if (full) vstore<true>(o, BINS, v, m, cs);
+            else if (valid) vstore<false>(o, BINS, v, m, cs);
         };
-        if (nb == NB && cs == TAB_CS) {
+        if (nb == NB && cs == CS) {
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) one_bin(it * RPI + ej, true, true);
         } else {
@@ -737,7 +772,7 @@ static int launch_staged(KernelT kernel, const RoiArgs& a, size_t smem, cudaStre
 template <typename KernelT>
 static int launch_tab(KernelT kernel, const RoiArgs& a, size_t smem, int threads, cudaStream_t stream) {
     FRCNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int slabs = cdiv(a.C, TAB_CS);
+    int slabs = cdiv(a.C, a.CS);
     FRCNN_CHECK_ARG(slabs <= 65535 && a.B <= 65535, "roi op: too many channel slabs / images");
     dim3 grid(a.groups, slabs, a.B);
     kernel<<<grid, threads, smem, stream>>>(a);
@@ -822,19 +857,36 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
     a.groups = pick_groups(K, B, cdiv(C, cs));
     size_t smem = (size_t)cs * H * W * 4;
     if (align) return launch_staged(roi_align_staged_kernel, a, smem, stream);
-    // inference RoIPool: sparse max-table kernel when the four tables of a 4-channel slab fit
-    size_t tab_smem = (size_t)4 * ((H * W + 3) & ~3) * sizeof(float4);
-    if (!argmax && PH == PW && (PH == 7 || PH == 14) && tab_smem <= ROI_SMEM_MAX) {
-        a.CS = TAB_CS;
-        const int tab_threads = 392;  // 2*14*14 = 8*7*7; measured best (784/588 are register-starved)
-        int per_batch = tab_threads / PH;
-        int slabs = cdiv(C, TAB_CS);
-        int per_image = cdiv(K, B);
-        int g = cdiv(per_image, 4 * per_batch);  // >= 4 batches per CTA amortise the table build
-        int want = cdiv(8 * sm_count(), B * slabs);
-        a.groups = std::max(1, std::min(g, want));
-        if (PH == 7) return launch_tab(roi_pool_tab_kernel<7, 392>, a, tab_smem, tab_threads, stream);
-        return launch_tab(roi_pool_tab_kernel<14, 392>, a, tab_smem, tab_threads, stream);
+    // inference RoIPool: sparse max-table kernel.  4 channels per CTA (float4 tables) when that leaves two
+    // CTAs per SM, else 2 channels (float2 tables), else one CTA per SM
+    if (!argmax && PH == PW && (PH == 7 || PH == 14)) {
+        const size_t HWp = (size_t)((H * W + 3) & ~3);
+        const size_t smem4 = 4 * HWp * 16, smem2 = 4 * HWp * 8;
+        const size_t two_per_sm = 92 * 1024, one_per_sm = 200 * 1024;  // dynamic part; ~20 KB static on top
+        int tcs = 0, minb = 0;
+        if (smem4 <= two_per_sm) tcs = 4, minb = 2;
+        else if (smem2 <= two_per_sm) tcs = 2, minb = 2;
+        else if (smem4 <= one_per_sm) tcs = 4, minb = 1;
+        else if (smem2 <= one_per_sm) tcs = 2, minb = 1;
+        if (tcs) {
+            const int tab_threads = 392;  // 2*14*14 = 8*7*7; measured best (784/588 are register-starved)
+            a.CS = tcs;
+            int per_batch = tab_threads / PH;
+            int slabs = cdiv(C, tcs);
+            int per_image = cdiv(K, B);
+            int g = cdiv(per_image, 4 * per_batch);  // >= 4 batches per CTA amortise the table build
+            int want = cdiv(8 * sm_count(), B * slabs);
+            a.groups = std::max(1, std::min(g, want));
+            const size_t smem = tcs == 4 ? smem4 : smem2;
+#define FRCNN_TAB(PP_, CS_, MB_) launch_tab(roi_pool_tab_kernel<PP_, 392, CS_, MB_>, a, smem, tab_threads, stream)
+            if (PH == 7) {
+                if (tcs == 4) return minb == 2 ? FRCNN_TAB(7, 4, 2) : FRCNN_TAB(7, 4, 1);
+                return minb == 2 ? FRCNN_TAB(7, 2, 2) : FRCNN_TAB(7, 2, 1);
+            }
+            if (tcs == 4) return minb == 2 ? FRCNN_TAB(14, 4, 2) : FRCNN_TAB(14, 4, 1);
+            return minb == 2 ? FRCNN_TAB(14, 2, 2) : FRCNN_TAB(14, 2, 1);
+#undef FRCNN_TAB
+        }
     }
     if (PH == PW && PH == 7)
         return argmax ? launch_staged(roi_pool_staged_kernel<7, true>, a, smem, stream)
