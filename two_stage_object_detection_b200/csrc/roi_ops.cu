@@ -648,6 +648,158 @@ __global__ void __launch_bounds__(ROI_THREADS, 2) roi_align_staged_kernel(RoiArg
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// RoIAlign forward, interleaved kernel (fixed sampling_ratio SR per bin side).
+//
+// Same skeleton as roi_pool_tab_kernel: the CTA owns (image, 4-channel slab, RoI group), TMA-stages the
+// slab's NCHW planes, re-lays them channel-interleaved (one float4 per pixel: one LDS.128 = one
+// bilinear tap for four channels), and a thread owns one output bin for good, so warp stores are
+// contiguous 128-byte runs.  Per RoI and axis the P*SR sample positions are reduced once to
+// {low offset, high offset, l, h} entries (16 B, double-buffered shared-memory tables); a bin then needs
+// 2*SR entry loads + 4*SR*SR taps.  Samples outside [-1, limit] get zero weights, which adds exactly 0
+// like the reference's `continue`.  Arithmetic order per channel is the reference's:
+// ((w1*v1 + w2*v2) + w3*v3) + w4*v4, samples accumulated iy-outer / ix-inner, divided by the count.
+// ---------------------------------------------------------------------------------------------
+struct AlignEntry {
+    int lo, hi;  // byte offsets of the low / high pixel along this axis
+    float l, h;  // weights of the high / low pixel (l = frac, h = 1 - frac); both 0 when out of range
+};
+
+__device__ __forceinline__ AlignEntry align_entry(int p, int i, int P, int SR, float c1, float c2, float scale,
+                                                  int aligned, int limit, int unit_bytes) {
+    const float off = aligned ? 0.5f : 0.f;
+    const float start = c1 * scale - off;
+    float size = (c2 * scale - off) - start;
+    if (!aligned) size = fmaxf(size, 1.f);
+    const float bin = size / (float)P;
+    float c = start + (float)p * bin;
+    c = c + ((float)i + .5f) * bin / (float)SR;
+    AlignEntry e;
+    if (c < -1.0f || c > (float)limit) {
+        e.lo = e.hi = 0;
+        e.l = e.h = 0.f;
+        return e;
+    }
+    if (c <= 0.f) c = 0.f;
+    int lo = (int)c, hi;
+    if (lo >= limit - 1) {
+        hi = lo = limit - 1;
+        c = (float)lo;
+    } else {
+        hi = lo + 1;
+    }
+    e.lo = lo * unit_bytes;
+    e.hi = hi * unit_bytes;
+    e.l = c - (float)lo;
+    e.h = 1.f - e.l;
+    return e;
+}
+
+template <int P, int SR, int AL_THREADS, int MINB>
+__global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs a) {
+    constexpr int BINS = P * P;
+    constexpr int RPI = AL_THREADS / BINS;               // RoIs per iteration
+    constexpr int EPR = 2 * P * SR;                      // table entries per RoI (rows then columns)
+    constexpr int NB = (2 * AL_THREADS / EPR) / RPI * RPI;  // RoIs per batch: <= 2 entries per thread
+    constexpr int ITERS = NB / RPI;
+    static_assert(RPI * BINS == AL_THREADS && NB > 0, "thread mapping");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(16) AlignEntry s_ent[2][NB][EPR];
+    __shared__ size_t s_ob[2][NB];
+    float4* tab = reinterpret_cast<float4*>(smem_raw);
+    const int H = a.H, W = a.W, HW = H * W, HWp = (HW + 3) & ~3;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * 4;
+    const int cs = min(4, a.C - c0);
+    int r_begin, r_end;
+    roi_range(a, b, r_begin, r_end);
+    const int stride = a.groups * NB;
+    int r0 = r_begin + blockIdx.x * NB;
+    if (r0 >= r_end) return;
+    const int tid = threadIdx.x;
+
+    float* raw = reinterpret_cast<float*>(tab + HWp);  // [cs][HW] planes, staged next to the table
+    stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
+    for (int p = tid; p < HW; p += AL_THREADS) {
+        float4 v;
+        v.x = raw[p];
+        v.y = cs > 1 ? raw[HW + p] : 0.f;
+        v.z = cs > 2 ? raw[2 * HW + p] : 0.f;
+        v.w = cs > 3 ? raw[3 * HW + p] : 0.f;
+        tab[p] = v;
+    }
+
+    const int e = tid % BINS, ej = tid / BINS;
+    const int ph = e / P, pw = e % P;
+    // entries tid and tid + AL_THREADS of the batch's NB*EPR entries
+    auto fill_tables = [&](int buf, int rbase) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int idx = tid + q * AL_THREADS;
+            if (idx < NB * EPR) {
+                const int j = idx / EPR, ent = idx % EPR;
+                const RoiBox box = load_roi(a, rbase + j, r_end);
+                const bool is_row = ent < P * SR;
+                const int pe = is_row ? ent : ent - P * SR;
+                s_ent[buf][j][ent] = is_row ? align_entry(pe / SR, pe % SR, P, SR, box.y1, box.y2, a.scale, a.aligned,
+                                                          H, W * 16)
+                                            : align_entry(pe / SR, pe % SR, P, SR, box.x1, box.x2, a.scale, a.aligned,
+                                                          W, 16);
+                if (ent == 0) s_ob[buf][j] = (((size_t)max(box.k, 0) * a.C + c0) * BINS) * sizeof(float);
+            }
+        }
+    };
+    fill_tables(0, r0);
+    int cur = 0;
+    for (; r0 < r_end; r0 += stride, cur ^= 1) {
+        __syncthreads();  // tables[cur] and the interleaved planes complete; tables[cur^1] free
+        if (r0 + stride < r_end) fill_tables(cur ^ 1, r0 + stride);
+        const int nb = min(NB, r_end - r0);
+        for (int it = 0; it < ITERS; ++it) {
+            const int j = it * RPI + ej;
+            if (it * RPI >= nb) break;
+            const bool valid = j < nb;
+            const int jc = valid ? j : 0;
+            const float4* rows = reinterpret_cast<const float4*>(&s_ent[cur][jc][ph * SR]);
+            const float4* cols = reinterpret_cast<const float4*>(&s_ent[cur][jc][P * SR + pw * SR]);
+            float4 cx[SR];
+#pragma unroll
+            for (int ix = 0; ix < SR; ++ix) cx[ix] = cols[ix];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int iy = 0; iy < SR; ++iy) {
+                const float4 ry = rows[iy];
+                const int ylo = __float_as_int(ry.x), yhi = __float_as_int(ry.y);
+                const float ly = ry.z, hy = ry.w;
+#pragma unroll
+                for (int ix = 0; ix < SR; ++ix) {
+                    const int xlo = __float_as_int(cx[ix].x), xhi = __float_as_int(cx[ix].y);
+                    const float lx = cx[ix].z, hx = cx[ix].w;
+                    const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+                    const float4 v1 = *reinterpret_cast<const float4*>(smem_raw + (ylo + xlo));
+                    const float4 v2 = *reinterpret_cast<const float4*>(smem_raw + (ylo + xhi));
+                    const float4 v3 = *reinterpret_cast<const float4*>(smem_raw + (yhi + xlo));
+                    const float4 v4 = *reinterpret_cast<const float4*>(smem_raw + (yhi + xhi));
+                    float t;
+                    t = w1 * v1.x; t = t + w2 * v2.x; t = t + w3 * v3.x; t = t + w4 * v4.x; acc.x = acc.x + t;
+                    t = w1 * v1.y; t = t + w2 * v2.y; t = t + w3 * v3.y; t = t + w4 * v4.y; acc.y = acc.y + t;
+                    t = w1 * v1.z; t = t + w2 * v2.z; t = t + w3 * v3.z; t = t + w4 * v4.z; acc.z = acc.z + t;
+                    t = w1 * v1.w; t = t + w2 * v2.w; t = t + w3 * v3.w; t = t + w4 * v4.w; acc.w = acc.w + t;
+                }
+            }
+            if (valid) {
+                const float cnt = (float)(SR * SR);
+                float* o = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.out) + s_ob[cur][j]) + e;
+                o[0] = acc.x / cnt;
+                if (cs > 1) o[BINS] = acc.y / cnt;
+                if (cs > 2) o[2 * BINS] = acc.z / cnt;
+                if (cs > 3) o[3 * BINS] = acc.w / cnt;
+            }
+        }
+    }
+}
+
 __global__ void roi_align_direct_kernel(RoiArgs a) {
     size_t total = (size_t)a.K * a.C * a.PH * a.PW;
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
@@ -770,6 +922,17 @@ static int launch_staged(KernelT kernel, const RoiArgs& a, size_t smem, cudaStre
 }
 
 template <typename KernelT>
+static int launch_align(KernelT kernel, const RoiArgs& a, size_t smem, cudaStream_t stream) {
+    FRCNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int slabs = cdiv(a.C, 4);
+    FRCNN_CHECK_ARG(slabs <= 65535 && a.B <= 65535, "roi op: too many channel slabs / images");
+    dim3 grid(a.groups, slabs, a.B);
+    kernel<<<grid, 392, smem, stream>>>(a);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
+template <typename KernelT>
 static int launch_tab(KernelT kernel, const RoiArgs& a, size_t smem, int threads, cudaStream_t stream) {
     FRCNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int slabs = cdiv(a.C, a.CS);
@@ -856,7 +1019,25 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
     a.CS = cs;
     a.groups = pick_groups(K, B, cdiv(C, cs));
     size_t smem = (size_t)cs * H * W * 4;
-    if (align) return launch_staged(roi_align_staged_kernel, a, smem, stream);
+    if (align) {
+        // interleaved kernel for the common fixed 2x2 sampling grid; plane + staging area must fit
+        const size_t al_smem = (size_t)2 * ((H * W + 3) & ~3) * sizeof(float4);
+        if (sampling_ratio == 2 && PH == PW && (PH == 7 || PH == 14) && al_smem <= 200 * 1024) {
+            a.CS = 4;
+            const int minb = al_smem <= 100 * 1024 ? 2 : 1;
+            const int nbatch = PH == 7 ? 24 : 14;  // NB of the kernel template
+            int slabs = cdiv(C, 4);
+            int g = cdiv(cdiv(K, B), 4 * nbatch);
+            int want = cdiv(8 * sm_count(), B * slabs);
+            a.groups = std::max(1, std::min(g, want));
+            if (PH == 7)
+                return minb == 2 ? launch_align(roi_align_tab_kernel<7, 2, 392, 2>, a, al_smem, stream)
+                                 : launch_align(roi_align_tab_kernel<7, 2, 392, 1>, a, al_smem, stream);
+            return minb == 2 ? launch_align(roi_align_tab_kernel<14, 2, 392, 2>, a, al_smem, stream)
+                             : launch_align(roi_align_tab_kernel<14, 2, 392, 1>, a, al_smem, stream);
+        }
+        return launch_staged(roi_align_staged_kernel, a, smem, stream);
+    }
     // inference RoIPool: sparse max-table kernel.  4 channels per CTA (float4 tables) when that leaves two
     // CTAs per SM, else 2 channels (float2 tables), else one CTA per SM
     if (!argmax && PH == PW && (PH == 7 || PH == 14)) {
