@@ -661,12 +661,12 @@ __global__ void __launch_bounds__(ROI_THREADS, 2) roi_align_staged_kernel(RoiArg
 // ((w1*v1 + w2*v2) + w3*v3) + w4*v4, samples accumulated iy-outer / ix-inner, divided by the count.
 // ---------------------------------------------------------------------------------------------
 struct AlignEntry {
-    int lo, hi;  // byte offsets of the low / high pixel along this axis
-    float l, h;  // weights of the high / low pixel (l = frac, h = 1 - frac); both 0 when out of range
+    int lohi;  // low pixel index | high pixel index << 16 along this axis (in pixels); bit 31: out of range
+    float l;   // weight of the high pixel (the low one gets 1 - l); 0 when out of range
 };
 
 __device__ __forceinline__ AlignEntry align_entry(int p, int i, int P, int SR, float c1, float c2, float scale,
-                                                  int aligned, int limit, int unit_bytes) {
+                                                  int aligned, int limit, int unit) {
     const float off = aligned ? 0.5f : 0.f;
     const float start = c1 * scale - off;
     float size = (c2 * scale - off) - start;
@@ -676,8 +676,8 @@ __device__ __forceinline__ AlignEntry align_entry(int p, int i, int P, int SR, f
     c = c + ((float)i + .5f) * bin / (float)SR;
     AlignEntry e;
     if (c < -1.0f || c > (float)limit) {
-        e.lo = e.hi = 0;
-        e.l = e.h = 0.f;
+        e.lohi = (int)0x80000000;
+        e.l = 0.f;
         return e;
     }
     if (c <= 0.f) c = 0.f;
@@ -688,25 +688,25 @@ __device__ __forceinline__ AlignEntry align_entry(int p, int i, int P, int SR, f
     } else {
         hi = lo + 1;
     }
-    e.lo = lo * unit_bytes;
-    e.hi = hi * unit_bytes;
+    e.lohi = (lo * unit) | ((hi * unit) << 16);
     e.l = c - (float)lo;
-    e.h = 1.f - e.l;
     return e;
 }
 
 template <int P, int SR, int AL_THREADS, int MINB>
 __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs a) {
     constexpr int BINS = P * P;
-    constexpr int RPI = AL_THREADS / BINS;               // RoIs per iteration
-    constexpr int EPR = 2 * P * SR;                      // table entries per RoI (rows then columns)
-    constexpr int NB = (2 * AL_THREADS / EPR) / RPI * RPI;  // RoIs per batch: <= 2 entries per thread
+    constexpr int RPI = AL_THREADS / BINS;                  // RoIs per iteration
+    constexpr int EPR = 2 * P * SR;                         // table entries per RoI (rows then columns)
+    constexpr int EPT = 4;                                  // table entries per thread and batch
+    constexpr int NB = (EPT * AL_THREADS / EPR) / RPI * RPI;  // RoIs per batch
     constexpr int ITERS = NB / RPI;
-    static_assert(RPI * BINS == AL_THREADS && NB > 0, "thread mapping");
+    static_assert(RPI * BINS == AL_THREADS && NB > 0 && NB <= AL_THREADS, "thread mapping");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(16) AlignEntry s_ent[2][NB][EPR];
     __shared__ size_t s_ob[2][NB];
+    __shared__ RoiBox s_box[2][NB];
     float4* tab = reinterpret_cast<float4*>(smem_raw);
     const int H = a.H, W = a.W, HW = H * W, HWp = (HW + 3) & ~3;
     const int b = blockIdx.z;
@@ -718,6 +718,12 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs
     int r0 = r_begin + blockIdx.x * NB;
     if (r0 >= r_end) return;
     const int tid = threadIdx.x;
+    // boxes: batch 0 and 1 go to shared memory now, batch 2 waits in a register
+    if (tid < NB) {
+        s_box[0][tid] = load_roi(a, r0 + tid, r_end);
+        s_box[1][tid] = load_roi(a, r0 + stride + tid, r_end);
+    }
+    RoiBox nxt = load_roi(a, r0 + 2 * stride + (tid < NB ? tid : 0), r_end);
 
     float* raw = reinterpret_cast<float*>(tab + HWp);  // [cs][HW] planes, staged next to the table
     stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
@@ -729,63 +735,81 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs
         v.w = cs > 3 ? raw[3 * HW + p] : 0.f;
         tab[p] = v;
     }
+    __syncthreads();  // s_box[0..1] visible
 
     const int e = tid % BINS, ej = tid / BINS;
     const int ph = e / P, pw = e % P;
-    // entries tid and tid + AL_THREADS of the batch's NB*EPR entries
-    auto fill_tables = [&](int buf, int rbase) {
+    auto fill_tables = [&](int buf) {  // geometry of the batch whose boxes sit in s_box[buf]
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < EPT; ++q) {
             const int idx = tid + q * AL_THREADS;
             if (idx < NB * EPR) {
                 const int j = idx / EPR, ent = idx % EPR;
-                const RoiBox box = load_roi(a, rbase + j, r_end);
+                const RoiBox box = s_box[buf][j];
                 const bool is_row = ent < P * SR;
                 const int pe = is_row ? ent : ent - P * SR;
-                s_ent[buf][j][ent] = is_row ? align_entry(pe / SR, pe % SR, P, SR, box.y1, box.y2, a.scale, a.aligned,
-                                                          H, W * 16)
-                                            : align_entry(pe / SR, pe % SR, P, SR, box.x1, box.x2, a.scale, a.aligned,
-                                                          W, 16);
+                s_ent[buf][j][ent] = is_row ? align_entry(pe / SR, pe % SR, P, SR, box.y1, box.y2, a.scale, a.aligned, H, W)
+                                            : align_entry(pe / SR, pe % SR, P, SR, box.x1, box.x2, a.scale, a.aligned, W, 1);
                 if (ent == 0) s_ob[buf][j] = (((size_t)max(box.k, 0) * a.C + c0) * BINS) * sizeof(float);
             }
         }
     };
-    fill_tables(0, r0);
+    fill_tables(0);
     int cur = 0;
     for (; r0 < r_end; r0 += stride, cur ^= 1) {
-        __syncthreads();  // tables[cur] and the interleaved planes complete; tables[cur^1] free
-        if (r0 + stride < r_end) fill_tables(cur ^ 1, r0 + stride);
+        __syncthreads();  // tables[cur] complete; tables[cur^1] and s_box[cur] no longer read
+        fill_tables(cur ^ 1);  // next batch (ALU only: its boxes are already in shared memory)
+        if (tid < NB) s_box[cur][tid] = nxt;  // boxes of the batch after next
+        nxt = load_roi(a, r0 + 3 * stride + (tid < NB ? tid : 0), r_end);
         const int nb = min(NB, r_end - r0);
         for (int it = 0; it < ITERS; ++it) {
             const int j = it * RPI + ej;
             if (it * RPI >= nb) break;
             const bool valid = j < nb;
             const int jc = valid ? j : 0;
-            const float4* rows = reinterpret_cast<const float4*>(&s_ent[cur][jc][ph * SR]);
-            const float4* cols = reinterpret_cast<const float4*>(&s_ent[cur][jc][P * SR + pw * SR]);
-            float4 cx[SR];
+            const int2* rows = reinterpret_cast<const int2*>(&s_ent[cur][jc][ph * SR]);
+            const int2* cols = reinterpret_cast<const int2*>(&s_ent[cur][jc][P * SR + pw * SR]);
+            int2 cx[SR];
 #pragma unroll
             for (int ix = 0; ix < SR; ++ix) cx[ix] = cols[ix];
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            // the four taps of the previous sample stay in registers; a sample reloads them only if its
+            // pixel quad differs (per lane: idle lanes cost no shared-memory wavefronts).  Neighbouring
+            // samples of a small bin usually share their quad.
+            float4 v1, v2, v3, v4;
+            int qlo = -1, qhi = -1;  // pixel indices (ylo+xlo, yhi+xhi) of the cached quad
+            auto sample = [&](const int2& ry, const int2& rx) -> float4 {
+                const int ylo = ry.x & 0xFFFF, yhi = (ry.x >> 16) & 0x7FFF;
+                const int xlo = rx.x & 0xFFFF, xhi = (rx.x >> 16) & 0x7FFF;
+                // (row offset + column offset) identifies the pixel: column offsets are < one row
+                if (ylo + xlo != qlo || yhi + xhi != qhi) {
+                    v1 = tab[ylo + xlo];
+                    v2 = tab[ylo + xhi];
+                    v3 = tab[yhi + xlo];
+                    v4 = tab[yhi + xhi];
+                    qlo = ylo + xlo;
+                    qhi = yhi + xhi;
+                }
+                const float ly = __int_as_float(ry.y), lx = __int_as_float(rx.y);
+                const float hy = ry.x < 0 ? 0.f : 1.f - ly, hx = rx.x < 0 ? 0.f : 1.f - lx;
+                const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+                float4 t;
+                t.x = w1 * v1.x; t.x = t.x + w2 * v2.x; t.x = t.x + w3 * v3.x; t.x = t.x + w4 * v4.x;
+                t.y = w1 * v1.y; t.y = t.y + w2 * v2.y; t.y = t.y + w3 * v3.y; t.y = t.y + w4 * v4.y;
+                t.z = w1 * v1.z; t.z = t.z + w2 * v2.z; t.z = t.z + w3 * v3.z; t.z = t.z + w4 * v4.z;
+                t.w = w1 * v1.w; t.w = t.w + w2 * v2.w; t.w = t.w + w3 * v3.w; t.w = t.w + w4 * v4.w;
+                return t;
+            };
 #pragma unroll
             for (int iy = 0; iy < SR; ++iy) {
-                const float4 ry = rows[iy];
-                const int ylo = __float_as_int(ry.x), yhi = __float_as_int(ry.y);
-                const float ly = ry.z, hy = ry.w;
+                const int2 ry = rows[iy];
 #pragma unroll
                 for (int ix = 0; ix < SR; ++ix) {
-                    const int xlo = __float_as_int(cx[ix].x), xhi = __float_as_int(cx[ix].y);
-                    const float lx = cx[ix].z, hx = cx[ix].w;
-                    const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-                    const float4 v1 = *reinterpret_cast<const float4*>(smem_raw + (ylo + xlo));
-                    const float4 v2 = *reinterpret_cast<const float4*>(smem_raw + (ylo + xhi));
-                    const float4 v3 = *reinterpret_cast<const float4*>(smem_raw + (yhi + xlo));
-                    const float4 v4 = *reinterpret_cast<const float4*>(smem_raw + (yhi + xhi));
-                    float t;
-                    t = w1 * v1.x; t = t + w2 * v2.x; t = t + w3 * v3.x; t = t + w4 * v4.x; acc.x = acc.x + t;
-                    t = w1 * v1.y; t = t + w2 * v2.y; t = t + w3 * v3.y; t = t + w4 * v4.y; acc.y = acc.y + t;
-                    t = w1 * v1.z; t = t + w2 * v2.z; t = t + w3 * v3.z; t = t + w4 * v4.z; acc.z = acc.z + t;
-                    t = w1 * v1.w; t = t + w2 * v2.w; t = t + w3 * v3.w; t = t + w4 * v4.w; acc.w = acc.w + t;
+                    const float4 t = sample(ry, cx[ix]);
+                    acc.x = acc.x + t.x;
+                    acc.y = acc.y + t.y;
+                    acc.z = acc.z + t.z;
+                    acc.w = acc.w + t.w;
                 }
             }
             if (valid) {
@@ -1025,7 +1049,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
         if (sampling_ratio == 2 && PH == PW && (PH == 7 || PH == 14) && al_smem <= 200 * 1024) {
             a.CS = 4;
             const int minb = al_smem <= 100 * 1024 ? 2 : 1;
-            const int nbatch = PH == 7 ? 24 : 14;  // NB of the kernel template
+            const int nbatch = PH == 7 ? 56 : 28;  // NB of the kernel template
             int slabs = cdiv(C, 4);
             int g = cdiv(cdiv(K, B), 4 * nbatch);
             int want = cdiv(8 * sm_count(), B * slabs);
