@@ -271,7 +271,7 @@ def run_ours(args):
     n_sb, c0, ln = 0, 0, s0
     while c0 < rows:
         n_sb, c0, ln = n_sb + 1, c0 + ln, min(2 * ln, smax)
-    launches = 1 + 1 + 2 * n_sb + 1 + 1 + 1  # decode, topk, nms(mask+scan)*sb, finalize, coords, gather
+    launches = 1 + 1 + n_sb + 1 + 1 + 1  # decode, topk, nms block kernel per super-block, finalize, coords, gather
     kernel_name = "roi_pool_tab_kernel<14,392>" if (cfg["op"], P) == ("pool", 14) else (
         "roi_pool_tab_kernel<7,392>" if cfg["op"] == "pool" else "roi_align_staged_kernel")
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from one ncu --set full capture

@@ -322,17 +322,15 @@ struct NmsArgs {
     uint32_t* removed;     // [B][S/32]
     float4* kept_box;      // [B][keep_cap]
     NmsState* state;       // [B]
+    unsigned* tile_count;  // [B] CTAs of the current launch that finished their mask tile
     int* keep;             // [B][keep_cap]
     int* n_keep;           // [B]
     int tri_tiles;
 };
 
-__global__ void __launch_bounds__(NMS_CB) nms_mask_kernel(NmsArgs a) {
-    __shared__ float4 srow[NMS_KC];
-    __shared__ float sarea[NMS_KC];
-    const int b = blockIdx.y;
-    const NmsState st = a.state[b];
-    if (st.done) return;
+// one mask tile (in-block triangle tile, or suppression of a column block by a chunk of the kept list)
+__device__ __forceinline__ void nms_mask_tile(const NmsArgs& a, int b, const NmsState& st, float4* srow,
+                                              float* sarea) {
     const int n = a.n_sel[b];
     const int c0 = a.c0;
     if (c0 >= n) return;
@@ -406,13 +404,9 @@ constexpr int NMS_MAX_WORDS = 256;  // S <= 8192
 // every thread t > u ORs the mask rows of the newly kept candidates into its removed word R[t].  The
 // 32 mask words thread t needs for step u+1 (M[t][32(u+1)..]) do not depend on the outcome of step u,
 // so they are loaded one step ahead and their latency hides behind the resolve.
-__global__ void __launch_bounds__(NMS_MAX_WORDS) nms_scan_kernel(NmsArgs a) {
-    __shared__ uint32_t R[NMS_MAX_WORDS];  // removed bits of this super-block
+__device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const NmsState& st, uint32_t* R) {
     __shared__ uint32_t s_kb;
     __shared__ int s_nkept, s_done;
-    const int b = blockIdx.x;
-    NmsState st = a.state[b];
-    if (st.done) return;
     const int n = a.n_sel[b];
     const int c0 = a.c0;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -429,7 +423,7 @@ __global__ void __launch_bounds__(NMS_MAX_WORDS) nms_scan_kernel(NmsArgs a) {
     uint32_t* removed = a.removed + (size_t)b * (a.S / 32);
     const uint32_t* mask = a.mask + (size_t)b * (a.S / 32) * a.S;
     if (t < a.S / 32) {
-        uint32_t v = removed[t];
+        uint32_t v = __ldcg(removed + t);  // written by other CTAs of this launch
         removed[t] = 0;  // ready for the next super-block
         if (t == nw - 1 && (ncol & 31)) v |= ~0u << (ncol & 31);
         R[t] = v;
@@ -459,13 +453,16 @@ __global__ void __launch_bounds__(NMS_MAX_WORDS) nms_scan_kernel(NmsArgs a) {
             const uint32_t Dn = diag(u + 1);  // in flight during the resolve
             uint32_t rw = R[u];
             uint32_t kb = 0;
+            // gather the 32 diagonal words first (independent shuffles), then run the serial chain on
+            // registers only
+            uint32_t dd[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dd[i] = __shfl_sync(0xFFFFFFFFu, D, i);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                uint32_t di = __shfl_sync(0xFFFFFFFFu, D, i);
-                if (!((rw >> i) & 1u)) {
-                    kb |= 1u << i;
-                    rw |= di;
-                }
+                const bool alive = !((rw >> i) & 1u);
+                kb |= alive ? (1u << i) : 0u;
+                rw |= alive ? dd[i] : 0u;
             }
             D = Dn;
             int nk = s_nkept;
@@ -512,6 +509,31 @@ __global__ void __launch_bounds__(NMS_MAX_WORDS) nms_scan_kernel(NmsArgs a) {
         a.state[b].done = done;
         a.n_keep[b] = s_nkept;
     }
+}
+
+// One launch per super-block: every CTA does its mask tile; the CTA that finishes last for an image
+// (counted with an atomic after a __threadfence, no CTA ever waits for another) runs that image's scan,
+// so the scan starts the moment the image's tiles are done and costs no launch of its own.
+__global__ void __launch_bounds__(NMS_MAX_WORDS) nms_block_kernel(NmsArgs a) {
+    __shared__ float4 srow[NMS_KC];
+    __shared__ float sarea[NMS_KC];
+    __shared__ uint32_t R[NMS_MAX_WORDS];
+    __shared__ int s_last;
+    const int b = blockIdx.y;
+    const NmsState st = a.state[b];
+    if (st.done) return;  // set by an earlier launch: identical for all CTAs of this image
+    nms_mask_tile(a, b, st, srow, sarea);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(a.tile_count + b, 1u);
+        s_last = prev == gridDim.x - 1;
+        if (s_last) a.tile_count[b] = 0;  // ready for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    nms_scan_image(a, b, st, R);
 }
 
 // nets/rpn.py:65-69: pad with arange, truncate, gather
@@ -593,14 +615,17 @@ static size_t nms_ws_layout(Workspace& ws, int batch, int n_rows, int keep_cap, 
     int S = max_superblock(superblock, n_rows, keep_cap);
     uint32_t* mask = ws.take<uint32_t>((size_t)batch * (S / 32) * S);
     // state + removed are cleared together by one memset
-    size_t clear_bytes = align_up((size_t)batch * sizeof(NmsState)) + align_up((size_t)batch * (S / 32) * 4);
+    size_t clear_bytes = align_up((size_t)batch * sizeof(NmsState)) + align_up((size_t)batch * sizeof(unsigned)) +
+                         align_up((size_t)batch * (S / 32) * 4);
     NmsState* state = ws.take<NmsState>(batch);
+    unsigned* tile_count = ws.take<unsigned>(batch);
     uint32_t* removed = ws.take<uint32_t>((size_t)batch * (S / 32));
     float4* kept_box = ws.take<float4>((size_t)batch * (keep_cap > 0 ? keep_cap : 1));
     if (a) {
         a->S = S;
         a->mask = mask;
         a->state = state;
+        a->tile_count = tile_count;
         a->removed = removed;
         a->kept_box = kept_box;
     }
@@ -637,9 +662,7 @@ static int run_nms_sorted(const float* sorted_boxes, const int32_t* n_sel, int b
         a.tri_tiles = 2 * ncb * (ncb + 1);
         int prev_tiles = c0 > 0 ? ncb * cdiv(keep_cap, NMS_KC) : 0;
         dim3 grid(a.tri_tiles + prev_tiles, batch);
-        nms_mask_kernel<<<grid, NMS_CB, 0, stream>>>(a);
-        FRCNN_LAUNCH_CHECK();
-        nms_scan_kernel<<<batch, std::max(32, (len / 32 + 31) / 32 * 32), 0, stream>>>(a);
+        nms_block_kernel<<<grid, NMS_CB, 0, stream>>>(a);
         FRCNN_LAUNCH_CHECK();
         c0 += len;
         if (superblock <= 0) len = std::min(2 * len, a.S);
