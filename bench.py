@@ -302,7 +302,7 @@ def run_ours(args):
     }
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_baseline(cfg, images=2)
+            out["cpu_baseline"] = cpu_baseline(cfg, images=cfg["batch"])
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -328,7 +328,7 @@ def cpu_baseline(cfg, images=2, reps=1):
     from oracle import ref_port as O
     loc, logits, feat = (t.numpy() for t in make_inputs(cfg, 7))
     images = min(images, cfg["batch"])
-    cpu_step(cfg, O, loc, logits, feat, 1)  # warm-up (builds / loads the C library)
+    cpu_step(cfg, O, loc, logits, feat, 2)  # warm-up (builds / loads the C library)
     t0 = time.perf_counter()
     for _ in range(reps):
         cpu_step(cfg, O, loc, logits, feat, images)
@@ -344,7 +344,7 @@ def run_reference(args):
         return
     from oracle import ref_port as O
     cfg = WORKLOADS[args.workload]
-    images = min(2, cfg["batch"])
+    images = cfg["batch"]  # one full batch per step: OpenMP spreads images / RoIs over every host core
     loc, logits, feat = (t.numpy() for t in make_inputs(cfg, 7))
     for _ in range(min(args.warmup, 1) or 1):
         cpu_step(cfg, O, loc, logits, feat, images)
