@@ -51,29 +51,62 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML every ~2 ms; nvidia-smi is too
+    slow for a 50 ms region and is only the fallback)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+               "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.sm, self.bits, self.max_mhz = [], 0, None
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        while not self._stop.is_set():
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                tok = vis.split(",")[self.index].strip()
+                if tok.isdigit():
+                    idx = int(tok)
+                else:
+                    uuid = tok
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid) if uuid else pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self._stop.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self._stop.wait(0.002)
+        except Exception:
+            self._smi_loop()
+
+    def _smi_loop(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while True:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
                 if out.returncode == 0 and out.stdout.strip():
-                    self.rows.append([c.strip() for c in out.stdout.strip().splitlines()[0].split(",")])
+                    r = [c.strip() for c in out.stdout.strip().splitlines()[0].split(",")]
+                    self.sm.append(float(r[0]))
+                    self.max_mhz = float(r[1])
+                    for i, n in enumerate(names):
+                        if r[2 + i].lower().startswith("active"):
+                            self.bits |= self.REASONS[n]
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            if self._stop.wait(0.2):
+                break
 
     def __enter__(self):
         self._t.start()
+        time.sleep(0.02)  # let the sampler open NVML before the timed region starts
         return self
 
     def __exit__(self, *a):
@@ -81,13 +114,9 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
-                "reasons": reasons, "samples": len(self.rows)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [n for n, bit in self.REASONS.items() if self.bits & bit], "samples": len(sm)}
 
 
 def make_inputs(cfg, seed, device=None, pin=False):
