@@ -451,3 +451,84 @@ def test_roi_pool_backward_matches_autograd_definition(F):
 def test_cpu_tensors_fail_loudly(F):
     with pytest.raises(RuntimeError):
         F.bbox_iou(torch.zeros(2, 4), torch.zeros(2, 4))
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases: tiny / empty / ragged inputs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 5, 9, 33, 257, 2049])
+def test_topk_and_nms_tiny_sizes(F, O, n):
+    """Fewer keys than cluster CTAs, non-multiples of every tile size; all-equal scores (every radix
+    pass trivial) and all-filtered inputs."""
+    rng = np.random.default_rng(n)
+    c = rng.uniform(0, 100, (n, 2)).astype(np.float32)
+    wh = rng.uniform(5, 60, (n, 2)).astype(np.float32)
+    boxes = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    for scores in (rng.uniform(0, 1, n).astype(np.float32), np.full(n, 0.5, np.float32),
+                   np.round(rng.uniform(0, 1, n) * 4).astype(np.float32) / 4):
+        keep = F.nms(T(boxes), T(scores), 0.5)
+        assert np.array_equal(N(keep), O.nms(boxes, scores, 0.5))
+    keys = torch.zeros((2, n), dtype=torch.int32, device=DEV)  # everything filtered out
+    order, n_sel, sb = F.topk_sorted(keys, T(np.stack([boxes, boxes])), n)
+    assert N(n_sel).tolist() == [0, 0] and (N(order) == -1).all() and not N(sb).any()
+
+
+def test_proposals_ragged_validity_and_no_valid_boxes(F, O):
+    """Images of one batch with very different numbers of boxes surviving the min-size filter,
+    including none at all (the reference raises there: status flag)."""
+    g = torch.Generator().manual_seed(9)
+    B, H, W = 4, 12, 10
+    Nn = H * W * 9
+    loc = (torch.randn(B, Nn, 4, generator=g) * 0.2).float()
+    loc[1, :, 2:] = -6.0          # image 1: every box shrinks below min_size -> nothing valid
+    loc[2, ::3, 2:] = -6.0        # image 2: a third filtered
+    score = torch.rand(B, Nn, generator=g)
+    base = F.base_anchors(device=DEV)
+    kw = dict(clip_x_max=160, clip_y_max=192, min_size=16.0)
+    boxes, keys, fg = F.decode_clip_score(loc.to(DEV), score.to(DEV), base=base, feat_stride=16, feat_hw=(H, W), **kw)
+    rois, src, n_keep, status = F.proposals(loc.to(DEV), score.to(DEV), base=base, feat_stride=16, feat_hw=(H, W),
+                                            n_pre_nms=400, n_post_nms=50, nms_iou=0.7, **kw)
+    ref, ref_src, ref_nk, rc = O.proposal_layer_batch_from_boxes(N(boxes), N(fg), (3, 160, 192), 1.0, 0.7, 400, 50, 16)
+    assert N(status).tolist() == [0, 1, 0, 0] and rc.tolist() == [0, -1, 0, 0]
+    for b in (0, 2, 3):
+        assert np.array_equal(N(rois[b]), ref[b]) and np.array_equal(N(src[b]).astype(np.int64), ref_src[b])
+    assert int(n_keep[1]) == 0
+
+
+def test_empty_inputs(F):
+    z4 = torch.zeros(0, 4, device=DEV)
+    feat = torch.randn(1, 4, 8, 8, device=DEV)
+    assert tuple(F.roi_pool(feat, torch.zeros(0, 5, device=DEV), 7).shape) == (0, 4, 7, 7)
+    assert tuple(F.roi_align(feat, torch.zeros(0, 5, device=DEV), 7, 1.0, 2).shape) == (0, 4, 7, 7)
+    assert tuple(F.bbox_iou(z4, torch.zeros(3, 4, device=DEV)).shape) == (0, 3)
+    assert tuple(F.bbox_iou(torch.zeros(3, 4, device=DEV), z4).shape) == (3, 0)
+    assert tuple(F.bbox2loc(z4, z4).shape) == (0, 4)
+    from two_stage_object_detection_b200.utils import enumerate_shifted_anchor, generate_basic_anchor
+    assert tuple(enumerate_shifted_anchor(generate_basic_anchor(), 16, 0, 5).shape) == (0, 4)
+
+
+def test_roi_pool_channel_tail_and_big_bins(F, O):
+    """C not a multiple of the 4-channel slab, RoIs with bins longer than 4 (loop path), RoIs reaching
+    past the map (empty bins), on maps that select the float4 / float2 / one-CTA-per-SM variants."""
+    for (B, Cc, H, W, P) in [(2, 7, 38, 38, 7), (1, 6, 64, 64, 14), (1, 5, 80, 76, 7), (1, 3, 120, 90, 7)]:
+        rng = np.random.default_rng(H * 7 + Cc)
+        feat = rng.standard_normal((B, Cc, H, W)).astype(np.float32)
+        K = 90
+        c = rng.uniform(-6, W + 6, (K, 2))
+        wh = np.concatenate([rng.uniform(1, 10, (K // 2, 2)), rng.uniform(W * 0.5, W * 1.3, (K - K // 2, 2))])
+        rois = np.concatenate([rng.integers(0, B, (K, 1)), c - wh / 2, c + wh / 2], 1).astype(np.float32)
+        assert np.array_equal(N(F.roi_pool_forward(T(feat), T(rois), P, 1.0)), O.roi_pool(feat, rois, P, 1.0)), (H, W, P)
+        assert np.array_equal(N(F.roi_align_forward(T(feat), T(rois), P, 1.0, 2, False)),
+                              O.roi_align(feat, rois, P, 1.0, 2, False)), (H, W, P)
+
+
+def test_nan_and_inf_features_in_roi_pool(F, O):
+    """The reference's `v > best` scan never selects NaN / -inf; all-NaN bins give -FLT_MAX."""
+    rng = np.random.default_rng(3)
+    feat = rng.standard_normal((1, 4, 20, 20)).astype(np.float32)
+    feat[0, 0, 2:6, 2:6] = np.nan
+    feat[0, 1, :, :] = -np.inf
+    feat[0, 2, 5, 5] = np.inf
+    rois = np.array([[0, 1, 1, 8, 8], [0, 0, 0, 19, 19], [0, 2.4, 2.4, 5.2, 5.2]], np.float32)
+    for P in (7, 14):
+        assert np.array_equal(N(F.roi_pool_forward(T(feat), T(rois), P, 1.0)), O.roi_pool(feat, rois, P, 1.0))

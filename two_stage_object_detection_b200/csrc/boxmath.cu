@@ -142,12 +142,12 @@ int frcnn_base_anchors(const float* ratios, const float* inv_ratios, int32_t nr,
 
 int frcnn_shifted_anchors(const float* base, int32_t A, int32_t stride, int32_t H, int32_t W,
                           float* out, frcnn_stream_t stream) {
-    FRCNN_CHECK_ARG(base && out, "frcnn_shifted_anchors: null pointer");
     FRCNN_CHECK_ARG(A > 0 && H >= 0 && W >= 0, "frcnn_shifted_anchors: bad shape");
     int64_t n64 = (int64_t)A * H * W;
     FRCNN_CHECK_ARG(n64 < (1ll << 31), "frcnn_shifted_anchors: too many anchors");
     int n = (int)n64;
     if (n == 0) return FRCNN_OK;
+    FRCNN_CHECK_ARG(base && out, "frcnn_shifted_anchors: null pointer");
     AnchorGen g{nullptr, (const float4*)base, A, stride, H, W};
     shifted_anchor_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(g, n, (float4*)out);
     FRCNN_LAUNCH_CHECK();
