@@ -211,6 +211,41 @@ def run_ours(args):
     roi_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(ev["r0"][sl], ev["r1"][sl])]))
     prop_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(ev["p0"][sl], ev["p1"][sl])]))
 
+    # ---- the same step replayed from CUDA graphs (one per input set; informational) -------------------
+    graph_ms = None
+    if world == 1:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(3):
+                    step(0)
+            torch.cuda.current_stream().wait_stream(side)
+            graphs = []
+            for i in range(3):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    loc, logits, feat = sets[i]
+                    rois_g, _, _, _ = F.proposals(loc, logits, **pkw)
+                    rois5_g = F.roi_head_coords(rois_g, idx, (S, S), (H, W))
+                    if cfg["op"] == "pool":
+                        F.roi_pool_forward(feat, rois5_g, P, 1.0, out=pooled, rois_per_image=n_post)
+                    else:
+                        F.roi_align_forward(feat, rois5_g, P, 1.0, 2, False, out=pooled, rois_per_image=n_post)
+                graphs.append(gr)
+            for i in range(3):
+                graphs[i].replay()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for i in range(args.steps):
+                graphs[i % 3].replay()
+            g1.record()
+            torch.cuda.synchronize()
+            graph_ms = g0.elapsed_time(g1) / args.steps
+        except Exception as exc:  # graphs are an extra, never the reported value
+            graph_ms = f"unavailable: {exc}"
+
     # ---- end to end through the module API, from pinned host memory --------------------------------
     creator = ProposalCreator("test", n_test_pre_nms=cfg["n_pre"], n_test_post_nms=n_post)
     head = HarNetRoIHead(n_class=21, roi_size=P, spatial_scale=1, classifier=GlobalAvgClassifier(),
@@ -319,6 +354,7 @@ def run_ours(args):
                    "parallelism": f"dp{world} (images sharded per GPU; all_gather of rois when N>1)"},
         "proposals_per_sec": world * K / (ms_step * 1e-3),
         "breakdown_ms": {"proposals": prop_ms, "roi_gather": roi_ms},
+        "cuda_graph_ms_per_step": graph_ms,
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "serial_ms_per_step": e2e_serial_ms,
                 "api": "ProposalCreator.batched + HarNetRoIHead.forward from pinned host buffers; copies of step "
@@ -397,7 +433,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))

@@ -532,3 +532,46 @@ def test_nan_and_inf_features_in_roi_pool(F, O):
     rois = np.array([[0, 1, 1, 8, 8], [0, 0, 0, 19, 19], [0, 2.4, 2.4, 5.2, 5.2]], np.float32)
     for P in (7, 14):
         assert np.array_equal(N(F.roi_pool_forward(T(feat), T(rois), P, 1.0)), O.roi_pool(feat, rois, P, 1.0))
+
+
+def test_step_is_cuda_graph_capturable(F):
+    """Nothing on the path synchronises or allocates behind torch's back: a whole step (proposals ->
+    head coordinates -> RoIPool) captures into one CUDA graph and replays bit-identically on new data."""
+    g = torch.Generator().manual_seed(4)
+    B, C, H, W, P = 3, 8, 38, 38, 7
+    Nn = H * W * 9
+    base = F.base_anchors(device=DEV)
+    idx = torch.arange(B, dtype=torch.int32, device=DEV)
+    loc = torch.zeros(B, Nn, 4, device=DEV)
+    logits = torch.zeros(B, Nn, 2, device=DEV)
+    feat = torch.zeros(B, C, H, W, device=DEV)
+
+    def step():
+        rois, src, n_keep, status = F.proposals(loc, logits, clip_x_max=600, clip_y_max=600, n_pre_nms=3000,
+                                                n_post_nms=300, base=base, feat_stride=16, feat_hw=(H, W),
+                                                score_is_logits=True)
+        rois5 = F.roi_head_coords(rois, idx, (600, 600), (H, W))
+        return rois, F.roi_pool_forward(feat, rois5, P, 1.0, rois_per_image=300)
+
+    def fill(seed):
+        gg = torch.Generator().manual_seed(seed)
+        loc.copy_(torch.randn(B, Nn, 4, generator=gg) * 0.2)
+        logits.copy_(torch.randn(B, Nn, 2, generator=gg))
+        feat.copy_(torch.randn(B, C, H, W, generator=gg))
+
+    fill(1)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step()  # warm-up on the side stream (sizes the workspace of that stream)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_rois, g_pool = step()
+    for seed in (2, 3):
+        fill(seed)
+        graph.replay()
+        torch.cuda.synchronize()
+        e_rois, e_pool = step()
+        assert torch.equal(g_rois, e_rois) and torch.equal(g_pool, e_pool)
