@@ -35,6 +35,9 @@ WORKLOADS = {
     "cfg2": dict(batch=16, img=600, C=1024, H=38, W=38, n_pre=3000, n_post=300, op="pool", P=14,
                  desc="ResNet-50 Faster R-CNN batched inference, batch 16 synthetic 600x600, 300 post-NMS "
                       "RoIs/image, RoIPool 14x14"),
+    "cfg3": dict(batch=8, img=600, C=512, H=38, W=38, n_pre=12000, n_post=600, op="pool", P=7, train=True, n_gt=8,
+                 desc="training-step hot path: proposals 12000->600, AnchorTargetCreator(256), "
+                      "ProposalTargetCreator(128), RoIPool 7x7 (+argmax) on the 128 sampled RoIs, 8 images per GPU"),
     "cfg4": dict(batch=32, img=800, C=512, H=50, W=50, n_pre=3000, n_post=300, op="align", P=7,
                  desc="HarDNet Faster R-CNN inference, batch 32 synthetic 800x800, RoIAlign 7x7 (sr=2)"),
     "cfg5": dict(batch=8, img=1024, C=512, H=64, W=64, n_pre=30000, n_post=2000, op="pool", P=7,
@@ -168,11 +171,34 @@ def run_ours(args):
                base=base, feat_stride=16, feat_hw=(H, W), score_is_logits=True)
     ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + args.warmup)] for k in
           ("p0", "p1", "r0", "r1")}
+    train = bool(cfg.get("train"))
+    if train:  # G boxes per image, centre U(0,S)^2, w,h U(50,250), clipped; labels in [0,20)
+        gg = torch.Generator().manual_seed(77 + rank)
+        G = cfg["n_gt"]
+        ctr = torch.rand(B, G, 2, generator=gg) * S
+        wh = 50 + torch.rand(B, G, 2, generator=gg) * 200
+        gt_box = torch.cat([ctr - wh / 2, ctr + wh / 2], -1).clamp(0, S).to(dev)
+        gt_lab = torch.randint(0, 20, (B, G), generator=gg).to(dev)
+        n_gt = torch.full((B,), G, dtype=torch.int32, device=dev)
+        n_roi = 128
+        K = B * n_roi
+        pooled = torch.empty((K, C, P, P), dtype=torch.float32, device=dev)
 
     def step(i):
         loc, logits, feat = sets[i % 3]
         ev["p0"][i].record()
         rois, src, n_keep, status = F.proposals(loc, logits, **pkw)
+        if train:
+            F.anchor_targets(gt_box, n_gt, base=base, feat_stride=16, feat_hw=(H, W))
+            sample, _, _, _, _ = F.proposal_targets(rois, gt_box, gt_lab, n_gt)
+            ev["p1"][i].record()
+            rois5 = F.roi_head_coords(sample, idx, (S, S), (H, W))
+            ev["r0"][i].record()
+            F.roi_pool_forward(feat, rois5, P, 1.0, with_argmax=True, out=pooled, rois_per_image=n_roi)
+            ev["r1"][i].record()
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, rois)
+            return rois, status
         ev["p1"][i].record()
         rois5 = F.roi_head_coords(rois, idx, (S, S), (H, W))
         ev["r0"][i].record()
@@ -213,7 +239,7 @@ def run_ours(args):
 
     # ---- the same step replayed from CUDA graphs (one per input set; informational) -------------------
     graph_ms = None
-    if world == 1:
+    if world == 1 and not train:
         try:
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream())
@@ -325,7 +351,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (RoI gather) -----------------------------------------------
     peak, peak_src = peaks()
-    alg_bytes = K * C * P * P * 4 + K * 20 + B * C * H * W * 4
+    alg_bytes = K * C * P * P * 4 * (2 if train else 1) + K * 20 + B * C * H * W * 4  # + int32 argmax when training
     achieved = alg_bytes / (roi_ms * 1e-3) / 1e9
     rows = min(cfg["n_pre"], N)
     # NMS super-block schedule of csrc/proposals.cu (run_nms_sorted): first block ~2*n_post, then doubling
@@ -336,8 +362,9 @@ def run_ours(args):
     while c0 < rows:
         n_sb, c0, ln = n_sb + 1, c0 + ln, min(2 * ln, smax)
     launches = 1 + 1 + n_sb + 1 + 1 + 1  # decode, topk, nms block kernel per super-block, finalize, coords, gather
-    kernel_name = "roi_pool_tab_kernel<14,392>" if (cfg["op"], P) == ("pool", 14) else (
-        "roi_pool_tab_kernel<7,392>" if cfg["op"] == "pool" else "roi_align_staged_kernel")
+    kernel_name = "roi_pool_tab_kernel<14,392,4,2>" if (cfg["op"], P) == ("pool", 14) else (
+        ("roi_pool_staged_kernel<7,argmax>" if train else "roi_pool_tab_kernel<7,392,...>") if cfg["op"] == "pool"
+        else "roi_align_tab_kernel<7,2,392,2>")
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from one ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
