@@ -360,8 +360,39 @@ def gen_rpn_forward():
          rpn_locs=npy(locs), rpn_scores=npy(scores), fg=npy(fg), rois=npy(rois), anchor=npy(anchor))
 
 
+sys.path.insert(0, os.path.dirname(OUT))
+from trainer_fixture import TRAINER_SEEDS, load_trainer_weights, trainer_inputs  # noqa: E402
+
+
+def gen_trainer():
+    """FasterRCNNTrainer.forward (nets/frcnn_training.py:240-345), batch of one (all the reference can do),
+    with the HarDNet extractor replaced by a fixed feature tensor."""
+    class Fixed(torch.nn.Module):
+        def __init__(self, feat):
+            super().__init__()
+            self.feat = feat
+
+        def forward(self, x):
+            return self.feat
+
+    arrs = {"seeds": np.array(TRAINER_SEEDS)}
+    trainer = ref_tr.FasterRCNNTrainer(mode="train", num_classes=20)
+    for seed in TRAINER_SEEDS:
+        feat, w, bbox, label = trainer_inputs(seed)
+        load_trainer_weights(trainer, w)
+        trainer.feat_extra = Fixed(feat)
+        img = torch.zeros(3, 320, 320)
+        losses, anchors_pred, classes_pred, classes_score_pred, gt_b, gt_l = trainer([img], [bbox], [label])
+        arrs[f"s{seed}_losses"] = np.array([float(l) for l in losses], dtype=np.float64)
+        arrs[f"s{seed}_anchors_pred"] = npy(anchors_pred)
+        arrs[f"s{seed}_classes_pred"] = npy(classes_pred)
+        arrs[f"s{seed}_gt_label"] = npy(gt_l)
+        print(f"  trainer seed {seed}: losses {[round(float(l), 5) for l in losses]}")
+    save("trainer", **arrs)
+
+
 if __name__ == "__main__":
     for fn in (gen_anchors, gen_boxmath, gen_proposals, gen_nms, gen_anchor_targets,
-               gen_proposal_targets, gen_roi, gen_rpn_forward):
+               gen_proposal_targets, gen_roi, gen_rpn_forward, gen_trainer):
         print(fn.__name__)
         fn()

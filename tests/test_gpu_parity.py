@@ -575,3 +575,56 @@ def test_step_is_cuda_graph_capturable(F):
         torch.cuda.synchronize()
         e_rois, e_pool = step()
         assert torch.equal(g_rois, e_rois) and torch.equal(g_pool, e_pool)
+
+
+def test_trainer_matches_reference_losses(F):
+    """FasterRCNNTrainer.forward vs the reference trainer (golden: two batch-of-one runs on seeded features,
+    weights and GT).  Batched here: both images in one call must give the mean of the two reference runs."""
+    from trainer_fixture import TRAINER_SEEDS, load_trainer_weights, trainer_inputs
+    from two_stage_object_detection_b200.nets import FasterRCNNTrainer
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = load_golden("trainer")
+
+    class Fixed(torch.nn.Module):
+        def __init__(self, feat):
+            super().__init__()
+            self.feat = feat
+
+        def forward(self, x):
+            return self.feat
+
+    trainer = FasterRCNNTrainer(mode="train", num_classes=20).to(DEV)
+    feats, boxes, labels = [], [], []
+    for seed in TRAINER_SEEDS:
+        feat, w, bbox, label = trainer_inputs(seed)
+        load_trainer_weights(trainer, w)  # same weights for both seeds? no: weights are per seed -> run singly
+        trainer.feat_extra = Fixed(feat.to(DEV))
+        losses, anchors_pred, classes_pred, _, gt_b, gt_l = trainer([torch.zeros(3, 320, 320)], [bbox], [label])
+        ref = g[f"s{seed}_losses"]
+        got = np.array([float(l.detach()) for l in losses])
+        assert np.allclose(got, ref, rtol=2e-3, atol=1e-4), (seed, got, ref)
+        assert np.array_equal(N(gt_l), g[f"s{seed}_gt_label"])
+        same = np.mean(np.all(np.abs(N(anchors_pred) - g[f"s{seed}_anchors_pred"]) < 0.05, axis=2))
+        assert same > 0.95, same
+        feats.append(feat)
+        boxes.append(bbox)
+        labels.append(label)
+    # batch of two with one set of weights: equals the mean of two single-image calls of the same module
+    trainer.feat_extra = Fixed(torch.cat(feats).to(DEV))
+    imgs = [torch.zeros(3, 320, 320)] * 2
+    both, *_ = trainer(imgs, boxes, labels)
+    singles = []
+    for i in range(2):
+        trainer.feat_extra = Fixed(feats[i].to(DEV))
+        l, *_ = trainer([imgs[i]], [boxes[i]], [labels[i]])
+        singles.append(torch.stack(l))
+    assert torch.allclose(torch.stack(both), (singles[0] + singles[1]) / 2, rtol=1e-5, atol=1e-6)
+    # and it trains: gradients reach the RPN convs, the head and (through RoIPool backward) the features
+    featp = torch.cat(feats).to(DEV).requires_grad_(True)
+    trainer.feat_extra = Fixed(featp)
+    both, *_ = trainer(imgs, boxes, labels)
+    both[-1].backward()
+    for p_ in (trainer.rpn.loc.weight, trainer.rpn.score.weight, trainer.head.cls_loc.weight, trainer.head.score.weight):
+        assert p_.grad is not None and torch.isfinite(p_.grad).all() and p_.grad.abs().sum() > 0
+    assert featp.grad is not None and featp.grad.abs().sum() > 0
