@@ -628,3 +628,19 @@ def test_trainer_matches_reference_losses(F):
     for p_ in (trainer.rpn.loc.weight, trainer.rpn.score.weight, trainer.head.cls_loc.weight, trainer.head.score.weight):
         assert p_.grad is not None and torch.isfinite(p_.grad).all() and p_.grad.abs().sum() > 0
     assert featp.grad is not None and featp.grad.abs().sum() > 0
+
+
+def test_ddp_training_step_two_gpus():
+    """Training configuration: DDP over NCCL, one process per GPU (skipped on a single-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tools", "ddp_train_step.py"), "--steps", "2"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "ddp ok" in out.stdout
