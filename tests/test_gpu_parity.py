@@ -518,6 +518,9 @@ def test_roi_pool_channel_tail_and_big_bins(F, O):
         wh = np.concatenate([rng.uniform(1, 10, (K // 2, 2)), rng.uniform(W * 0.5, W * 1.3, (K - K // 2, 2))])
         rois = np.concatenate([rng.integers(0, B, (K, 1)), c - wh / 2, c + wh / 2], 1).astype(np.float32)
         assert np.array_equal(N(F.roi_pool_forward(T(feat), T(rois), P, 1.0)), O.roi_pool(feat, rois, P, 1.0)), (H, W, P)
+        out, am = F.roi_pool_forward(T(feat), T(rois), P, 1.0, with_argmax=True)  # training variant of the table kernel
+        ro, ra = O.roi_pool(feat, rois, P, 1.0, return_argmax=True)
+        assert np.array_equal(N(out), ro) and np.array_equal(N(am), ra), (H, W, P)
         assert np.array_equal(N(F.roi_align_forward(T(feat), T(rois), P, 1.0, 2, False)),
                               O.roi_align(feat, rois, P, 1.0, 2, False)), (H, W, P)
 
@@ -530,8 +533,14 @@ def test_nan_and_inf_features_in_roi_pool(F, O):
     feat[0, 1, :, :] = -np.inf
     feat[0, 2, 5, 5] = np.inf
     rois = np.array([[0, 1, 1, 8, 8], [0, 0, 0, 19, 19], [0, 2.4, 2.4, 5.2, 5.2]], np.float32)
+    feat[0, 3, 8:12, 8:12] = 0.0       # exact ties (+0 / -0 mixed): the first element in row-major order wins
+    feat[0, 3, 9, 9] = -0.0
+    feat[0, 3, 12:, :] = -np.finfo(np.float32).max  # a real -FLT_MAX is never "selected" either
     for P in (7, 14):
         assert np.array_equal(N(F.roi_pool_forward(T(feat), T(rois), P, 1.0)), O.roi_pool(feat, rois, P, 1.0))
+        out, am = F.roi_pool_forward(T(feat), T(rois), P, 1.0, with_argmax=True)
+        ro, ra = O.roi_pool(feat, rois, P, 1.0, return_argmax=True)
+        assert np.array_equal(N(out), ro) and np.array_equal(N(am), ra), P
 
 
 def test_step_is_cuda_graph_capturable(F):

@@ -1,6 +1,7 @@
 // boxmath.cu -- anchors (utils/basic_anchors.py) and box arithmetic (utils/loc_bbox_iou.py) of the
 // reference as sm_100a kernels, plus the library's runtime helpers.
 #include <stdarg.h>
+#include <algorithm>
 #include <string.h>
 
 #include "common.cuh"
@@ -73,34 +74,77 @@ __global__ void bbox2loc_kernel(const float4* __restrict__ src, const float4* __
 }
 
 // ---------------------------------------------------------------------------------------------
-// utils/loc_bbox_iou.py:4-27   dense [Na,Nb]; a tile of b staged in shared memory, each thread
-// owns one a-row and streams over the b tile; stores are coalesced along Nb via a transposed
-// thread mapping (threadIdx.x walks b).
+// utils/loc_bbox_iou.py:4-27   dense [Na,Nb].  The output is the only large stream (4*Na*Nb bytes against
+// 16*(Na+Nb) read), so threads walk it FLAT: a thread owns four consecutive elements of the row-major
+// matrix and writes them with one 16-byte store whatever Nb is (the callers' Nb is the GT count: 1-90, so a
+// [rows x Nb-tile] mapping would leave most lanes idle and store 4*Nb-byte runs).  The b boxes and their
+// areas are staged in shared memory once per CTA (grid-stride loop), the a box is re-read only when the
+// flat index crosses a row.
 // ---------------------------------------------------------------------------------------------
-constexpr int IOU_TB = 128;  // b boxes per CTA tile (threadIdx.x)
-constexpr int IOU_TA = 8;    // a rows per thread-row group (threadIdx.y)
-constexpr int IOU_ROWS = 32; // a rows per CTA
+constexpr int IOU_THREADS = 256;
+constexpr int IOU_STAGE = 1024;  // b boxes kept in shared memory (20 KB); larger Nb reads b through L1
 
-__global__ void __launch_bounds__(IOU_TB* IOU_TA)
-bbox_iou_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int64_t na, int64_t nb,
+template <bool STAGED, bool VEC>
+__global__ void __launch_bounds__(IOU_THREADS)
+bbox_iou_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int64_t na, int nb, int64_t total,
                 float* __restrict__ out) {
-    __shared__ float4 sa[IOU_ROWS];
-    __shared__ float sarea[IOU_ROWS];
-    int64_t a0 = (int64_t)blockIdx.y * IOU_ROWS;
-    int64_t j = (int64_t)blockIdx.x * IOU_TB + threadIdx.x;
-    int tid = threadIdx.y * IOU_TB + threadIdx.x;
-    if (tid < IOU_ROWS && a0 + tid < na) {
-        float4 v = __ldg(a + a0 + tid);
-        sa[tid] = v;
-        sarea[tid] = box_area(v);
+    __shared__ float4 sb[STAGED ? IOU_STAGE : 1];
+    __shared__ float sarea[STAGED ? IOU_STAGE : 1];
+    if (STAGED) {
+        for (int j = threadIdx.x; j < nb; j += IOU_THREADS) {
+            float4 v = __ldg(b + j);
+            sb[j] = v;
+            sarea[j] = box_area(v);
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    if (j >= nb) return;
-    float4 bb = __ldg(b + j);
-    float barea = box_area(bb);
+    const int64_t quads = (total + 3) >> 2;
+    for (int64_t q = (int64_t)blockIdx.x * IOU_THREADS + threadIdx.x; q < quads; q += (int64_t)gridDim.x * IOU_THREADS) {
+        const int64_t idx = q << 2;
+        int64_t i;
+        int j;
+        if (total < (1ll << 31)) {  // uniform: 32-bit division whenever it is enough
+            uint32_t ii = (uint32_t)idx / (uint32_t)nb;
+            i = ii;
+            j = (int)((uint32_t)idx - ii * (uint32_t)nb);
+        } else {
+            i = idx / nb;
+            j = (int)(idx - i * nb);
+        }
+        float4 av = __ldg(a + i);
+        float aa = box_area(av);
+        float r[4];
+        const int nvalid = (int)min((int64_t)4, total - idx);
 #pragma unroll
-    for (int r = threadIdx.y; r < IOU_ROWS; r += IOU_TA) {
-        if (a0 + r < na) out[(a0 + r) * nb + j] = iou_eps(sa[r], sarea[r], bb, barea);
+        for (int k = 0; k < 4; ++k) {
+            r[k] = 0.f;
+            if (k < nvalid) {
+                float4 bv;
+                float ba;
+                if (STAGED) {
+                    bv = sb[j];
+                    ba = sarea[j];
+                } else {
+                    bv = __ldg(b + j);
+                    ba = box_area(bv);
+                }
+                r[k] = iou_eps(av, aa, bv, ba);
+                if (++j == nb && k < 3) {
+                    j = 0;
+                    if (++i < na) {
+                        av = __ldg(a + i);
+                        aa = box_area(av);
+                    }
+                }
+            }
+        }
+        if (VEC && nvalid == 4) {
+            __stcs(reinterpret_cast<float4*>(out + idx), make_float4(r[0], r[1], r[2], r[3]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < nvalid) out[idx + k] = r[k];
+        }
     }
 }
 
@@ -181,10 +225,19 @@ int frcnn_bbox_iou(const float* a, const float* b, int64_t na, int64_t nb, float
     FRCNN_CHECK_ARG(na >= 0 && nb >= 0, "frcnn_bbox_iou: bad shape");
     if (na == 0 || nb == 0) return FRCNN_OK;
     FRCNN_CHECK_ARG(a && b && out, "frcnn_bbox_iou: null pointer");
-    dim3 grid(cdiv(nb, IOU_TB), cdiv(na, IOU_ROWS));
-    FRCNN_CHECK_ARG(grid.y <= 65535, "frcnn_bbox_iou: Na too large (max %d)", 65535 * IOU_ROWS);
-    bbox_iou_kernel<<<grid, dim3(IOU_TB, IOU_TA), 0, (cudaStream_t)stream>>>(
-        (const float4*)a, (const float4*)b, na, nb, out);
+    FRCNN_CHECK_ARG(nb < (1ll << 31) && na <= (1ll << 40) / nb, "frcnn_bbox_iou: matrix too large");
+    const int64_t total = na * nb;
+    const int64_t quads = (total + 3) / 4;
+    const int grid = (int)std::min<int64_t>((quads + IOU_THREADS - 1) / IOU_THREADS, (int64_t)sm_count() * 16);
+    const bool vec = ((uintptr_t)out & 15) == 0;
+    const bool staged = nb <= IOU_STAGE;
+    auto* a4 = (const float4*)a;
+    auto* b4 = (const float4*)b;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (staged && vec) bbox_iou_kernel<true, true><<<grid, IOU_THREADS, 0, st>>>(a4, b4, na, (int)nb, total, out);
+    else if (staged) bbox_iou_kernel<true, false><<<grid, IOU_THREADS, 0, st>>>(a4, b4, na, (int)nb, total, out);
+    else if (vec) bbox_iou_kernel<false, true><<<grid, IOU_THREADS, 0, st>>>(a4, b4, na, (int)nb, total, out);
+    else bbox_iou_kernel<false, false><<<grid, IOU_THREADS, 0, st>>>(a4, b4, na, (int)nb, total, out);
     FRCNN_LAUNCH_CHECK();
     return FRCNN_OK;
 }

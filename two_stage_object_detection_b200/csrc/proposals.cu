@@ -516,7 +516,7 @@ __device__ __forceinline__ bool nms_suppresses(const float4& r, float ra, const 
     float inter = w * h;
     float uni = ra + ca;
     uni = uni - inter;
-    return (inter / uni) > thr;
+    return div_mostly_zero(inter, uni) > thr;
 }
 
 struct NmsArgs {

@@ -379,7 +379,55 @@ __device__ __noinline__ V tab_big_bin(const V* tab, int hr, int wr, int W) {
     return v;
 }
 
-template <int P, int TAB_THREADS, int CS, int MINB>
+// argmax of one bin (training): the reference records the first element, in row-major order, that
+// attains the maximum under `v > best`; with the maximum already known that is the first table-T11
+// element equal to it (clamped NaN / -inf never match a maximum above -FLT_MAX; a maximum of exactly
+// -FLT_MAX means nothing was ever selected: -1).
+__device__ __forceinline__ void first_match(int4& idx, const float4& t, const float4& v, int p) {
+    if (idx.x < 0 && t.x == v.x) idx.x = p;
+    if (idx.y < 0 && t.y == v.y) idx.y = p;
+    if (idx.z < 0 && t.z == v.z) idx.z = p;
+    if (idx.w < 0 && t.w == v.w) idx.w = p;
+}
+__device__ __forceinline__ void first_match(int2& idx, const float2& t, const float2& v, int p) {
+    if (idx.x < 0 && t.x == v.x) idx.x = p;
+    if (idx.y < 0 && t.y == v.y) idx.y = p;
+}
+__device__ __forceinline__ void vneg(int4& i) { i = make_int4(-1, -1, -1, -1); }
+__device__ __forceinline__ void vneg(int2& i) { i = make_int2(-1, -1); }
+// a maximum of -FLT_MAX was never "selected"; empty bins have no argmax either
+__device__ __forceinline__ void argmax_fixup(int4& i, const float4& v, bool empty) {
+    if (empty || v.x == -FLT_MAX) i.x = -1;
+    if (empty || v.y == -FLT_MAX) i.y = -1;
+    if (empty || v.z == -FLT_MAX) i.z = -1;
+    if (empty || v.w == -FLT_MAX) i.w = -1;
+}
+__device__ __forceinline__ void argmax_fixup(int2& i, const float2& v, bool empty) {
+    if (empty || v.x == -FLT_MAX) i.x = -1;
+    if (empty || v.y == -FLT_MAX) i.y = -1;
+}
+__device__ __forceinline__ void istore(int* o, int stride, const int4& i, int cs) {
+    o[0] = i.x;
+    if (cs > 1) o[stride] = i.y;
+    if (cs > 2) o[2 * stride] = i.z;
+    if (cs > 3) o[3 * stride] = i.w;
+}
+__device__ __forceinline__ void istore(int* o, int stride, const int2& i, int cs) {
+    o[0] = i.x;
+    if (cs > 1) o[stride] = i.y;
+}
+template <int CS>
+struct IdxT;
+template <>
+struct IdxT<4> {
+    typedef int4 type;
+};
+template <>
+struct IdxT<2> {
+    typedef int2 type;
+};
+
+template <int P, int TAB_THREADS, int CS, int MINB, bool ARGMAX>
 __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs a) {
     typedef typename VecT<CS>::type V;
     constexpr int BINS = P * P;
@@ -479,6 +527,17 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
             float* o = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.out) + s_ob[cur][j]) + e;
             if (full) vstore<true>(o, BINS, v, m, cs);
             else if (valid) vstore<false>(o, BINS, v, m, cs);
+            if (ARGMAX) {
+                typename IdxT<CS>::type idx;
+                vneg(idx);
+                const int hr = s_hraw[cur][j][ph], wr = s_wraw[cur][j][pw];
+                for (int y = hr & 0xFFFF; y < (hr >> 16); ++y)
+                    for (int x = wr & 0xFFFF; x < (wr >> 16); ++x) first_match(idx, tab[y * W + x], v, y * W + x);
+                argmax_fixup(idx, v, m == 0u);
+                if (valid)
+                    istore(reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(a.argmax) + s_ob[cur][j]) + e, BINS,
+                           idx, cs);
+            }
         };
         if (nb == NB && cs == CS) {
 #pragma unroll
@@ -1064,7 +1123,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
     }
     // inference RoIPool: sparse max-table kernel.  4 channels per CTA (float4 tables) when that leaves two
     // CTAs per SM, else 2 channels (float2 tables), else one CTA per SM
-    if (!argmax && PH == PW && (PH == 7 || PH == 14)) {
+    if (PH == PW && (PH == 7 || PH == 14)) {
         const size_t HWp = (size_t)((H * W + 3) & ~3);
         const size_t smem4 = 4 * HWp * 16, smem2 = 4 * HWp * 8;
         const size_t two_per_sm = 92 * 1024, one_per_sm = 200 * 1024;  // dynamic part; ~20 KB static on top
@@ -1083,7 +1142,9 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             int want = cdiv(8 * sm_count(), B * slabs);
             a.groups = std::max(1, std::min(g, want));
             const size_t smem = tcs == 4 ? smem4 : smem2;
-#define FRCNN_TAB(PP_, CS_, MB_) launch_tab(roi_pool_tab_kernel<PP_, 392, CS_, MB_>, a, smem, tab_threads, stream)
+#define FRCNN_TAB(PP_, CS_, MB_)                                                                              \
+    (argmax ? launch_tab(roi_pool_tab_kernel<PP_, 392, CS_, MB_, true>, a, smem, tab_threads, stream)          \
+            : launch_tab(roi_pool_tab_kernel<PP_, 392, CS_, MB_, false>, a, smem, tab_threads, stream))
             if (PH == 7) {
                 if (tcs == 4) return minb == 2 ? FRCNN_TAB(7, 4, 2) : FRCNN_TAB(7, 4, 1);
                 return minb == 2 ? FRCNN_TAB(7, 2, 2) : FRCNN_TAB(7, 2, 1);

@@ -6,7 +6,10 @@
 
 namespace frcnn {
 
-constexpr int AT_TILE = 256;
+constexpr int AT_THREADS = 256;
+constexpr int AT_PER = 4;                       // anchors per thread, strided by AT_THREADS inside the tile
+constexpr int AT_TILE = AT_THREADS * AT_PER;    // 1024 anchors per CTA
+constexpr int AT_WARPS = AT_THREADS / 32;
 
 struct AnchorTargetArgs {
     AnchorGen gen;
@@ -16,9 +19,9 @@ struct AnchorTargetArgs {
     int n_sample, n_pos;
     float pos_thr, neg_thr;
     // workspace
-    float* max_iou;              // [B,N]
-    int* argmax;                 // [B,N]  (bit 30 = forced by a GT's best anchor)
-    unsigned long long* colbest; // [B,Gmax] packed (key<<32 | ~anchor)
+    int* packed;                 // [B,N]  argmax | class << 28 | forced << 30
+    unsigned long long* colbest; // [B,Gmax] packed (key<<32 | ~anchor), zeroed per call
+    int* done;                   // [B] tiles finished (zeroed per call, same memset as colbest)
     int* cnt_pos;                // [B,tiles]
     int* cnt_neg;                // [B,tiles]
     // outputs
@@ -27,116 +30,136 @@ struct AnchorTargetArgs {
     int* argmax_out;
 };
 
-constexpr int FORCED_BIT = 0x40000000;
+// one 32-bit word per anchor between the two launches (4 B written + 4 B read instead of max_iou + argmax)
+constexpr int AT_FORCED_BIT = 0x40000000;  // this anchor is some GT's best anchor (frcnn_training.py:56-62)
+constexpr int AT_CLS_SHIFT = 28;           // 0: ignore (-1), 1: negative (0), 2: positive (1), from the thresholds only
+constexpr int AT_ARG_MASK = 0xFFFF;        // argmax over the GT boxes (max_gt <= 4096)
 
-// K1: per anchor row max / argmax over the image's GT boxes; per GT column argmax (first index).
-__global__ void __launch_bounds__(AT_TILE) anchor_iou_kernel(AnchorTargetArgs a) {
+__device__ __forceinline__ int label_class(float max_iou, float pos_thr, float neg_thr) {
+    int c = 0;
+    if (max_iou < neg_thr) c = 1;   // frcnn_training.py:79
+    if (max_iou >= pos_thr) c = 2;  // :80
+    return c;
+}
+
+// K1: per anchor, row max / argmax over the image's GT boxes and the label class the thresholds give;
+// per GT, the column argmax (largest IoU, then smallest anchor index: torch.argmax's first index) through
+// REDUX + packed 64-bit atomicMax.  The CTA that finishes an image last applies "each GT's best anchor
+// takes that GT; later GT wins" to at most G words and corrects the per-tile counts, so no kernel has to
+// re-read every anchor for it.
+__global__ void __launch_bounds__(AT_THREADS) anchor_iou_kernel(AnchorTargetArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sgt = reinterpret_cast<float4*>(smem_raw);
     float* sarea = reinterpret_cast<float*>(sgt + a.max_gt);
     unsigned long long* sbest = reinterpret_cast<unsigned long long*>(sarea + ((a.max_gt + 1) & ~1));
+    __shared__ int s_cnt[2][AT_WARPS];
+    __shared__ int s_last;
     const int b = blockIdx.y, tile = blockIdx.x;
     const int G = min(a.n_gt[b], a.max_gt);
-    const int lane = threadIdx.x & 31;
-    for (int g = threadIdx.x; g < G; g += AT_TILE) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int g = tid; g < G; g += AT_THREADS) {
         float4 v = __ldg(a.bbox + (size_t)b * a.max_gt + g);
         sgt[g] = v;
         sarea[g] = box_area(v);
         sbest[g] = 0ull;
     }
     __syncthreads();
-    const int i = tile * AT_TILE + threadIdx.x;
-    const bool valid = i < a.n;
-    float4 an = valid ? load_anchor(a.gen, i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float aa = box_area(an);
-    float best = 0.f;
-    int besti = 0;
-    for (int g = 0; g < G; ++g) {
-        float v = iou_eps(an, aa, sgt[g], sarea[g]);
-        if (g == 0 || beats(v, best)) {
-            best = v;
-            besti = g;
-        }
-        // column argmax: biggest key, then smallest anchor index (lanes are in index order)
-        uint32_t key = valid ? score_key(v) : 0u;
-        uint32_t m = __reduce_max_sync(0xFFFFFFFFu, key);
-        uint32_t who = __ballot_sync(0xFFFFFFFFu, key == m);
-        if (m != 0u && lane == __ffs(who) - 1) {
-            unsigned long long packed = ((unsigned long long)m << 32) | (uint32_t)(~(uint32_t)i);
-            atomicMax(&sbest[g], packed);
-        }
-    }
-    if (valid) {
-        a.max_iou[(size_t)b * a.n + i] = best;
-        a.argmax[(size_t)b * a.n + i] = besti;
-    }
-    __syncthreads();
-    for (int g = threadIdx.x; g < G; g += AT_TILE)
-        if (sbest[g]) atomicMax(a.colbest + (size_t)b * a.max_gt + g, sbest[g]);
-}
-
-__device__ __forceinline__ int label_before_cap(float max_iou, bool forced, float pos_thr, float neg_thr) {
-    int l = -1;
-    if (max_iou < neg_thr) l = 0;
-    if (max_iou >= pos_thr) l = 1;
-    if (forced) l = 1;
-    return l;
-}
-
-__device__ __forceinline__ int block_sum_256(int v, int* scratch) {
-    v = __reduce_add_sync(0xFFFFFFFFu, v);
-    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-    __syncthreads();
-    int t = 0;
+    const int i0 = tile * AT_TILE + tid;
+    float4 an[AT_PER];
+    float aa[AT_PER];
+    uint32_t kbest[AT_PER];  // row max as an order-preserving key: NaN largest, first index wins ties (torch.max)
+    int besti[AT_PER];
 #pragma unroll
-    for (int w = 0; w < AT_TILE / 32; ++w) t += scratch[w];
-    __syncthreads();
-    return t;
-}
-
-// K2: "each GT's best anchor takes that GT; later GT wins" (frcnn_training.py:60-62, :82) + counts
-__global__ void __launch_bounds__(AT_TILE) anchor_force_count_kernel(AnchorTargetArgs a) {
-    __shared__ int forced[AT_TILE];
-    __shared__ int scratch[AT_TILE / 32];
-    const int b = blockIdx.y, tile = blockIdx.x;
-    const int G = min(a.n_gt[b], a.max_gt);
-    const int t0 = tile * AT_TILE;
-    forced[threadIdx.x] = -1;
-    __syncthreads();
-    for (int g = threadIdx.x; g < G; g += AT_TILE) {
-        unsigned long long p = a.colbest[(size_t)b * a.max_gt + g];
-        int anchor = (int)(~(uint32_t)(p & 0xFFFFFFFFull));
-        if (p != 0ull && anchor >= t0 && anchor < t0 + AT_TILE) atomicMax(&forced[anchor - t0], g);
+    for (int k = 0; k < AT_PER; ++k) {
+        const int i = i0 + k * AT_THREADS;
+        an[k] = i < a.n ? load_anchor(a.gen, i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        aa[k] = box_area(an[k]);
+        kbest[k] = 0u;
+        besti[k] = 0;
     }
-    __syncthreads();
-    const int i = t0 + threadIdx.x;
+    for (int g = 0; g < G; ++g) {
+        const float4 gt = sgt[g];
+        const float ga = sarea[g];
+        uint32_t kmax = 0u;
+        int imax = 0x7FFFFFFF;
+#pragma unroll
+        for (int k = 0; k < AT_PER; ++k) {
+            const int i = i0 + k * AT_THREADS;
+            uint32_t key = score_key(iou_eps(an[k], aa[k], gt, ga));
+            if (key > kbest[k]) {  // keys are never 0: g = 0 always enters
+                kbest[k] = key;
+                besti[k] = g;
+            }
+            if (i >= a.n) key = 0u;
+            if (key > kmax) {  // ascending i: the first of equal keys stays
+                kmax = key;
+                imax = i;
+            }
+        }
+        // column argmax: biggest key, then smallest anchor index
+        const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, kmax);
+        if (m != 0u) {
+            const int cand = kmax == m ? imax : 0x7FFFFFFF;
+            const int first = __reduce_min_sync(0xFFFFFFFFu, cand);
+            if (cand == first) atomicMax(&sbest[g], ((unsigned long long)m << 32) | (uint32_t)(~(uint32_t)first));
+        }
+    }
     int pos = 0, neg = 0;
-    if (i < a.n) {
-        size_t o = (size_t)b * a.n + i;
-        int f = forced[threadIdx.x];
-        if (f >= 0) a.argmax[o] = f | FORCED_BIT;
-        int l = label_before_cap(a.max_iou[o], f >= 0, a.pos_thr, a.neg_thr);
-        pos = l == 1;
-        neg = l == 0;
+#pragma unroll
+    for (int k = 0; k < AT_PER; ++k) {
+        const int i = i0 + k * AT_THREADS;
+        if (i < a.n) {
+            const int c = label_class(G > 0 ? key_score(kbest[k]) : 0.f, a.pos_thr, a.neg_thr);
+            pos += c == 2;
+            neg += c == 1;
+            a.packed[(size_t)b * a.n + i] = besti[k] | (c << AT_CLS_SHIFT);
+        }
     }
-    int tp = block_sum_256(pos, scratch);
-    int tn = block_sum_256(neg, scratch);
-    if (threadIdx.x == 0) {
-        a.cnt_pos[b * a.tiles + tile] = tp;
-        a.cnt_neg[b * a.tiles + tile] = tn;
+    pos = __reduce_add_sync(0xFFFFFFFFu, pos);
+    neg = __reduce_add_sync(0xFFFFFFFFu, neg);
+    if (lane == 0) {
+        s_cnt[0][warp] = pos;
+        s_cnt[1][warp] = neg;
+    }
+    __syncthreads();  // sbest complete, s_cnt visible
+    for (int g = tid; g < G; g += AT_THREADS)
+        if (sbest[g]) atomicMax(a.colbest + (size_t)b * a.max_gt + g, sbest[g]);
+    if (tid < 2) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < AT_WARPS; ++w) t += s_cnt[tid][w];
+        (tid == 0 ? a.cnt_pos : a.cnt_neg)[b * a.tiles + tile] = t;
+    }
+    // last CTA of the image: everything the others wrote is visible after their fence + ticket
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(a.done + b, 1) == a.tiles - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int g = tid; g < G; g += AT_THREADS) {
+        const unsigned long long p = __ldcg(a.colbest + (size_t)b * a.max_gt + g);
+        if (p == 0ull) continue;
+        const int anchor = (int)(~(uint32_t)(p & 0xFFFFFFFFull));
+        // forced words outrank every unforced one; among forced ones the larger g (the later GT) wins
+        const int old = atomicMax(a.packed + (size_t)b * a.n + anchor, g | AT_FORCED_BIT);
+        if (!(old & AT_FORCED_BIT)) {  // first GT to claim this anchor: its label becomes 1 (:82)
+            const int c = (old >> AT_CLS_SHIFT) & 3, t = anchor / AT_TILE;
+            if (c != 2) atomicAdd(a.cnt_pos + b * a.tiles + t, 1);
+            if (c == 1) atomicSub(a.cnt_neg + b * a.tiles + t, 1);
+        }
     }
 }
 
-// K3: first-k cap on positives, the len()-of-a-tuple negative rule, bbox2loc for every anchor
-__global__ void __launch_bounds__(AT_TILE) anchor_label_kernel(AnchorTargetArgs a) {
-    __shared__ int scratch[AT_TILE / 32];
-    __shared__ int wsum_pos[AT_TILE / 32], wsum_neg[AT_TILE / 32];
-    __shared__ int s_pre_pos, s_pre_neg, s_tot_pos, s_tot_neg;
+// K2: first-k cap on positives, the len()-of-a-tuple negative rule, bbox2loc for every anchor
+__global__ void __launch_bounds__(AT_THREADS) anchor_label_kernel(AnchorTargetArgs a) {
+    __shared__ int s_red[4][AT_WARPS];
+    __shared__ int s_wpos[AT_PER * AT_WARPS], s_wneg[AT_PER * AT_WARPS];
     const int b = blockIdx.y, tile = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // totals and prefixes over tiles
     int pp = 0, pn = 0, tp = 0, tn = 0;
-    for (int t = threadIdx.x; t < a.tiles; t += AT_TILE) {
+    for (int t = tid; t < a.tiles; t += AT_THREADS) {
         int cp = a.cnt_pos[b * a.tiles + t], cn = a.cnt_neg[b * a.tiles + t];
         tp += cp;
         tn += cn;
@@ -145,55 +168,80 @@ __global__ void __launch_bounds__(AT_TILE) anchor_label_kernel(AnchorTargetArgs 
             pn += cn;
         }
     }
-    pp = block_sum_256(pp, scratch);
-    pn = block_sum_256(pn, scratch);
-    tp = block_sum_256(tp, scratch);
-    tn = block_sum_256(tn, scratch);
-    if (threadIdx.x == 0) {
-        s_pre_pos = pp;
-        s_pre_neg = pn;
-        s_tot_pos = tp;
-        s_tot_neg = tn;
-    }
-    __syncthreads();
-    const int G = min(a.n_gt[b], a.max_gt);
-    const int i = tile * AT_TILE + threadIdx.x;
-    const bool valid = i < a.n;
-    size_t o = (size_t)b * a.n + (valid ? i : 0);
-    int am = valid ? a.argmax[o] : 0;
-    bool forced = (am & FORCED_BIT) != 0;
-    am &= ~FORCED_BIT;
-    int l = valid ? label_before_cap(a.max_iou[o], forced, a.pos_thr, a.neg_thr) : -1;
-    // exclusive ranks inside the tile
-    uint32_t bp = __ballot_sync(0xFFFFFFFFu, l == 1), bn = __ballot_sync(0xFFFFFFFFu, l == 0);
+    pp = __reduce_add_sync(0xFFFFFFFFu, pp);
+    pn = __reduce_add_sync(0xFFFFFFFFu, pn);
+    tp = __reduce_add_sync(0xFFFFFFFFu, tp);
+    tn = __reduce_add_sync(0xFFFFFFFFu, tn);
     if (lane == 0) {
-        wsum_pos[warp] = __popc(bp);
-        wsum_neg[warp] = __popc(bn);
+        s_red[0][warp] = pp;
+        s_red[1][warp] = pn;
+        s_red[2][warp] = tp;
+        s_red[3][warp] = tn;
+    }
+    const int G = min(a.n_gt[b], a.max_gt);
+    const int i0 = tile * AT_TILE + tid;
+    int am[AT_PER], l[AT_PER];
+    uint32_t bp[AT_PER], bn[AT_PER];
+#pragma unroll
+    for (int k = 0; k < AT_PER; ++k) {
+        const int i = i0 + k * AT_THREADS;
+        const int w = i < a.n ? __ldcg(a.packed + (size_t)b * a.n + i) : 0;
+        const int c = (w & AT_FORCED_BIT) ? 2 : ((w >> AT_CLS_SHIFT) & 3);
+        am[k] = w & AT_ARG_MASK;
+        l[k] = i < a.n ? c - 1 : -1;
+        bp[k] = __ballot_sync(0xFFFFFFFFu, l[k] == 1);
+        bn[k] = __ballot_sync(0xFFFFFFFFu, l[k] == 0);
+        if (lane == 0) {
+            s_wpos[k * AT_WARPS + warp] = __popc(bp[k]);
+            s_wneg[k * AT_WARPS + warp] = __popc(bn[k]);
+        }
     }
     __syncthreads();
-    int rp = s_pre_pos + __popc(bp & lanemask_lt()), rn = s_pre_neg + __popc(bn & lanemask_lt());
-    for (int w = 0; w < warp; ++w) {
-        rp += wsum_pos[w];
-        rn += wsum_neg[w];
+    pp = pn = tp = tn = 0;
+#pragma unroll
+    for (int w = 0; w < AT_WARPS; ++w) {
+        pp += s_red[0][w];
+        pn += s_red[1][w];
+        tp += s_red[2][w];
+        tn += s_red[3][w];
     }
-    const int tot_pos = s_tot_pos, tot_neg = s_tot_neg;
-    if (l == 1 && tot_pos > a.n_pos && rp >= a.n_pos) l = -1;  // frcnn_training.py:85-91
-    const int pos_len = tot_pos > a.n_pos ? a.n_pos : tot_pos;
+    // exclusive ranks inside the tile: chunk k of the tile precedes chunk k+1, warps in order inside a chunk
+    static_assert(AT_PER * AT_WARPS == 32, "one warp scans the per-(chunk,warp) counts");
+    if (warp == 0) {
+        int vp = s_wpos[lane], vn = s_wneg[lane];
+        int ip = vp, in = vn;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int up = __shfl_up_sync(0xFFFFFFFFu, ip, d), un = __shfl_up_sync(0xFFFFFFFFu, in, d);
+            if (lane >= d) {
+                ip += up;
+                in += un;
+            }
+        }
+        s_wpos[lane] = ip - vp;
+        s_wneg[lane] = in - vn;
+    }
+    __syncthreads();
+    const int pos_len = tp > a.n_pos ? a.n_pos : tp;
     const int n_neg = a.n_sample - pos_len;
-    if (l == 0 && 1 > n_neg) {  // frcnn_training.py:96-99: len(neg_index) is 1
-        int start = n_neg == 0 ? 0 : max(tot_neg + n_neg, 0);
-        if (rn >= start) l = -1;
+    const int neg_start = n_neg == 0 ? 0 : max(tn + n_neg, 0);
+    const bool any_pos = pos_len > 0 && G > 0;  // (label > 0).any()
+#pragma unroll
+    for (int k = 0; k < AT_PER; ++k) {
+        const int i = i0 + k * AT_THREADS;
+        if (i >= a.n) continue;
+        const int rp = pp + s_wpos[k * AT_WARPS + warp] + __popc(bp[k] & lanemask_lt());
+        const int rn = pn + s_wneg[k * AT_WARPS + warp] + __popc(bn[k] & lanemask_lt());
+        int lab = l[k];
+        if (lab == 1 && tp > a.n_pos && rp >= a.n_pos) lab = -1;  // frcnn_training.py:85-91
+        if (lab == 0 && 1 > n_neg && rn >= neg_start) lab = -1;   // :96-99: len(neg_index) is 1
+        const size_t o = (size_t)b * a.n + i;
+        __stcs(a.label + o, (long long)lab);
+        if (a.argmax_out) __stcs(a.argmax_out + o, am[k]);
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (any_pos) out = encode_box(load_anchor(a.gen, i), __ldg(a.bbox + (size_t)b * a.max_gt + am[k]));
+        __stcs(a.loc + o, out);
     }
-    if (!valid) return;
-    a.label[o] = (long long)l;
-    if (a.argmax_out) a.argmax_out[o] = am;
-    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pos_len > 0 && G > 0) {  // (label > 0).any()
-        float4 an = load_anchor(a.gen, i);
-        float4 gt = __ldg(a.bbox + (size_t)b * a.max_gt + am);
-        out = encode_box(an, gt);
-    }
-    a.loc[o] = out;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -340,9 +388,10 @@ static size_t at_smem(int max_gt) {
 }
 
 struct AtWs {
-    float* max_iou;
-    int* argmax;
+    int* packed;
     unsigned long long* colbest;
+    int* done;
+    size_t zero_bytes;  // colbest and done are one region, cleared by one memset
     int* cnt_pos;
     int* cnt_neg;
 };
@@ -350,9 +399,11 @@ struct AtWs {
 static size_t at_layout(Workspace& ws, const frcnn_anchor_target_params* p, AtWs* out) {
     int tiles = cdiv(p->num_anchors, AT_TILE);
     AtWs w;
-    w.max_iou = ws.take<float>((size_t)p->batch * p->num_anchors);
-    w.argmax = ws.take<int>((size_t)p->batch * p->num_anchors);
-    w.colbest = ws.take<unsigned long long>((size_t)p->batch * (p->max_gt > 0 ? p->max_gt : 1));
+    w.packed = ws.take<int>((size_t)p->batch * p->num_anchors);
+    const size_t ncol = (size_t)p->batch * (p->max_gt > 0 ? p->max_gt : 1);
+    w.zero_bytes = ncol * sizeof(unsigned long long) + (size_t)p->batch * sizeof(int);
+    w.colbest = reinterpret_cast<unsigned long long*>(ws.take<unsigned char>(w.zero_bytes));
+    w.done = reinterpret_cast<int*>(w.colbest + ncol);
     w.cnt_pos = ws.take<int>((size_t)p->batch * tiles);
     w.cnt_neg = ws.take<int>((size_t)p->batch * tiles);
     if (out) *out = w;
@@ -413,25 +464,22 @@ int frcnn_anchor_targets(const frcnn_anchor_target_params* p, const frcnn_anchor
     a.n_pos = p->n_pos;
     a.pos_thr = p->pos_iou_thresh;
     a.neg_thr = p->neg_iou_thresh;
-    a.max_iou = w.max_iou;
-    a.argmax = w.argmax;
+    a.packed = w.packed;
     a.colbest = w.colbest;
+    a.done = w.done;
     a.cnt_pos = w.cnt_pos;
     a.cnt_neg = w.cnt_neg;
     a.loc = (float4*)loc;
     a.label = (long long*)label;
     a.argmax_out = argmax;
-    FRCNN_CUDA(cudaMemsetAsync(w.colbest, 0, sizeof(unsigned long long) * p->batch * (p->max_gt > 0 ? p->max_gt : 1),
-                               stream));
+    FRCNN_CUDA(cudaMemsetAsync(w.colbest, 0, w.zero_bytes, stream));
     size_t smem = at_smem(p->max_gt);
     if (smem > 48 * 1024)
         FRCNN_CUDA(cudaFuncSetAttribute(anchor_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(a.tiles, p->batch);
-    anchor_iou_kernel<<<grid, AT_TILE, smem, stream>>>(a);
+    anchor_iou_kernel<<<grid, AT_THREADS, smem, stream>>>(a);
     FRCNN_LAUNCH_CHECK();
-    anchor_force_count_kernel<<<grid, AT_TILE, 0, stream>>>(a);
-    FRCNN_LAUNCH_CHECK();
-    anchor_label_kernel<<<grid, AT_TILE, 0, stream>>>(a);
+    anchor_label_kernel<<<grid, AT_THREADS, 0, stream>>>(a);
     FRCNN_LAUNCH_CHECK();
     return FRCNN_OK;
 }
