@@ -65,6 +65,35 @@ def test_boxmath(F):
     assert loc2bbox(torch.zeros(0, 4, device=DEV), torch.zeros(0, 4, device=DEV)).shape == (0, 4)
 
 
+@pytest.mark.parametrize("shape", [(1, 1), (7, 3), (1000, 8), (333, 64), (50, 1100), (5, 2048), (4099, 5)])
+def test_dense_iou_shapes_vs_oracle(F, O, shape):
+    """Every dense-IoU kernel variant (rows of four / flat, b staged in shared memory / read through L1,
+    16-byte aligned output or not), with degenerate boxes: zero area, inverted, touching, NaN, inf."""
+    na, nb = shape
+    rng = np.random.default_rng(na * 31 + nb)
+
+    def boxes(n):
+        c = rng.uniform(0, 300, (n, 2)).astype(np.float32)
+        wh = rng.uniform(0, 120, (n, 2)).astype(np.float32)
+        b = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+        b[::7, 2:] = b[::7, :2]             # zero area
+        b[3::11] = b[3::11][:, [2, 3, 0, 1]]  # inverted
+        if n > 5:
+            b[5, 0] = np.nan
+            b[2, 2] = np.inf
+        return np.round(b * 4) / 4          # quarter-pixel grid: exact ties and touching edges occur
+
+    a, b = boxes(na), boxes(nb)
+    with np.errstate(all="ignore"):
+        ref = O.iou(a, b)
+    got = N(F.bbox_iou(T(a), T(b)))
+    assert np.array_equal(got, ref, equal_nan=True)
+    # output view that is only 4-byte aligned: the scalar-store variants
+    lib_out = torch.empty(na * nb + 1, dtype=torch.float32, device=DEV)[1:].view(na, nb)
+    got2 = N(F.bbox_iou(T(a), T(b), out=lib_out))
+    assert np.array_equal(got2, ref, equal_nan=True)
+
+
 def test_nms_exact(F):
     g = load_golden("nms")
     for i in range(int(g["n_cases"])):

@@ -148,6 +148,42 @@ bbox_iou_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int6
     }
 }
 
+// Fast path for Nb % 4 == 0 (and a 16-byte aligned output): a thread's four elements never cross a row,
+// so there is no per-element range or wrap test and the row index comes from one multiply-high.
+template <bool STAGED>
+__global__ void __launch_bounds__(IOU_THREADS)
+bbox_iou_rows4_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int nb, FastDiv by_quads_per_row,
+                      int64_t quads, float* __restrict__ out) {
+    __shared__ float4 sb[STAGED ? IOU_STAGE : 1];
+    const int qpr = by_quads_per_row.d;
+    if (STAGED) {  // box j lives at (j % 4) * qpr + j / 4: lanes reading their k-th box hit consecutive float4s
+        for (int j = threadIdx.x; j < nb; j += IOU_THREADS) sb[(j & 3) * qpr + (j >> 2)] = __ldg(b + j);
+        __syncthreads();
+    }
+    for (int64_t q = (int64_t)blockIdx.x * IOU_THREADS + threadIdx.x; q < quads; q += (int64_t)gridDim.x * IOU_THREADS) {
+        int64_t i;
+        int jq;
+        if (quads < (1ll << 31)) {
+            const int ii = fast_div((int)q, by_quads_per_row);
+            i = ii;
+            jq = (int)q - ii * qpr;
+        } else {
+            i = q / qpr;
+            jq = (int)(q - i * qpr);
+        }
+        const float4 av = __ldg(a + i);
+        const float aa = box_area(av);
+        const float4* bp = STAGED ? sb + jq : b + 4 * jq;
+        float r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 bv = STAGED ? bp[k * qpr] : __ldg(bp + k);
+            r[k] = iou_eps(av, aa, bv, box_area(bv));
+        }
+        __stcs(reinterpret_cast<float4*>(out) + q, make_float4(r[0], r[1], r[2], r[3]));
+    }
+}
+
 }  // namespace frcnn
 
 using namespace frcnn;
@@ -192,7 +228,7 @@ int frcnn_shifted_anchors(const float* base, int32_t A, int32_t stride, int32_t 
     int n = (int)n64;
     if (n == 0) return FRCNN_OK;
     FRCNN_CHECK_ARG(base && out, "frcnn_shifted_anchors: null pointer");
-    AnchorGen g{nullptr, (const float4*)base, A, stride, H, W};
+    AnchorGen g = make_anchor_gen(nullptr, base, A, stride, H, W);
     shifted_anchor_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(g, n, (float4*)out);
     FRCNN_LAUNCH_CHECK();
     return FRCNN_OK;
@@ -234,6 +270,13 @@ int frcnn_bbox_iou(const float* a, const float* b, int64_t na, int64_t nb, float
     auto* a4 = (const float4*)a;
     auto* b4 = (const float4*)b;
     cudaStream_t st = (cudaStream_t)stream;
+    if (vec && nb % 4 == 0) {
+        const FastDiv fd = make_fastdiv((int)(nb / 4));
+        if (staged) bbox_iou_rows4_kernel<true><<<grid, IOU_THREADS, 0, st>>>(a4, b4, (int)nb, fd, quads, out);
+        else bbox_iou_rows4_kernel<false><<<grid, IOU_THREADS, 0, st>>>(a4, b4, (int)nb, fd, quads, out);
+        FRCNN_LAUNCH_CHECK();
+        return FRCNN_OK;
+    }
     if (staged && vec) bbox_iou_kernel<true, true><<<grid, IOU_THREADS, 0, st>>>(a4, b4, na, (int)nb, total, out);
     else if (staged) bbox_iou_kernel<true, false><<<grid, IOU_THREADS, 0, st>>>(a4, b4, na, (int)nb, total, out);
     else if (vec) bbox_iou_kernel<false, true><<<grid, IOU_THREADS, 0, st>>>(a4, b4, na, (int)nb, total, out);

@@ -60,18 +60,57 @@ struct BaseAnchors {
     float v[FRCNN_MAX_BASE_ANCHORS][4];
 };
 
+// Division by a launch-invariant divisor: quotient = umulhi(n, mul) >> shr, exact for 0 <= n < 2^31
+// (the runtime `/` and `%` of the anchor index cost ~20 instructions each; three of them per anchor made
+// the streaming kernels issue-bound).
+struct FastDiv {
+    uint32_t mul, shr;
+    int d;
+};
+static inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = d;
+    f.mul = 0;
+    f.shr = 0;
+    if (d > 1) {
+        int lg = 0;
+        while ((1ll << lg) < d) ++lg;
+        const int p = 31 + lg;
+        f.mul = (uint32_t)(((1ull << p) + (uint64_t)d - 1) / (uint64_t)d);
+        f.shr = (uint32_t)(p - 32);
+    }
+    return f;
+}
+__device__ __forceinline__ int fast_div(int n, const FastDiv& f) {
+    return f.d > 1 ? (int)(__umulhi((uint32_t)n, f.mul) >> f.shr) : n;
+}
+
 struct AnchorGen {
     const float4* anchors;  // explicit [N,4] or nullptr
     const float4* base;     // [A,4]
     int num_base, stride, height, width;
+    FastDiv by_base, by_width;
 };
+static inline AnchorGen make_anchor_gen(const float* anchors, const float* base, int num_base, int stride,
+                                        int height, int width) {
+    AnchorGen g;
+    g.anchors = (const float4*)anchors;
+    g.base = (const float4*)base;
+    g.num_base = num_base;
+    g.stride = stride;
+    g.height = height;
+    g.width = width;
+    g.by_base = make_fastdiv(num_base > 0 ? num_base : 1);
+    g.by_width = make_fastdiv(width > 0 ? width : 1);
+    return g;
+}
 
 __device__ __forceinline__ float4 load_anchor(const AnchorGen& g, int i) {
     if (g.anchors) return __ldg(g.anchors + i);
-    int a = i % g.num_base;
-    int k = i / g.num_base;
-    int x = k % g.width;
-    int y = k / g.width;
+    const int k = fast_div(i, g.by_base);
+    const int a = i - k * g.num_base;
+    const int y = fast_div(k, g.by_width);
+    const int x = k - y * g.width;
     float4 b = __ldg(g.base + a);
     float sx = (float)(x * g.stride), sy = (float)(y * g.stride);
     return make_float4(b.x + sx, b.y + sy, b.z + sx, b.w + sy);

@@ -39,10 +39,9 @@ __device__ __forceinline__ float clamp_torch(float v, float hi) {
 }
 
 __global__ void __launch_bounds__(256) decode_clip_key_kernel(DecodeArgs a) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t total = (int64_t)a.batch * a.n;
-    if (t >= total) return;
-    int i = (int)(t % a.n);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // anchor; blockIdx.y = image
+    if (i >= a.n) return;
+    const int64_t t = (int64_t)blockIdx.y * a.n + i;
     float4 l = __ldg(a.loc + t);
     float4 r;
     if (a.decoded) {
@@ -905,14 +904,7 @@ static int run_topk(const uint32_t* keys, const float* boxes, int batch, int n, 
 }
 
 static AnchorGen make_gen(const frcnn_anchor_spec* s) {
-    AnchorGen g;
-    g.anchors = (const float4*)s->anchors;
-    g.base = (const float4*)s->base;
-    g.num_base = s->num_base;
-    g.stride = s->feat_stride;
-    g.height = s->height;
-    g.width = s->width;
-    return g;
+    return make_anchor_gen(s->anchors, s->base, s->num_base, s->feat_stride, s->height, s->width);
 }
 
 static int check_anchor_spec(const frcnn_anchor_spec* s, int n, const char* who) {
@@ -946,8 +938,8 @@ static int run_decode(const frcnn_proposal_params* p, const frcnn_anchor_spec* a
     a.boxes = (float4*)boxes;
     a.keys = keys;
     a.fg_out = fg_out;
-    int64_t total = (int64_t)p->batch * p->num_anchors;
-    decode_clip_key_kernel<<<cdiv(total, 256), 256, 0, stream>>>(a);
+    FRCNN_CHECK_ARG(p->batch <= 65535, "frcnn_decode_clip_score: batch %d > 65535", p->batch);
+    decode_clip_key_kernel<<<dim3(cdiv(p->num_anchors, 256), p->batch), 256, 0, stream>>>(a);
     FRCNN_LAUNCH_CHECK();
     return FRCNN_OK;
 }

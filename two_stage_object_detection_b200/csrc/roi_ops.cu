@@ -11,6 +11,8 @@
 
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace frcnn {
@@ -157,6 +159,7 @@ struct RoiArgs {
     int* argmax;
     int sampling_ratio, aligned;
     int per_image;   // > 0: RoIs are grouped, rows [b*per_image, (b+1)*per_image) belong to image b
+    int pitch;       // table kernels: row pitch of the shared-memory tables (>= W)
 };
 
 __device__ __forceinline__ int round_half_away(float v) { return (int)roundf(v); }
@@ -294,6 +297,13 @@ template <>
 struct VecT<2> {
     typedef float2 type;
 };
+template <>
+struct VecT<1> {
+    typedef float type;
+};
+__device__ __forceinline__ float vmax(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ void vsplat(float& v, float x) { v = x; }
+__device__ __forceinline__ void vgather(float& v, const float* raw, int, int p, int) { v = fmaxf(raw[p], -FLT_MAX); }
 __device__ __forceinline__ float4 vmax(const float4& a, const float4& b) {
     return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
@@ -327,6 +337,11 @@ __device__ __forceinline__ void vstore(float* o, int stride, const float2& v, un
     if (FULL || cs > 1) o[stride] = __uint_as_float(__float_as_uint(v.y) & m);
 }
 
+template <bool FULL>
+__device__ __forceinline__ void vstore(float* o, int, float v, unsigned m, int) {
+    o[0] = __uint_as_float(__float_as_uint(v) & m);
+}
+
 struct RoiBox {
     int k;
     float x1, y1, x2, y2;
@@ -348,8 +363,9 @@ __device__ __forceinline__ RoiBox load_roi(const RoiArgs& a, int r, int r_end) {
 }
 
 // One axis of the bin grid: [lo,hi) of bin `i`, as (byte offset of first corner, byte offset of second
-// corner | flags); `unit` = table elements per step along this axis (W for rows, 1 for columns), `tsel`
-// = table stride selected by a 2-long window along this axis, `esz` = bytes per table element.
+// corner | flags); `unit` = table elements per step along this axis (row pitch for rows, 1 for columns),
+// `tsel` = table stride per window level along this axis, `esz` = bytes per table element.
+template <int LV>
 __device__ __forceinline__ int2 tab_entry(int i, int P, float c1, float c2, float scale, int limit, int unit,
                                           int tsel, int esz, int* raw) {
     const int s = round_half_away(c1 * scale), e = round_half_away(c2 * scale);
@@ -359,11 +375,13 @@ __device__ __forceinline__ int2 tab_entry(int i, int P, float c1, float c2, floa
     const int len = hi - lo;
     *raw = lo | (hi << 16);
     const bool empty = len <= 0;
-    const int a = min(max(len, 1), 2);
+    // window level: the longest of 1, 2 (, 4) that fits; two such windows placed at both ends cover the run
+    const int lvl = (LV == 3 && len >= 4) ? 2 : ((LV >= 2 && len >= 2) ? 1 : 0);
+    const int a = 1 << lvl;
     const int lo_ = empty ? 0 : lo, hi_ = empty ? a : hi;
     int2 r;
-    r.x = ((a - 1) * tsel + lo_ * unit) * esz;
-    r.y = (((a - 1) * tsel + (hi_ - a) * unit) * esz) | (empty ? 0 : TAB_NE_BIT) | (len > 4 ? TAB_BIG_BIT : 0);
+    r.x = (lvl * tsel + lo_ * unit) * esz;
+    r.y = ((lvl * tsel + (hi_ - a) * unit) * esz) | (empty ? 0 : TAB_NE_BIT) | (len > (LV == 3 ? 8 : (LV == 2 ? 4 : 1)) ? TAB_BIG_BIT : 0);
     return r;
 }
 
@@ -371,41 +389,34 @@ __device__ __forceinline__ int2 tab_entry(int i, int P, float c1, float c2, floa
 // sits inside the unrolled fast loop, and a larger callee (e.g. one tiling the bin with 2 x 2 table
 // windows) raises the register pressure at every call site enough to cost the fast path 6 % (measured).
 template <typename V>
-__device__ __noinline__ V tab_big_bin(const V* tab, int hr, int wr, int W) {
+__device__ __noinline__ V tab_big_bin(const V* tab, int hr, int wr, int pitch) {
     V v;
     vsplat(v, -FLT_MAX);
     for (int y = hr & 0xFFFF; y < (hr >> 16); ++y)
-        for (int x = wr & 0xFFFF; x < (wr >> 16); ++x) v = vmax(v, tab[y * W + x]);
+        for (int x = wr & 0xFFFF; x < (wr >> 16); ++x) v = vmax(v, tab[y * pitch + x]);
     return v;
 }
 
-// argmax of one bin (training): the reference records the first element, in row-major order, that
-// attains the maximum under `v > best`; with the maximum already known that is the first table-T11
-// element equal to it (clamped NaN / -inf never match a maximum above -FLT_MAX; a maximum of exactly
-// -FLT_MAX means nothing was ever selected: -1).
-__device__ __forceinline__ void first_match(int4& idx, const float4& t, const float4& v, int p) {
-    if (idx.x < 0 && t.x == v.x) idx.x = p;
-    if (idx.y < 0 && t.y == v.y) idx.y = p;
-    if (idx.z < 0 && t.z == v.z) idx.z = p;
-    if (idx.w < 0 && t.w == v.w) idx.w = p;
+// value + argmax of one bin (training): the reference keeps the first element, in row-major order, that
+// is `> best` starting from -FLT_MAX; pixels are pre-clamped with fmaxf(., -FLT_MAX), so NaN / -inf (and a
+// genuine -FLT_MAX) are never selected and leave the index at -1.
+__device__ __forceinline__ void scan_first_max(float4& v, int4& idx, const float4& t, int p) {
+    if (t.x > v.x) v.x = t.x, idx.x = p;
+    if (t.y > v.y) v.y = t.y, idx.y = p;
+    if (t.z > v.z) v.z = t.z, idx.z = p;
+    if (t.w > v.w) v.w = t.w, idx.w = p;
 }
-__device__ __forceinline__ void first_match(int2& idx, const float2& t, const float2& v, int p) {
-    if (idx.x < 0 && t.x == v.x) idx.x = p;
-    if (idx.y < 0 && t.y == v.y) idx.y = p;
+__device__ __forceinline__ void scan_first_max(float2& v, int2& idx, const float2& t, int p) {
+    if (t.x > v.x) v.x = t.x, idx.x = p;
+    if (t.y > v.y) v.y = t.y, idx.y = p;
 }
+__device__ __forceinline__ void scan_first_max(float& v, int& idx, float t, int p) {
+    if (t > v) v = t, idx = p;
+}
+__device__ __forceinline__ void vneg(int& i) { i = -1; }
 __device__ __forceinline__ void vneg(int4& i) { i = make_int4(-1, -1, -1, -1); }
 __device__ __forceinline__ void vneg(int2& i) { i = make_int2(-1, -1); }
-// a maximum of -FLT_MAX was never "selected"; empty bins have no argmax either
-__device__ __forceinline__ void argmax_fixup(int4& i, const float4& v, bool empty) {
-    if (empty || v.x == -FLT_MAX) i.x = -1;
-    if (empty || v.y == -FLT_MAX) i.y = -1;
-    if (empty || v.z == -FLT_MAX) i.z = -1;
-    if (empty || v.w == -FLT_MAX) i.w = -1;
-}
-__device__ __forceinline__ void argmax_fixup(int2& i, const float2& v, bool empty) {
-    if (empty || v.x == -FLT_MAX) i.x = -1;
-    if (empty || v.y == -FLT_MAX) i.y = -1;
-}
+__device__ __forceinline__ void istore(int* o, int, int i, int) { o[0] = i; }
 __device__ __forceinline__ void istore(int* o, int stride, const int4& i, int cs) {
     o[0] = i.x;
     if (cs > 1) o[stride] = i.y;
@@ -426,14 +437,19 @@ template <>
 struct IdxT<2> {
     typedef int2 type;
 };
+template <>
+struct IdxT<1> {
+    typedef int type;
+};
 
-template <int P, int TAB_THREADS, int CS, int MINB, bool ARGMAX>
+template <int P, int TAB_THREADS, int CS, int MINB, bool ARGMAX, int LV>
 __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs a) {
     typedef typename VecT<CS>::type V;
     constexpr int BINS = P * P;
-    constexpr int RPI = TAB_THREADS / BINS;      // RoIs per iteration (2 or 8)
-    constexpr int NB = TAB_THREADS / P;          // RoIs per batch: two table entries per thread (28 or 56)
+    constexpr int RPI = TAB_THREADS / BINS;      // RoIs per iteration
+    constexpr int NB = TAB_THREADS / P;          // RoIs per batch: two table entries per thread
     constexpr int ITERS = NB / RPI;
+    constexpr int NT = LV * LV;                  // tables: (row level, column level), levels 1, 2 (, 4)
     static_assert(RPI * BINS == TAB_THREADS && NB * P == TAB_THREADS && ITERS * RPI == NB, "thread mapping");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -441,7 +457,8 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     __shared__ int s_hraw[2][NB][P], s_wraw[2][NB][P];
     __shared__ size_t s_ob[2][NB];                   // per RoI: byte offset of its [CS,P,P] output block
     V* tab = reinterpret_cast<V*>(smem_raw);
-    const int H = a.H, W = a.W, HW = H * W, HWp = (HW + 3) & ~3;
+    const int H = a.H, W = a.W, HW = H * W;
+    const int WP = a.pitch, HWp = (H * WP + 3) & ~3;  // row pitch (odd when rows would alias banks), table stride
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * CS;
     const int cs = min(CS, a.C - c0);
@@ -455,26 +472,65 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     const int tj = tid / (2 * P), ti = tid % (2 * P);
     RoiBox nx0 = load_roi(a, r0 + tj, r_end), nx1 = load_roi(a, r0 + tj + NB / 2, r_end);
 
-    float* raw = reinterpret_cast<float*>(tab + 3 * HWp);  // [cs][HW], lives where T22 will be
+    // staged planes [cs][HW]: where the last-built table will be (LV = 1: a region of their own)
+    float* raw = reinterpret_cast<float*>(tab + (LV == 1 ? 1 : NT - 1) * HWp);
     stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
-    for (int p = tid; p < HW; p += TAB_THREADS) {
+    // T[lr][lc][y][x] = max of the (1<<lr) x (1<<lc) window anchored at (y,x), at tab + (lr*LV + lc)*HWp.
+    // Windows that would leave the map are clamped; the lookups never use those entries.
+    // Pixels p = tid, tid + TAB_THREADS, ... with (y,x) carried along instead of divided out each time (the
+    // build is ~5 % of a CTA's instructions on the 14x14 configuration).
+    const int step_y = TAB_THREADS / W, step_x = TAB_THREADS - step_y * W;
+    const int y_first = tid / W, x_first = tid - y_first * W;
+    auto for_pixels = [&](auto&& f) {
+        int y = y_first, x = x_first;
+        for (int p = tid; p < HW; p += TAB_THREADS) {
+            f(p, y, x, y * WP + x);
+            x += step_x;
+            y += step_y;
+            if (x >= W) {
+                x -= W;
+                ++y;
+            }
+        }
+    };
+    auto level_up = [&](int dst, int src, int dy, int dx) {  // dst = max(src, src shifted by (dy,dx))
+        for_pixels([&](int, int y, int x, int q) {
+            const int qs = (y + dy < H ? q + dy * WP : q) + (x + dx < W ? dx : 0);
+            tab[dst * HWp + q] = vmax(tab[src * HWp + q], tab[src * HWp + qs]);
+        });
+    };
+    for_pixels([&](int p, int, int, int q) {
         V v;
         vgather(v, raw, HW, p, cs);
-        tab[p] = v;
-    }
+        tab[q] = v;
+    });
     __syncthreads();
-    for (int p = tid; p < HW; p += TAB_THREADS) {
-        int y = p / W, x = p - y * W;
-        int pr = x + 1 < W ? p + 1 : p, pd = y + 1 < H ? p + W : p;
-        V v = tab[p];
-        tab[HWp + p] = vmax(v, tab[pr]);      // 1 x 2
-        tab[2 * HWp + p] = vmax(v, tab[pd]);  // 2 x 1
-    }
-    __syncthreads();
-    for (int p = tid; p < HW; p += TAB_THREADS) {
-        int y = p / W;
-        int pd = y + 1 < H ? p + W : p;
-        tab[3 * HWp + p] = vmax(tab[HWp + p], tab[HWp + pd]);  // 2 x 2
+    if (LV == 1) {
+        // raw pixels only: every bin is scanned
+    } else if (LV == 2) {
+        for_pixels([&](int, int y, int x, int q) {
+            const int qr = x + 1 < W ? q + 1 : q, qd = y + 1 < H ? q + WP : q;
+            const V v = tab[q];
+            tab[HWp + q] = vmax(v, tab[qr]);      // 1 x 2
+            tab[2 * HWp + q] = vmax(v, tab[qd]);  // 2 x 1
+        });
+        __syncthreads();
+        for_pixels([&](int, int y, int, int q) {
+            const int qd = y + 1 < H ? q + WP : q;
+            tab[3 * HWp + q] = vmax(tab[HWp + q], tab[HWp + qd]);  // 2 x 2
+        });
+    } else {
+        level_up(1, 0, 0, 1);  // 1 x 2
+        level_up(3, 0, 1, 0);  // 2 x 1
+        __syncthreads();
+        level_up(2, 1, 0, 2);  // 1 x 4
+        level_up(6, 3, 2, 0);  // 4 x 1
+        level_up(4, 1, 1, 0);  // 2 x 2
+        __syncthreads();
+        level_up(5, 2, 1, 0);  // 2 x 4
+        level_up(7, 6, 0, 1);  // 4 x 2
+        __syncthreads();
+        level_up(8, 7, 0, 2);  // 4 x 4 (overwrites the staged planes, no longer needed)
     }
 
     // compute role: bin e = (ph,pw) of the (tid / BINS)-th RoI of each iteration
@@ -482,10 +538,11 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     const int ph = e / P, pw = e % P;
     auto fill_tables = [&](int buf, int j, const RoiBox& q) {
         if (ti < P)
-            s_th[buf][j][ti] = tab_entry(ti, P, q.y1, q.y2, a.scale, H, W, 2 * HWp, sizeof(V), &s_hraw[buf][j][ti]);
+            s_th[buf][j][ti] = tab_entry<LV>(ti, P, q.y1, q.y2, a.scale, H, WP, LV * HWp, sizeof(V),
+                                             &s_hraw[buf][j][ti]);
         else
-            s_tw[buf][j][ti - P] = tab_entry(ti - P, P, q.x1, q.x2, a.scale, W, 1, HWp, sizeof(V),
-                                             &s_wraw[buf][j][ti - P]);
+            s_tw[buf][j][ti - P] = tab_entry<LV>(ti - P, P, q.x1, q.x2, a.scale, W, 1, HWp, sizeof(V),
+                                                 &s_wraw[buf][j][ti - P]);
         if (ti == 0)
             s_ob[buf][j] = (((size_t)max(q.k, 0) * a.C + c0) * BINS) * sizeof(float);
     };
@@ -504,40 +561,51 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
         // one bin (this thread's ph,pw) of RoI j of the batch, all CS channels
         auto one_bin = [&](int j, bool full, bool valid) {
             const int2 h = s_th[cur][j][ph], w = s_tw[cur][j][pw];
-            const int hy = h.y & TAB_OFF_MASK, wy = w.y & TAB_OFF_MASK;
-            // lookups that coincide with the first one are skipped: warp-uniformly when no lane needs
-            // them (saves the issue slots), per lane otherwise (idle lanes cost no LSU wavefronts)
-            const bool wide = w.x != wy, tall = h.x != hy;
-            const bool any_wide = __any_sync(0xFFFFFFFFu, wide), any_tall = __any_sync(0xFFFFFFFFu, tall);
-            V v = *reinterpret_cast<const V*>(smem_raw + (w.x + h.x));
-            if (any_wide) {
-                if (wide) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (wy + h.x)));
+            if (ARGMAX) {
+                // training: one scan of the window gives the maximum and the first position that attains it
+                // (the reference's `v > best` order); clamped NaN / -inf pixels are never selected
+                V v;
+                typename IdxT<CS>::type idx;
+                vsplat(v, -FLT_MAX);
+                vneg(idx);
+                const int hr = s_hraw[cur][j][ph], wr = s_wraw[cur][j][pw];
+                const int x0 = wr & 0xFFFF, x1 = wr >> 16;
+                for (int y = hr & 0xFFFF; y < (hr >> 16); ++y)
+                    for (int x = x0; x < x1; ++x) scan_first_max(v, idx, tab[y * WP + x], y * W + x);
+                const unsigned m = (unsigned)((h.y & w.y) >> 31);  // all ones iff the bin is non-empty
+                float* o = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.out) + s_ob[cur][j]) + e;
+                if (valid) {
+                    vstore<false>(o, BINS, v, m, cs);
+                    istore(reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(a.argmax) + s_ob[cur][j]) + e, BINS,
+                           idx, cs);
+                }
+                return;
             }
-            if (any_tall) {
-                if (tall) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (w.x + hy)));
+            const int hy = h.y & TAB_OFF_MASK, wy = w.y & TAB_OFF_MASK;
+            V v = *reinterpret_cast<const V*>(smem_raw + (w.x + h.x));
+            if (LV > 1) {
+                // lookups that coincide with the first one are skipped: warp-uniformly when no lane needs
+                // them (saves the issue slots), per lane otherwise (idle lanes cost no LSU wavefronts)
+                const bool wide = w.x != wy, tall = h.x != hy;
+                const bool any_wide = __any_sync(0xFFFFFFFFu, wide), any_tall = __any_sync(0xFFFFFFFFu, tall);
                 if (any_wide) {
-                    if (wide && tall) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (wy + hy)));
+                    if (wide) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (wy + h.x)));
+                }
+                if (any_tall) {
+                    if (tall) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (w.x + hy)));
+                    if (any_wide) {
+                        if (wide && tall) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (wy + hy)));
+                    }
                 }
             }
             const bool big = ((h.y | w.y) & TAB_BIG_BIT) != 0;
             if (__any_sync(0xFFFFFFFFu, big)) {
-                if (big) v = tab_big_bin<V>(tab, s_hraw[cur][j][ph], s_wraw[cur][j][pw], W);
+                if (big) v = tab_big_bin<V>(tab, s_hraw[cur][j][ph], s_wraw[cur][j][pw], WP);
             }
             const unsigned m = (unsigned)((h.y & w.y) >> 31);  // all ones iff the bin is non-empty
             float* o = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.out) + s_ob[cur][j]) + e;
             if (full) vstore<true>(o, BINS, v, m, cs);
             else if (valid) vstore<false>(o, BINS, v, m, cs);
-            if (ARGMAX) {
-                typename IdxT<CS>::type idx;
-                vneg(idx);
-                const int hr = s_hraw[cur][j][ph], wr = s_wraw[cur][j][pw];
-                for (int y = hr & 0xFFFF; y < (hr >> 16); ++y)
-                    for (int x = wr & 0xFFFF; x < (wr >> 16); ++x) first_match(idx, tab[y * W + x], v, y * W + x);
-                argmax_fixup(idx, v, m == 0u);
-                if (valid)
-                    istore(reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(a.argmax) + s_ob[cur][j]) + e, BINS,
-                           idx, cs);
-            }
         };
         if (nb == NB && cs == CS) {
 #pragma unroll
@@ -1121,38 +1189,70 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
         }
         return launch_staged(roi_align_staged_kernel, a, smem, stream);
     }
-    // inference RoIPool: sparse max-table kernel.  4 channels per CTA (float4 tables) when that leaves two
-    // CTAs per SM, else 2 channels (float2 tables), else one CTA per SM
+    // RoIPool 7x7 / 14x14: thread-per-bin kernel over shared-memory max tables (roi_pool_tab_kernel).
+    //   LV = 2 (windows 1,2: bins up to 4 long)  inference, 14x14 and 7x7 with small RoIs
+    //   LV = 3 (windows 1,2,4: bins up to 8)     inference 7x7 with many RoIs per image
+    //   LV = 1 (pixels only, every bin scanned)  training (value + argmax in one scan), few RoIs per image
     if (PH == PW && (PH == 7 || PH == 14)) {
-        const size_t HWp = (size_t)((H * W + 3) & ~3);
-        const size_t smem4 = 4 * HWp * 16, smem2 = 4 * HWp * 8;
-        const size_t two_per_sm = 92 * 1024, one_per_sm = 200 * 1024;  // dynamic part; ~20 KB static on top
-        int tcs = 0, minb = 0;
-        if (smem4 <= two_per_sm) tcs = 4, minb = 2;
-        else if (smem2 <= two_per_sm) tcs = 2, minb = 2;
-        else if (smem4 <= one_per_sm) tcs = 4, minb = 1;
-        else if (smem2 <= one_per_sm) tcs = 2, minb = 1;
-        if (tcs) {
-            const int tab_threads = 392;  // 2*14*14 = 8*7*7; measured best (784/588 are register-starved)
+        const int per_image_rois = cdiv(K, B);
+        const size_t budget2 = 92 * 1024, budget1 = 180 * 1024;  // dynamic part for 2 / 1 CTAs per SM
+        auto table_bytes = [&](int lv, int tcs, int pitch) {
+            return (size_t)(lv == 1 ? 2 : lv * lv) * (size_t)((H * pitch + 3) & ~3) * 4 * tcs;
+        };
+        auto set_groups = [&](int tcs, int threads) {
+            const int per_batch = threads / PH;
+            const int slabs = cdiv(C, tcs);
+            const int g = cdiv(per_image_rois, 4 * per_batch);  // >= 4 batches per CTA amortise the table build
+            const int want = cdiv(8 * sm_count(), B * slabs);
             a.CS = tcs;
-            int per_batch = tab_threads / PH;
-            int slabs = cdiv(C, tcs);
-            int per_image = cdiv(K, B);
-            int g = cdiv(per_image, 4 * per_batch);  // >= 4 batches per CTA amortise the table build
-            int want = cdiv(8 * sm_count(), B * slabs);
             a.groups = std::max(1, std::min(g, want));
-            const size_t smem = tcs == 4 ? smem4 : smem2;
-#define FRCNN_TAB(PP_, CS_, MB_)                                                                              \
-    (argmax ? launch_tab(roi_pool_tab_kernel<PP_, 392, CS_, MB_, true>, a, smem, tab_threads, stream)          \
-            : launch_tab(roi_pool_tab_kernel<PP_, 392, CS_, MB_, false>, a, smem, tab_threads, stream))
-            if (PH == 7) {
-                if (tcs == 4) return minb == 2 ? FRCNN_TAB(7, 4, 2) : FRCNN_TAB(7, 4, 1);
-                return minb == 2 ? FRCNN_TAB(7, 2, 2) : FRCNN_TAB(7, 2, 1);
+        };
+#define FRCNN_TAB(PP_, TH_, CS_, MB_, AM_, LV_)                                                             \
+    do {                                                                                                    \
+        set_groups(CS_, TH_);                                                                               \
+        return launch_tab(roi_pool_tab_kernel<PP_, TH_, CS_, MB_, AM_, LV_>, a, table_bytes(LV_, CS_, a.pitch), \
+                          TH_, stream);                                                                     \
+    } while (0)
+        static const int mode7 = getenv("FRCNN_POOL7_MODE") ? atoi(getenv("FRCNN_POOL7_MODE")) : 0;
+        if (argmax) {
+            a.pitch = W | 1;
+            if (table_bytes(1, 4, a.pitch) <= budget2) {
+                if (PH == 7) FRCNN_TAB(7, 392, 4, 2, true, 1);
+                FRCNN_TAB(14, 392, 4, 2, true, 1);
             }
-            if (tcs == 4) return minb == 2 ? FRCNN_TAB(14, 4, 2) : FRCNN_TAB(14, 4, 1);
-            return minb == 2 ? FRCNN_TAB(14, 2, 2) : FRCNN_TAB(14, 2, 1);
-#undef FRCNN_TAB
+            if (table_bytes(1, 1, a.pitch) <= budget1) {
+                if (PH == 7) FRCNN_TAB(7, 392, 1, 2, true, 1);
+                FRCNN_TAB(14, 392, 1, 2, true, 1);
+            }
+        } else if (PH == 7 && (mode7 == 1 || mode7 == 3)) {
+            a.pitch = W | 1;
+            if (mode7 == 3 && table_bytes(1, 4, a.pitch) <= budget1) FRCNN_TAB(7, 392, 4, 2, false, 1);
+            if (table_bytes(3, 1, a.pitch) <= budget2 - 8 * 1024) FRCNN_TAB(7, 392, 1, 2, false, 3);
+            if (table_bytes(3, 1, a.pitch) <= budget1) FRCNN_TAB(7, 784, 1, 1, false, 3);
         }
+        if (!argmax) {
+            a.pitch = W;
+            const size_t smem4 = table_bytes(2, 4, W), smem2 = table_bytes(2, 2, W);
+            int tcs = 0, minb = 0;
+            if (smem4 <= budget2) tcs = 4, minb = 2;
+            else if (smem2 <= budget2) tcs = 2, minb = 2;
+            else if (smem4 <= 200 * 1024) tcs = 4, minb = 1;
+            else if (smem2 <= 200 * 1024) tcs = 2, minb = 1;
+            if (tcs == 4 && minb == 2) {
+                if (PH == 7) FRCNN_TAB(7, 392, 4, 2, false, 2);
+                FRCNN_TAB(14, 392, 4, 2, false, 2);
+            } else if (tcs == 2 && minb == 2) {
+                if (PH == 7) FRCNN_TAB(7, 392, 2, 2, false, 2);
+                FRCNN_TAB(14, 392, 2, 2, false, 2);
+            } else if (tcs == 4) {
+                if (PH == 7) FRCNN_TAB(7, 392, 4, 1, false, 2);
+                FRCNN_TAB(14, 392, 4, 1, false, 2);
+            } else if (tcs == 2) {
+                if (PH == 7) FRCNN_TAB(7, 392, 2, 1, false, 2);
+                FRCNN_TAB(14, 392, 2, 1, false, 2);
+            }
+        }
+#undef FRCNN_TAB
     }
     if (PH == PW && PH == 7)
         return argmax ? launch_staged(roi_pool_staged_kernel<7, true>, a, smem, stream)

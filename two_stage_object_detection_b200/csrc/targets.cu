@@ -448,12 +448,8 @@ int frcnn_anchor_targets(const frcnn_anchor_target_params* p, const frcnn_anchor
     }
     AnchorTargetArgs a;
     memset(&a, 0, sizeof(a));
-    a.gen.anchors = (const float4*)anchors->anchors;
-    a.gen.base = (const float4*)anchors->base;
-    a.gen.num_base = anchors->num_base;
-    a.gen.stride = anchors->feat_stride;
-    a.gen.height = anchors->height;
-    a.gen.width = anchors->width;
+    a.gen = make_anchor_gen(anchors->anchors, anchors->base, anchors->num_base, anchors->feat_stride,
+                            anchors->height, anchors->width);
     a.bbox = (const float4*)bbox;
     a.n_gt = n_gt;
     a.batch = p->batch;

@@ -97,13 +97,17 @@ def bbox2loc(src_bbox: torch.Tensor, dst_bbox: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def bbox_iou(bbox_a: torch.Tensor, bbox_b: torch.Tensor) -> torch.Tensor:
+def bbox_iou(bbox_a: torch.Tensor, bbox_b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     if bbox_a.shape[1] != 4 or bbox_b.shape[1] != 4:
         raise IndexError  # utils/loc_bbox_iou.py:14-16
     lib = _lib.load()
     dev = _lib.require_cuda(bbox_a, bbox_b)
     a, b = f32c(bbox_a), f32c(bbox_b)
-    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=dev)
+    elif (out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev
+          or tuple(out.shape) != (a.shape[0], b.shape[0])):
+        raise ValueError("bbox_iou: out must be a contiguous float32 [Na,Nb] tensor on the inputs' device")
     with torch.cuda.device(dev):
         check(lib.frcnn_bbox_iou(a.data_ptr(), b.data_ptr(), a.shape[0], b.shape[0], out.data_ptr(),
                                  _lib.stream_ptr(dev)), "frcnn_bbox_iou")
