@@ -187,6 +187,15 @@ int frcnn_roi_pool_forward(const float* feat, int32_t batch, int32_t channels, i
                            int32_t width, const float* rois5, int32_t num_rois, int32_t rois_per_image,
                            int32_t pooled_h, int32_t pooled_w, float spatial_scale, float* out, int32_t* argmax,
                            void* workspace, size_t workspace_bytes, frcnn_stream_t stream);
+/* RoIPool followed by the HarDNet head's classifier, which is only a global average over the bins
+ * (models/hardnet.py:203-212 AdaptiveAvgPool2d(1)+Flatten, called at nets/classify.py:43-46):
+ * out [K,C] = mean over the PH*PW bins of roi_pool(feat, rois5), without materialising [K,C,PH,PW].
+ * Fixed summation order (run-to-run identical); agrees with pool().mean() to fp32 rounding.  7x7 and 14x14
+ * bins on maps whose max tables fit in shared memory, else FRCNN_ERR_UNSUPPORTED (use the two steps).  */
+int frcnn_roi_pool_mean_forward(const float* feat, int32_t batch, int32_t channels, int32_t height,
+                                int32_t width, const float* rois5, int32_t num_rois, int32_t rois_per_image,
+                                int32_t pooled_h, int32_t pooled_w, float spatial_scale, float* out,
+                                void* workspace, size_t workspace_bytes, frcnn_stream_t stream);
 /* grad_in [B,C,H,W] must be zero-initialised by the caller.                                     */
 int frcnn_roi_pool_backward(const float* grad_out, const int32_t* argmax, const float* rois5,
                             int32_t num_rois, int32_t channels, int32_t height, int32_t width,

@@ -380,6 +380,53 @@ def test_roi_ops_vs_oracle(F, O, shape):
         assert np.array_equal(N(F.roi_align(T(feat), T(rois), P, 1.0, sr, al)), O.roi_align(feat, rois, P, 1.0, sr, al))
 
 
+@pytest.mark.parametrize("shape", [(3, 40, 38, 38, 14), (2, 24, 50, 50, 7), (2, 13, 37, 41, 7), (1, 6, 64, 64, 14),
+                                   (1, 5, 120, 90, 7)])
+def test_roi_pool_mean_fused_vs_oracle(F, O, shape):
+    """Fused RoIPool + global average against mean(oracle RoIPool) in float64: 1e-5 of the
+    largest pooled magnitude (summation order differs from AdaptiveAvgPool2d; every bin value is exact).
+    Covers float4 / float2 tables, channel tails, empty bins, bins longer than 4, ungrouped RoIs."""
+    B, Cc, H, W, P = shape
+    rng = np.random.default_rng(5 + H + P)
+    feat = rng.standard_normal((B, Cc, H, W)).astype(np.float32)
+    K = 120
+    c = rng.uniform(-4, W + 4, (K, 2))
+    wh = np.concatenate([rng.uniform(0.5, 12, (K // 2, 2)), rng.uniform(W * 0.3, W * 1.2, (K - K // 2, 2))])
+    rois = np.concatenate([rng.integers(0, B, (K, 1)), c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    ref = O.roi_pool(feat, rois, P, 1.0).astype(np.float64).mean((2, 3))
+    got = N(F.roi_pool_mean(T(feat), T(rois), P, 1.0))
+    assert got.shape == (K, Cc)
+    tol = 1e-5 * np.abs(O.roi_pool(feat, rois, P, 1.0)).max()
+    assert np.abs(got - ref).max() <= tol
+    # run-to-run identical, and identical when the caller promises grouped RoIs
+    order = np.argsort(rois[:, 0], kind="stable")
+    per = np.bincount(rois[:, 0].astype(int), minlength=B)
+    if (per == per[0]).all():
+        g2 = N(F.roi_pool_mean(T(feat), T(rois[order]), P, 1.0, rois_per_image=int(per[0])))
+        assert np.array_equal(g2, got[order])
+    assert np.array_equal(N(F.roi_pool_mean(T(feat), T(rois), P, 1.0)), got)
+
+
+def test_roi_head_fused_mean_equals_two_step(F):
+    from two_stage_object_detection_b200.nets import HarNetRoIHead
+    from two_stage_object_detection_b200.nets.frcnn import GlobalAvgClassifier
+    torch.manual_seed(3)
+    head = HarNetRoIHead(n_class=5, roi_size=14, spatial_scale=1, classifier=GlobalAvgClassifier(),
+                         in_features=24).to(DEV).eval()
+    x = torch.relu(torch.randn(2, 24, 38, 38, device=DEV))
+    c = torch.rand(2, 50, 2, device=DEV) * 600
+    wh = torch.rand(2, 50, 2, device=DEV) * 200 + 16
+    rois = torch.cat([c - wh / 2, c + wh / 2], -1).clamp(0, 600)
+    with torch.no_grad():
+        assert head._fused_mean_ok(x)
+        a_loc, a_sc = head(x, rois, None, (600, 600))
+        head.fuse_mean = False
+        b_loc, b_sc = head(x, rois, None, (600, 600))
+    assert torch.allclose(a_loc, b_loc, rtol=1e-5, atol=1e-6) and torch.allclose(a_sc, b_sc, rtol=1e-5, atol=1e-6)
+    head.fuse_mean = True
+    assert not head._fused_mean_ok(x.requires_grad_(True))  # training keeps the pooled tensor (argmax backward)
+
+
 def test_roi_grouped_path_equals_bucketed(F):
     """rois_per_image promise (no bucketing pass) gives the same bits as the general path."""
     rng = np.random.default_rng(77)

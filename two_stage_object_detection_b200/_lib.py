@@ -14,6 +14,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FRCNN_B200_LIB") or os.path.join(_PKG, "libfrcnn_b200.so")
 ABI_VERSION = 1
+ERR_UNSUPPORTED = -4  # FRCNN_ERR_UNSUPPORTED
 MAX_BASE_ANCHORS = 64
 
 IMG_OK = 0
@@ -80,6 +81,7 @@ SIGNATURES = {
     "frcnn_roi_head_coords": (_I, [_P, _P, _I, _I, _F, _F, _I, _I, _P, _P]),
     "frcnn_roi_workspace_bytes": (_Z, [_I, _I]),
     "frcnn_roi_pool_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
+    "frcnn_roi_pool_mean_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _F, _P, _P, _Z, _P]),
     "frcnn_roi_pool_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "frcnn_roi_align_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _F, _I, _I, _P, _P, _Z, _P]),
     "frcnn_roi_align_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P]),

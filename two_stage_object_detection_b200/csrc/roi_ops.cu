@@ -442,48 +442,22 @@ struct IdxT<1> {
     typedef int type;
 };
 
-template <int P, int TAB_THREADS, int CS, int MINB, bool ARGMAX, int LV>
-__global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs a) {
-    typedef typename VecT<CS>::type V;
-    constexpr int BINS = P * P;
-    constexpr int RPI = TAB_THREADS / BINS;      // RoIs per iteration
-    constexpr int NB = TAB_THREADS / P;          // RoIs per batch: two table entries per thread
-    constexpr int ITERS = NB / RPI;
-    constexpr int NT = LV * LV;                  // tables: (row level, column level), levels 1, 2 (, 4)
-    static_assert(RPI * BINS == TAB_THREADS && NB * P == TAB_THREADS && ITERS * RPI == NB, "thread mapping");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ int2 s_th[2][NB][P], s_tw[2][NB][P];  // per RoI: row / column corner offsets + flags
-    __shared__ int s_hraw[2][NB][P], s_wraw[2][NB][P];
-    __shared__ size_t s_ob[2][NB];                   // per RoI: byte offset of its [CS,P,P] output block
-    V* tab = reinterpret_cast<V*>(smem_raw);
-    const int H = a.H, W = a.W, HW = H * W;
-    const int WP = a.pitch, HWp = (H * WP + 3) & ~3;  // row pitch (odd when rows would alias banks), table stride
-    const int b = blockIdx.z;
-    const int c0 = blockIdx.y * CS;
-    const int cs = min(CS, a.C - c0);
-    int r_begin, r_end;
-    roi_range(a, b, r_begin, r_end);
-    const int stride = a.groups * NB;
-    int r0 = r_begin + blockIdx.x * NB;  // first RoI of this CTA's current batch
-    if (r0 >= r_end) return;
-    const int tid = threadIdx.x;
-    // table-entry role: axis entry ti (rows first, then columns) of RoIs tj and tj + NB/2 of the batch
-    const int tj = tid / (2 * P), ti = tid % (2 * P);
-    RoiBox nx0 = load_roi(a, r0 + tj, r_end), nx1 = load_roi(a, r0 + tj + NB / 2, r_end);
-
-    // staged planes [cs][HW]: where the last-built table will be (LV = 1: a region of their own)
-    float* raw = reinterpret_cast<float*>(tab + (LV == 1 ? 1 : NT - 1) * HWp);
-    stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
+// Builds the max tables of one channel slab from the staged planes `raw` [cs][H*W]:
+// T[lr][lc][y][x] = max of the (1<<lr) x (1<<lc) window anchored at (y,x), at tab + (lr*LV + lc)*HWp, row
+// pitch WP.  Pixels are first clamped with fmaxf(., -FLT_MAX).  Ends without a barrier.
+template <typename V, int LV, int THREADS>
+__device__ __forceinline__ void build_max_tables(V* tab, const float* raw, int cs, int H, int W, int WP, int HWp,
+                                                 int tid) {
+    const int HW = H * W;
     // T[lr][lc][y][x] = max of the (1<<lr) x (1<<lc) window anchored at (y,x), at tab + (lr*LV + lc)*HWp.
     // Windows that would leave the map are clamped; the lookups never use those entries.
-    // Pixels p = tid, tid + TAB_THREADS, ... with (y,x) carried along instead of divided out each time (the
+    // Pixels p = tid, tid + THREADS, ... with (y,x) carried along instead of divided out each time (the
     // build is ~5 % of a CTA's instructions on the 14x14 configuration).
-    const int step_y = TAB_THREADS / W, step_x = TAB_THREADS - step_y * W;
+    const int step_y = THREADS / W, step_x = THREADS - step_y * W;
     const int y_first = tid / W, x_first = tid - y_first * W;
     auto for_pixels = [&](auto&& f) {
         int y = y_first, x = x_first;
-        for (int p = tid; p < HW; p += TAB_THREADS) {
+        for (int p = tid; p < HW; p += THREADS) {
             f(p, y, x, y * WP + x);
             x += step_x;
             y += step_y;
@@ -532,6 +506,43 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
         __syncthreads();
         level_up(8, 7, 0, 2);  // 4 x 4 (overwrites the staged planes, no longer needed)
     }
+
+}
+
+template <int P, int TAB_THREADS, int CS, int MINB, bool ARGMAX, int LV>
+__global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs a) {
+    typedef typename VecT<CS>::type V;
+    constexpr int BINS = P * P;
+    constexpr int RPI = TAB_THREADS / BINS;      // RoIs per iteration
+    constexpr int NB = TAB_THREADS / P;          // RoIs per batch: two table entries per thread
+    constexpr int ITERS = NB / RPI;
+    constexpr int NT = LV * LV;                  // tables: (row level, column level), levels 1, 2 (, 4)
+    static_assert(RPI * BINS == TAB_THREADS && NB * P == TAB_THREADS && ITERS * RPI == NB, "thread mapping");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int2 s_th[2][NB][P], s_tw[2][NB][P];  // per RoI: row / column corner offsets + flags
+    __shared__ int s_hraw[2][NB][P], s_wraw[2][NB][P];
+    __shared__ size_t s_ob[2][NB];                   // per RoI: byte offset of its [CS,P,P] output block
+    V* tab = reinterpret_cast<V*>(smem_raw);
+    const int H = a.H, W = a.W, HW = H * W;
+    const int WP = a.pitch, HWp = (H * WP + 3) & ~3;  // row pitch (odd when rows would alias banks), table stride
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * CS;
+    const int cs = min(CS, a.C - c0);
+    int r_begin, r_end;
+    roi_range(a, b, r_begin, r_end);
+    const int stride = a.groups * NB;
+    int r0 = r_begin + blockIdx.x * NB;  // first RoI of this CTA's current batch
+    if (r0 >= r_end) return;
+    const int tid = threadIdx.x;
+    // table-entry role: axis entry ti (rows first, then columns) of RoIs tj and tj + NB/2 of the batch
+    const int tj = tid / (2 * P), ti = tid % (2 * P);
+    RoiBox nx0 = load_roi(a, r0 + tj, r_end), nx1 = load_roi(a, r0 + tj + NB / 2, r_end);
+
+    // staged planes [cs][HW]: where the last-built table will be (LV = 1: a region of their own)
+    float* raw = reinterpret_cast<float*>(tab + (LV == 1 ? 1 : NT - 1) * HWp);
+    stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
+    build_max_tables<V, LV, TAB_THREADS>(tab, raw, cs, H, W, WP, HWp, tid);
 
     // compute role: bin e = (ph,pw) of the (tid / BINS)-th RoI of each iteration
     const int e = tid % BINS, ej = tid / BINS;
@@ -616,6 +627,121 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
                 one_bin(j < nb ? j : 0, false, j < nb);
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RoIPool + global average pool in one kernel.  The HarDNet head's classifier is only
+// AdaptiveAvgPool2d(1) + Flatten (models/hardnet.py:203-212), so HarNetRoIHead.forward reads nothing of the
+// [K,C,P,P] tensor but its mean over the bins: this kernel writes [K,C] and the P*P*4 bytes per (RoI,
+// channel) never exist (3.85 GB on the 14x14 configuration, plus the pass that would re-read them).
+//
+// Same tables as roi_pool_tab_kernel; the mapping is chosen for the reduction instead of for the stores:
+// a group of LPR = 8 / 16 lanes owns one RoI, lane l owns column pw = l of its bin grid and walks the P rows,
+// accumulating in registers; the row geometry lives in the lanes too (lane l computes row l's entry, the
+// others fetch it by shuffle), so the main loop has no shared-memory geometry tables and no barrier.  The
+// P column sums are combined by an xor tree.  Summation order: rows top to bottom inside a column, then the
+// tree over columns -- fixed, so results are run-to-run identical; they agree with pool().mean() to fp32
+// rounding (1e-6 relative to the largest bin value), not bit for bit.
+// ---------------------------------------------------------------------------------------------
+constexpr int PM_THREADS = 512;
+
+__device__ __forceinline__ void vacc(float4& s, const float4& v, unsigned m) {
+    s.x += __uint_as_float(__float_as_uint(v.x) & m);
+    s.y += __uint_as_float(__float_as_uint(v.y) & m);
+    s.z += __uint_as_float(__float_as_uint(v.z) & m);
+    s.w += __uint_as_float(__float_as_uint(v.w) & m);
+}
+__device__ __forceinline__ void vacc(float2& s, const float2& v, unsigned m) {
+    s.x += __uint_as_float(__float_as_uint(v.x) & m);
+    s.y += __uint_as_float(__float_as_uint(v.y) & m);
+}
+__device__ __forceinline__ void vxor_add(float4& s, int d) {
+    s.x += __shfl_xor_sync(0xFFFFFFFFu, s.x, d);
+    s.y += __shfl_xor_sync(0xFFFFFFFFu, s.y, d);
+    s.z += __shfl_xor_sync(0xFFFFFFFFu, s.z, d);
+    s.w += __shfl_xor_sync(0xFFFFFFFFu, s.w, d);
+}
+__device__ __forceinline__ void vxor_add(float2& s, int d) {
+    s.x += __shfl_xor_sync(0xFFFFFFFFu, s.x, d);
+    s.y += __shfl_xor_sync(0xFFFFFFFFu, s.y, d);
+}
+__device__ __forceinline__ void vmean_store(float* o, const float4& s, float n, int cs) {
+    o[0] = s.x / n;
+    if (cs > 1) o[1] = s.y / n;
+    if (cs > 2) o[2] = s.z / n;
+    if (cs > 3) o[3] = s.w / n;
+}
+__device__ __forceinline__ void vmean_store(float* o, const float2& s, float n, int cs) {
+    o[0] = s.x / n;
+    if (cs > 1) o[1] = s.y / n;
+}
+
+template <int P, int CS, int LV>
+__global__ void __launch_bounds__(PM_THREADS, 2) roi_pool_mean_kernel(RoiArgs a) {
+    typedef typename VecT<CS>::type V;
+    constexpr int LPR = P <= 8 ? 8 : 16;  // lanes per RoI
+    constexpr int RPW = 32 / LPR;         // RoIs per warp
+    constexpr int NW = PM_THREADS / 32;
+    constexpr int NT = LV * LV;
+    static_assert(P <= 16, "one lane per bin column");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    V* tab = reinterpret_cast<V*>(smem_raw);
+    const int H = a.H, W = a.W, HW = H * W;
+    const int WP = a.pitch, HWp = (H * WP + 3) & ~3;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * CS;
+    const int cs = min(CS, a.C - c0);
+    int r_begin, r_end;
+    roi_range(a, b, r_begin, r_end);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (r_begin + blockIdx.x * NW * RPW >= r_end) return;
+    float* raw = reinterpret_cast<float*>(tab + (NT - 1) * HWp);
+    stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
+    build_max_tables<V, LV, PM_THREADS>(tab, raw, cs, H, W, WP, HWp, tid);
+    __syncthreads();
+
+    const int sub = lane / LPR, l = lane % LPR, le = min(l, P - 1);
+    const int stride = a.groups * NW * RPW;
+    for (int rw = r_begin + (blockIdx.x * NW + warp) * RPW; rw < r_end; rw += stride) {  // warp-uniform
+        const RoiBox q = load_roi(a, rw + sub, r_end);
+        int hraw, wraw;
+        const int2 row = tab_entry<LV>(le, P, q.y1, q.y2, a.scale, H, WP, LV * HWp, sizeof(V), &hraw);
+        const int2 w = tab_entry<LV>(le, P, q.x1, q.x2, a.scale, W, 1, HWp, sizeof(V), &wraw);
+        const int wy = w.y & TAB_OFF_MASK;
+        const bool wide = w.x != wy;
+        const bool any_wide = __any_sync(0xFFFFFFFFu, wide);
+        V acc;
+        vsplat(acc, 0.f);
+#pragma unroll
+        for (int ph = 0; ph < P; ++ph) {
+            const int src = sub * LPR + ph;
+            const int hx = __shfl_sync(0xFFFFFFFFu, row.x, src), hyf = __shfl_sync(0xFFFFFFFFu, row.y, src);
+            const int hy = hyf & TAB_OFF_MASK;
+            const bool tall = hx != hy;
+            const bool any_tall = __any_sync(0xFFFFFFFFu, tall);
+            V v = *reinterpret_cast<const V*>(smem_raw + (w.x + hx));
+            if (any_wide) {
+                if (wide) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (wy + hx)));
+            }
+            if (any_tall) {
+                if (tall) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (w.x + hy)));
+                if (any_wide) {
+                    if (wide && tall) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (wy + hy)));
+                }
+            }
+            const bool big = ((hyf | w.y) & TAB_BIG_BIT) != 0;
+            if (__any_sync(0xFFFFFFFFu, big)) {
+                const int hr = __shfl_sync(0xFFFFFFFFu, hraw, src);
+                if (big) v = tab_big_bin<V>(tab, hr, wraw, WP);
+            }
+            vacc(acc, v, (unsigned)((hyf & w.y) >> 31));  // empty bins pool to 0
+        }
+        if (l >= P) vsplat(acc, 0.f);  // spare lanes of the group shadowed column P-1
+#pragma unroll
+        for (int d = LPR / 2; d > 0; d >>= 1) vxor_add(acc, d);
+        if (l == 0 && q.k >= 0) vmean_store(a.out + (size_t)q.k * a.C + c0, acc, (float)(P * P), cs);
     }
 }
 
@@ -1120,7 +1246,7 @@ size_t frcnn_roi_workspace_bytes(int32_t batch, int32_t num_rois) {
 static int roi_forward_common(bool align, const float* feat, int B, int C, int H, int W, const float* rois5,
                               int K, int per_image, int PH, int PW, float scale, int sampling_ratio, int aligned, float* out,
                               int32_t* argmax, void* workspace, size_t workspace_bytes, cudaStream_t stream,
-                              const char* who) {
+                              const char* who, bool mean = false) {
     int rc = check_roi_common(feat, B, C, H, W, rois5, K, PH, PW, out, who);
     if (rc) return rc;
     if (K == 0) return FRCNN_OK;
@@ -1142,6 +1268,10 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
     a.aligned = aligned;
     int cs = pick_slab(C, H * W);
     bool staged = cs > 0 && PH <= ROI_MAX_P && PW <= ROI_MAX_P && B <= 4096;
+    if (mean && !(staged && !align && PH == PW && (PH == 7 || PH == 14))) {
+        set_error("%s: fused pool + mean supports 7x7 / 14x14 RoIPool on maps that fit in shared memory", who);
+        return FRCNN_ERR_UNSUPPORTED;
+    }
     if (!staged) {
         size_t total = (size_t)K * C * PH * PW;
         int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 32);
@@ -1214,6 +1344,27 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
                           TH_, stream);                                                                     \
     } while (0)
         static const int mode7 = getenv("FRCNN_POOL7_MODE") ? atoi(getenv("FRCNN_POOL7_MODE")) : 0;
+        if (mean) {  // [K,C] = mean over the bins of RoIPool, never materialising [K,C,P,P]
+            a.pitch = W;
+            int tcs = 0;
+            if (table_bytes(2, 4, W) <= 200 * 1024) tcs = 4;
+            else if (table_bytes(2, 2, W) <= 200 * 1024) tcs = 2;
+            if (!tcs) {
+                set_error("%s: feature map too large for the fused pool + mean kernel", who);
+                return FRCNN_ERR_UNSUPPORTED;
+            }
+            const int per_iter = (PM_THREADS / 32) * (PH <= 8 ? 4 : 2);  // RoIs per CTA pass
+            const int slabs = cdiv(C, tcs);
+            a.CS = tcs;
+            a.groups = std::max(1, std::min(cdiv(per_image_rois, 4 * per_iter), cdiv(8 * sm_count(), B * slabs)));
+            const size_t smem = table_bytes(2, tcs, W);
+            if (PH == 7) {
+                if (tcs == 4) return launch_tab(roi_pool_mean_kernel<7, 4, 2>, a, smem, PM_THREADS, stream);
+                return launch_tab(roi_pool_mean_kernel<7, 2, 2>, a, smem, PM_THREADS, stream);
+            }
+            if (tcs == 4) return launch_tab(roi_pool_mean_kernel<14, 4, 2>, a, smem, PM_THREADS, stream);
+            return launch_tab(roi_pool_mean_kernel<14, 2, 2>, a, smem, PM_THREADS, stream);
+        }
         if (argmax) {
             a.pitch = W | 1;
             if (table_bytes(1, 4, a.pitch) <= budget2) {
@@ -1269,6 +1420,13 @@ int frcnn_roi_pool_forward(const float* feat, int32_t B, int32_t C, int32_t H, i
                            int32_t* argmax, void* workspace, size_t workspace_bytes, frcnn_stream_t stream) {
     return roi_forward_common(false, feat, B, C, H, W, rois5, K, per_image, PH, PW, scale, 0, 0, out, argmax, workspace,
                               workspace_bytes, (cudaStream_t)stream, "frcnn_roi_pool_forward");
+}
+
+int frcnn_roi_pool_mean_forward(const float* feat, int32_t B, int32_t C, int32_t H, int32_t W, const float* rois5,
+                                int32_t K, int32_t per_image, int32_t PH, int32_t PW, float scale, float* out,
+                                void* workspace, size_t workspace_bytes, frcnn_stream_t stream) {
+    return roi_forward_common(false, feat, B, C, H, W, rois5, K, per_image, PH, PW, scale, 0, 0, out, nullptr, workspace,
+                              workspace_bytes, (cudaStream_t)stream, "frcnn_roi_pool_mean_forward", true);
 }
 
 int frcnn_roi_align_forward(const float* feat, int32_t B, int32_t C, int32_t H, int32_t W, const float* rois5,

@@ -371,6 +371,29 @@ def roi_pool_forward(feat, rois5, output_size, spatial_scale=1.0, with_argmax=Fa
     return (out, am) if with_argmax else out
 
 
+def roi_pool_mean(feat, rois5, output_size, spatial_scale=1.0, rois_per_image=0):
+    """mean over the bins of roi_pool(feat, rois5) -> [K,C], in one kernel (the HarDNet head's
+    RoIPool + AdaptiveAvgPool2d(1) + Flatten, nets/classify.py:43-46 with models/hardnet.py:203-212).
+    Inference only (no autograd).  Shapes the fused kernel does not cover take the two steps."""
+    lib = _lib.load()
+    dev = _lib.require_cuda(feat, rois5)
+    f, r = f32c(feat), f32c(rois5).view(-1, 5)
+    B, Cc, H, W = f.shape
+    K = r.shape[0]
+    ph, pw = _pair(output_size)
+    out = torch.empty((K, Cc), dtype=torch.float32, device=dev)
+    nbytes = lib.frcnn_roi_workspace_bytes(B, K)
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(dev, nbytes)
+        rc = lib.frcnn_roi_pool_mean_forward(f.data_ptr(), B, Cc, H, W, r.data_ptr(), K, int(rois_per_image), ph, pw,
+                                             float(spatial_scale), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             _lib.stream_ptr(dev))
+    if rc == _lib.ERR_UNSUPPORTED:
+        return roi_pool_forward(f, r, output_size, spatial_scale, rois_per_image=rois_per_image).mean((2, 3))
+    check(rc, "frcnn_roi_pool_mean_forward")
+    return out
+
+
 def roi_align_forward(feat, rois5, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=False, out=None,
                       rois_per_image=0):
     lib = _lib.load()

@@ -9,6 +9,10 @@ from torch import nn
 from .. import functional as F
 
 
+def _pair2(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
 class RoIPool(nn.Module):
     """torchvision.ops.RoIPool stand-in (nets/classify.py:4,17): (input [B,C,H,W], rois [K,5])."""
 
@@ -57,6 +61,7 @@ class HarNetRoIHead(nn.Module):
             self.roi = RoIAlign((roi_size, roi_size), spatial_scale, sampling_ratio, aligned)
         else:
             raise ValueError("roi_op must be 'pool' or 'align'")
+        self.fuse_mean = True  # set False to always materialise the pooled tensor
 
     def gather(self, x, rois, roi_indices, img_size):
         """The hot part: coordinate map + index concat + RoI gather -> [n*R, C, P, P]."""
@@ -68,10 +73,28 @@ class HarNetRoIHead(nn.Module):
         indices_and_rois = F.roi_head_coords(rois, roi_indices, img_size, (x.size()[2], x.size()[3]))
         return self.roi(x, indices_and_rois, grouped)
 
+    def _fused_mean_ok(self, x):
+        """RoIPool -> classifier collapses to one kernel when the classifier is exactly the reference's
+        HarNetClassifier (AdaptiveAvgPool2d(1) + Flatten, models/hardnet.py:203-212) and nothing needs the
+        pooled tensor for a backward pass."""
+        seq = getattr(self.classifier, "clssifier", None)
+        return (self.fuse_mean and isinstance(self.roi, RoIPool) and isinstance(seq, nn.Sequential) and len(seq) == 2
+                and isinstance(seq[0], nn.AdaptiveAvgPool2d) and tuple(_pair2(seq[0].output_size)) == (1, 1)
+                and isinstance(seq[1], nn.Flatten) and not (torch.is_grad_enabled() and x.requires_grad))
+
     def forward(self, x, rois, roi_indices, img_size):
         n = x.shape[0]
-        pool = self.gather(x, rois, roi_indices, img_size)
-        fc7 = self.classifier(pool)
+        if self._fused_mean_ok(x):
+            rois_ = rois.view(n, -1, 4)
+            grouped = 0
+            if roi_indices is None:
+                roi_indices = torch.arange(n, dtype=torch.int32, device=x.device)
+                grouped = rois_.shape[1]
+            r5 = F.roi_head_coords(rois_, roi_indices, img_size, (x.size()[2], x.size()[3]))
+            fc7 = F.roi_pool_mean(x, r5, self.roi.output_size, self.roi.spatial_scale, grouped)
+        else:
+            pool = self.gather(x, rois, roi_indices, img_size)
+            fc7 = self.classifier(pool)
         roi_cls_locs = self.cls_loc(fc7)
         roi_scores = self.score(fc7)
         roi_cls_locs = roi_cls_locs.view(n, -1, roi_cls_locs.size(1))
