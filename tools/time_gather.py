@@ -30,3 +30,7 @@ for grouped in (0, cfg["n_post"]):
     print(f"{name} {cfg['op']} P={P} grouped={grouped}: {t:.3f} ms  {alg / t / 1e6:.0f} GB/s  ({alg / t / 1e6 / 6552.6:.3f} of peak)")
 t = timeit(lambda: F.proposals(loc, logits, clip_x_max=S, clip_y_max=S, n_pre_nms=cfg["n_pre"], n_post_nms=cfg["n_post"], base=base, feat_stride=16, feat_hw=(H, W), score_is_logits=True))
 print(f"{name} proposals: {t*1e3:.1f} us")
+if cfg["op"] == "pool":
+    t = timeit(lambda: F.roi_pool_mean(feat, rois5, P, 1.0, rois_per_image=cfg["n_post"]))
+    t2 = timeit(lambda: F.roi_pool_forward(feat, rois5, P, 1.0, out=pooled, rois_per_image=cfg["n_post"]).mean((2, 3)))
+    print(f"{name} fused pool+mean -> [K,C]: {t:.3f} ms   (pool then .mean((2,3)): {t2:.3f} ms)")

@@ -282,8 +282,9 @@ __global__ void __launch_bounds__(ROI_THREADS, 2) roi_pool_staged_kernel(RoiArgs
 // shared-memory tables (one entry per thread), and the next batch's RoI boxes are prefetched.
 // ---------------------------------------------------------------------------------------------
 constexpr int TAB_NE_BIT = 0x80000000;   // entry .y bit 31: bin row / column is non-empty
-constexpr int TAB_BIG_BIT = 0x40000000;  // entry .y bit 30: longer than 4 -> loop path
-constexpr int TAB_OFF_MASK = 0x3FFFFFFF;
+constexpr int TAB_BIG_BIT = 0x40000000;  // entry .y bit 30: longer than the tables cover -> loop path
+constexpr int TAB_MID_BIT = 0x20000000;  // entry .y bit 29 (tables 1,2 only): 5..8 long -> four 2-windows
+constexpr int TAB_OFF_MASK = 0x1FFFFFFF;
 
 // CS channel-interleaved floats per pixel: float4 (LDS.128) for CS = 4, float2 (LDS.64) for CS = 2.
 // Native vector types on purpose: a struct-of-array wrapper made ptxas split the predicated loads.
@@ -365,7 +366,7 @@ __device__ __forceinline__ RoiBox load_roi(const RoiArgs& a, int r, int r_end) {
 // One axis of the bin grid: [lo,hi) of bin `i`, as (byte offset of first corner, byte offset of second
 // corner | flags); `unit` = table elements per step along this axis (row pitch for rows, 1 for columns),
 // `tsel` = table stride per window level along this axis, `esz` = bytes per table element.
-template <int LV>
+template <int LV, bool MID = false>
 __device__ __forceinline__ int2 tab_entry(int i, int P, float c1, float c2, float scale, int limit, int unit,
                                           int tsel, int esz, int* raw) {
     const int s = round_half_away(c1 * scale), e = round_half_away(c2 * scale);
@@ -381,8 +382,27 @@ __device__ __forceinline__ int2 tab_entry(int i, int P, float c1, float c2, floa
     const int lo_ = empty ? 0 : lo, hi_ = empty ? a : hi;
     int2 r;
     r.x = (lvl * tsel + lo_ * unit) * esz;
-    r.y = ((lvl * tsel + (hi_ - a) * unit) * esz) | (empty ? 0 : TAB_NE_BIT) | (len > (LV == 3 ? 8 : (LV == 2 ? 4 : 1)) ? TAB_BIG_BIT : 0);
+    r.y = ((lvl * tsel + (hi_ - a) * unit) * esz) | (empty ? 0 : TAB_NE_BIT) |
+          (len > (LV == 1 ? 1 : ((LV == 3 || MID) ? 8 : 4)) ? TAB_BIG_BIT : 0) |
+          ((MID && len > 4 && len <= 8) ? TAB_MID_BIT : 0);
     return r;
+}
+
+// A run of 5..8 pixels is covered by the 2-long windows at lo, lo+2, hi-4, hi-2 (the first and the last are
+// the regular two lookups).  `h0,h1` / `w0,w1` are the regular corner offsets, `hm` / `wm` say which axis is
+// 5..8 long, `rstep` / `cstep` = byte distance of two pixels along the axis.  Twelve extra lookups at most;
+// on an axis that is not long the extra positions repeat the regular ones (max is idempotent).
+template <typename V>
+__device__ __noinline__ V tab_mid_bin(V v, const unsigned char* smem, int h0, int h1, bool hm, int w0, int w1,
+                                         bool wm, int rstep, int cstep) {
+    const int hp[4] = {h0, h1, hm ? h0 + rstep : h0, hm ? h1 - rstep : h1};
+    const int wp[4] = {w0, w1, wm ? w0 + cstep : w0, wm ? w1 - cstep : w1};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i >= 2 || j >= 2) v = vmax(v, *reinterpret_cast<const V*>(smem + (hp[i] + wp[j])));
+    return v;
 }
 
 // Loop path for one bin longer than 4 in some direction.  Deliberately tiny and out of line: the call
@@ -517,6 +537,9 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     constexpr int NB = TAB_THREADS / P;          // RoIs per batch: two table entries per thread
     constexpr int ITERS = NB / RPI;
     constexpr int NT = LV * LV;                  // tables: (row level, column level), levels 1, 2 (, 4)
+    // 5..8-long bins through four 2-windows: 7x7 bins only (a 14x14 grid needs a RoI > 56 pixels wide for
+    // one, and the extra call site costs the 14x14 fast path registers)
+    constexpr bool MID = LV == 2 && P == 7;
     static_assert(RPI * BINS == TAB_THREADS && NB * P == TAB_THREADS && ITERS * RPI == NB, "thread mapping");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -549,11 +572,11 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     const int ph = e / P, pw = e % P;
     auto fill_tables = [&](int buf, int j, const RoiBox& q) {
         if (ti < P)
-            s_th[buf][j][ti] = tab_entry<LV>(ti, P, q.y1, q.y2, a.scale, H, WP, LV * HWp, sizeof(V),
-                                             &s_hraw[buf][j][ti]);
+            s_th[buf][j][ti] = tab_entry<LV, MID>(ti, P, q.y1, q.y2, a.scale, H, WP, LV * HWp, sizeof(V),
+                                                  &s_hraw[buf][j][ti]);
         else
-            s_tw[buf][j][ti - P] = tab_entry<LV>(ti - P, P, q.x1, q.x2, a.scale, W, 1, HWp, sizeof(V),
-                                                 &s_wraw[buf][j][ti - P]);
+            s_tw[buf][j][ti - P] = tab_entry<LV, MID>(ti - P, P, q.x1, q.x2, a.scale, W, 1, HWp, sizeof(V),
+                                                      &s_wraw[buf][j][ti - P]);
         if (ti == 0)
             s_ob[buf][j] = (((size_t)max(q.k, 0) * a.C + c0) * BINS) * sizeof(float);
     };
@@ -607,6 +630,14 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
                     if (any_wide) {
                         if (wide && tall) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (wy + hy)));
                     }
+                }
+            }
+            if (MID) {
+                const bool mid = ((h.y | w.y) & TAB_MID_BIT) != 0;
+                if (__any_sync(0xFFFFFFFFu, mid)) {
+                    if (mid)
+                        v = tab_mid_bin<V>(v, smem_raw, h.x, hy, (h.y & TAB_MID_BIT) != 0, w.x, wy,
+                                           (w.y & TAB_MID_BIT) != 0, 2 * WP * (int)sizeof(V), 2 * (int)sizeof(V));
                 }
             }
             const bool big = ((h.y | w.y) & TAB_BIG_BIT) != 0;
@@ -684,6 +715,7 @@ __global__ void __launch_bounds__(PM_THREADS, 2) roi_pool_mean_kernel(RoiArgs a)
     constexpr int RPW = 32 / LPR;         // RoIs per warp
     constexpr int NW = PM_THREADS / 32;
     constexpr int NT = LV * LV;
+    constexpr bool MID = LV == 2 && P == 7;
     static_assert(P <= 16, "one lane per bin column");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -707,8 +739,8 @@ __global__ void __launch_bounds__(PM_THREADS, 2) roi_pool_mean_kernel(RoiArgs a)
     for (int rw = r_begin + (blockIdx.x * NW + warp) * RPW; rw < r_end; rw += stride) {  // warp-uniform
         const RoiBox q = load_roi(a, rw + sub, r_end);
         int hraw, wraw;
-        const int2 row = tab_entry<LV>(le, P, q.y1, q.y2, a.scale, H, WP, LV * HWp, sizeof(V), &hraw);
-        const int2 w = tab_entry<LV>(le, P, q.x1, q.x2, a.scale, W, 1, HWp, sizeof(V), &wraw);
+        const int2 row = tab_entry<LV, MID>(le, P, q.y1, q.y2, a.scale, H, WP, LV * HWp, sizeof(V), &hraw);
+        const int2 w = tab_entry<LV, MID>(le, P, q.x1, q.x2, a.scale, W, 1, HWp, sizeof(V), &wraw);
         const int wy = w.y & TAB_OFF_MASK;
         const bool wide = w.x != wy;
         const bool any_wide = __any_sync(0xFFFFFFFFu, wide);
@@ -729,6 +761,14 @@ __global__ void __launch_bounds__(PM_THREADS, 2) roi_pool_mean_kernel(RoiArgs a)
                 if (tall) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (w.x + hy)));
                 if (any_wide) {
                     if (wide && tall) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (wy + hy)));
+                }
+            }
+            if (MID) {
+                const bool mid = ((hyf | w.y) & TAB_MID_BIT) != 0;
+                if (__any_sync(0xFFFFFFFFu, mid)) {
+                    if (mid)
+                        v = tab_mid_bin<V>(v, smem_raw, hx, hy, (hyf & TAB_MID_BIT) != 0, w.x, wy,
+                                           (w.y & TAB_MID_BIT) != 0, 2 * WP * (int)sizeof(V), 2 * (int)sizeof(V));
                 }
             }
             const bool big = ((hyf | w.y) & TAB_BIG_BIT) != 0;
@@ -1344,11 +1384,14 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
                           TH_, stream);                                                                     \
     } while (0)
         static const int mode7 = getenv("FRCNN_POOL7_MODE") ? atoi(getenv("FRCNN_POOL7_MODE")) : 0;
+        // rows whose byte length is a multiple of 64 would put vertically adjacent bins on the same banks
+        // (64-wide maps: 45 % of the shared-memory wavefronts were conflicts): pad the pitch by one pixel
+        auto pitch_for = [&](int tcs) { return (W * 4 * tcs) % 64 == 0 ? W + 1 : W; };
         if (mean) {  // [K,C] = mean over the bins of RoIPool, never materialising [K,C,P,P]
-            a.pitch = W;
             int tcs = 0;
-            if (table_bytes(2, 4, W) <= 200 * 1024) tcs = 4;
-            else if (table_bytes(2, 2, W) <= 200 * 1024) tcs = 2;
+            if (table_bytes(2, 4, pitch_for(4)) <= 200 * 1024) tcs = 4;
+            else if (table_bytes(2, 2, pitch_for(2)) <= 200 * 1024) tcs = 2;
+            a.pitch = pitch_for(tcs ? tcs : 4);
             if (!tcs) {
                 set_error("%s: feature map too large for the fused pool + mean kernel", who);
                 return FRCNN_ERR_UNSUPPORTED;
@@ -1357,7 +1400,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             const int slabs = cdiv(C, tcs);
             a.CS = tcs;
             a.groups = std::max(1, std::min(cdiv(per_image_rois, 4 * per_iter), cdiv(8 * sm_count(), B * slabs)));
-            const size_t smem = table_bytes(2, tcs, W);
+            const size_t smem = table_bytes(2, tcs, a.pitch);
             if (PH == 7) {
                 if (tcs == 4) return launch_tab(roi_pool_mean_kernel<7, 4, 2>, a, smem, PM_THREADS, stream);
                 return launch_tab(roi_pool_mean_kernel<7, 2, 2>, a, smem, PM_THREADS, stream);
@@ -1382,13 +1425,13 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             if (table_bytes(3, 1, a.pitch) <= budget1) FRCNN_TAB(7, 784, 1, 1, false, 3);
         }
         if (!argmax) {
-            a.pitch = W;
-            const size_t smem4 = table_bytes(2, 4, W), smem2 = table_bytes(2, 2, W);
+            const size_t smem4 = table_bytes(2, 4, pitch_for(4)), smem2 = table_bytes(2, 2, pitch_for(2));
             int tcs = 0, minb = 0;
             if (smem4 <= budget2) tcs = 4, minb = 2;
             else if (smem2 <= budget2) tcs = 2, minb = 2;
             else if (smem4 <= 200 * 1024) tcs = 4, minb = 1;
             else if (smem2 <= 200 * 1024) tcs = 2, minb = 1;
+            a.pitch = pitch_for(tcs ? tcs : 4);
             if (tcs == 4 && minb == 2) {
                 if (PH == 7) FRCNN_TAB(7, 392, 4, 2, false, 2);
                 FRCNN_TAB(14, 392, 4, 2, false, 2);
@@ -1399,6 +1442,8 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
                 if (PH == 7) FRCNN_TAB(7, 392, 4, 1, false, 2);
                 FRCNN_TAB(14, 392, 4, 1, false, 2);
             } else if (tcs == 2) {
+                // one CTA per SM: twice the threads to keep the SM's latency hidden
+                if (PH == 7 && smem2 + 40 * 1024 <= 220 * 1024 && mode7 != 4) FRCNN_TAB(7, 784, 2, 1, false, 2);
                 if (PH == 7) FRCNN_TAB(7, 392, 2, 1, false, 2);
                 FRCNN_TAB(14, 392, 2, 1, false, 2);
             }
