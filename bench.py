@@ -362,14 +362,18 @@ def run_ours(args):
     while c0 < rows:
         n_sb, c0, ln = n_sb + 1, c0 + ln, min(2 * ln, smax)
     launches = 1 + 1 + n_sb + 1 + 1 + 1  # decode, topk, nms block kernel per super-block, finalize, coords, gather
-    kernel_name = "roi_pool_tab_kernel<14,392,4,2>" if (cfg["op"], P) == ("pool", 14) else (
-        ("roi_pool_staged_kernel<7,argmax>" if train else "roi_pool_tab_kernel<7,392,...>") if cfg["op"] == "pool"
-        else "roi_align_tab_kernel<7,2,392,2>")
+    # <P, threads, channels per CTA, CTAs per SM, argmax, table levels> as csrc/roi_ops.cu picks them
+    kernel_name = "roi_pool_tab_kernel<14,392,4,2,false,2>" if (cfg["op"], P) == ("pool", 14) else (
+        ("roi_pool_tab_kernel<7,392,4,2,true,1>" if train else
+         ("roi_pool_tab_kernel<7,784,2,1,false,2>" if H * W > 3000 else "roi_pool_tab_kernel<7,392,4,2,false,2>"))
+        if cfg["op"] == "pool" else "roi_align_tab_kernel<7,2,392,2>")
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from one ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get(args.workload, {}).get("dram_bytes")
+    in_mb = sum(t.numel() * 4 for t in sets[0]) / 1e6
+    out_mb = pooled.numel() * 4 * (2 if train else 1) / 1e6
     out = {
         "metric": "images/sec (RPN proposals + RoI gather hot path)", "value": world * B / (ms_step * 1e-3),
         "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -377,15 +381,18 @@ def run_ours(args):
         "config": {"workload": f"{args.workload}: {cfg['desc']}", "batch_per_gpu": B, "global_batch": world * B,
                    "anchors_per_image": N, "n_pre_nms": cfg["n_pre"], "n_post_nms": n_post,
                    "feature": [B, C, H, W], "roi_op": f"{cfg['op']} {P}x{P}",
-                   "l2": "3 input sets rotated (3x100 MB) + 3.85 GB output written per step: inputs never L2-resident",
+                   "l2": f"3 input sets rotated (3 x {in_mb:.0f} MB) + {out_mb:.0f} MB of gather output written per "
+                         "step: a step never finds its inputs in L2 (126 MB)",
                    "parallelism": f"dp{world} (images sharded per GPU; all_gather of rois when N>1)"},
         "proposals_per_sec": world * K / (ms_step * 1e-3),
         "breakdown_ms": {"proposals": prop_ms, "roi_gather": roi_ms},
         "cuda_graph_ms_per_step": graph_ms,
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "serial_ms_per_step": e2e_serial_ms,
-                "api": "ProposalCreator.batched + HarNetRoIHead.forward from pinned host buffers; copies of step "
-                       "i+1 overlap the compute of step i (copy stream + compute stream, double-buffered)"},
+                "api": "ProposalCreator.batched + HarNetRoIHead.forward (RoIPool + global-average classifier fused "
+                       "into one kernel, Linear heads) from pinned host buffers; copies of step i+1 overlap the "
+                       "compute of step i (copy stream + compute stream, double-buffered); PCIe-bound: "
+                       "h2d_bytes_per_step / ms_per_step is the host link's measured ~55 GB/s"},
         "gpu_launches": launches * args.steps,
         "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
