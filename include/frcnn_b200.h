@@ -196,6 +196,17 @@ int frcnn_roi_pool_mean_forward(const float* feat, int32_t batch, int32_t channe
                                 int32_t width, const float* rois5, int32_t num_rois, int32_t rois_per_image,
                                 int32_t pooled_h, int32_t pooled_w, float spatial_scale, float* out,
                                 void* workspace, size_t workspace_bytes, frcnn_stream_t stream);
+/* The same fusion for RoIAlign (the RoIAlign 7x7 HarDNet configuration): out [K,C] = mean over the bins
+ * of roi_align(feat, rois5, sampling_ratio > 0).  The mean is linear and separable in the features, so the
+ * kernel reads every pixel of a RoI's window once with a per-axis weight instead of 4*sr*sr taps per bin.
+ * Needs pooled*sampling_ratio <= 32 per side and a map of at most 64x64, else FRCNN_ERR_UNSUPPORTED.
+ * Agrees with roi_align().mean() to fp32 rounding (1e-5 relative).                                       */
+size_t frcnn_roi_align_mean_workspace_bytes(int32_t batch, int32_t num_rois);
+int frcnn_roi_align_mean_forward(const float* feat, int32_t batch, int32_t channels, int32_t height,
+                                 int32_t width, const float* rois5, int32_t num_rois, int32_t rois_per_image,
+                                 int32_t pooled_h, int32_t pooled_w, float spatial_scale,
+                                 int32_t sampling_ratio, int32_t aligned, float* out, void* workspace,
+                                 size_t workspace_bytes, frcnn_stream_t stream);
 /* grad_in [B,C,H,W] must be zero-initialised by the caller.                                     */
 int frcnn_roi_pool_backward(const float* grad_out, const int32_t* argmax, const float* rois5,
                             int32_t num_rois, int32_t channels, int32_t height, int32_t width,

@@ -34,3 +34,7 @@ if cfg["op"] == "pool":
     t = timeit(lambda: F.roi_pool_mean(feat, rois5, P, 1.0, rois_per_image=cfg["n_post"]))
     t2 = timeit(lambda: F.roi_pool_forward(feat, rois5, P, 1.0, out=pooled, rois_per_image=cfg["n_post"]).mean((2, 3)))
     print(f"{name} fused pool+mean -> [K,C]: {t:.3f} ms   (pool then .mean((2,3)): {t2:.3f} ms)")
+else:
+    t = timeit(lambda: F.roi_align_mean(feat, rois5, P, 1.0, 2, False, rois_per_image=cfg["n_post"]))
+    t2 = timeit(lambda: F.roi_align_forward(feat, rois5, P, 1.0, 2, False, out=pooled, rois_per_image=cfg["n_post"]).mean((2, 3)))
+    print(f"{name} fused align+mean -> [K,C]: {t:.3f} ms   (align then .mean((2,3)): {t2:.3f} ms)")

@@ -1117,6 +1117,151 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// RoIAlign + global average pool (HarDNet head with the RoIAlign configuration).
+//
+// mean over bins of RoIAlign is LINEAR in the features and, with a fixed sampling grid, SEPARABLE:
+//   out[k,c] = 1/(P*P*SR*SR) * sum_{sy,sx} sum_{taps} wy(sy,y) * wx(sx,x) * feat[c,y,x]
+//            = 1/(P*P*SR*SR) * sum_y Wy[y] * sum_x Wx[x] * feat[c,y,x],   Wy[y] = sum_sy wy(sy,y), Wx likewise
+// (a sample outside [-1, limit] has zero weight on its axis, so the reference's `continue` factorises too).
+// So instead of 4*SR*SR*P*P bilinear taps per (RoI, channel) -- 784 for 7x7 / 2x2 -- the kernel reads each
+// pixel of the RoI's window once, weighted: ~100 reads for a typical RoI, and writes [K,C].
+// Step 1 (roi_align_weights_kernel, one warp per RoI, once for all channels): per-axis window + weights into
+// a 528-byte record.  Step 2 (roi_align_mean_kernel, CTA = image x 4-channel slab like the other gather
+// kernels): a warp owns a RoI, its lanes tile the window, weighted sum, warp tree reduction.
+// Agreement with roi_align().mean((2,3)): fp32 rounding (different association), 1e-5 relative.
+// ---------------------------------------------------------------------------------------------
+constexpr int AW_MAX = 64;  // widest / tallest window a record holds (maps up to 64 pixels per side)
+struct AlignWeights {
+    int x0, nx, y0, ny;  // window origin and extent in pixels (nx, ny = 0: nothing in range)
+    float wx[AW_MAX], wy[AW_MAX];
+};
+
+__device__ __forceinline__ void axis_weights(int s, int NS, int P, int SR, float c1, float c2, float scale, int aligned,
+                                             int limit, int lane, int& origin, int& extent, float& w0, float& w1) {
+    AlignEntry e;
+    e.lohi = (int)0x80000000;
+    e.l = 0.f;
+    if (s < NS) e = align_entry(s / SR, s % SR, P, SR, c1, c2, scale, aligned, limit, 1);
+    const bool ok = s < NS && e.lohi >= 0;
+    const int lo = e.lohi & 0xFFFF, hi = (e.lohi >> 16) & 0x7FFF;
+    const int mn = __reduce_min_sync(0xFFFFFFFFu, ok ? lo : 0x7FFFFFFF);
+    const int mx = __reduce_max_sync(0xFFFFFFFFu, ok ? hi : -1);
+    origin = mn;
+    extent = mx >= mn ? min(mx - mn + 1, AW_MAX) : 0;
+    w0 = w1 = 0.f;
+    for (int t = 0; t < NS; ++t) {  // lane accumulates the weights landing on pixels origin+lane, origin+lane+32
+        const int tl = __shfl_sync(0xFFFFFFFFu, e.lohi, t);
+        const float l = __shfl_sync(0xFFFFFFFFu, e.l, t);
+        if (tl < 0) continue;  // uniform
+        const int plo = (tl & 0xFFFF) - mn, phi = ((tl >> 16) & 0x7FFF) - mn;
+        const float h = 1.f - l;
+        if (plo == lane) w0 += h;
+        if (phi == lane) w0 += l;
+        if (plo == lane + 32) w1 += h;
+        if (phi == lane + 32) w1 += l;
+    }
+}
+
+__global__ void __launch_bounds__(256) roi_align_weights_kernel(RoiArgs a, AlignWeights* __restrict__ rec) {
+    const int k = blockIdx.x * (256 / 32) + (threadIdx.x >> 5);
+    if (k >= a.K) return;
+    const int lane = threadIdx.x & 31;
+    const float* r = a.rois5 + (size_t)k * 5;
+    const float x1 = __ldg(r + 1), y1 = __ldg(r + 2), x2 = __ldg(r + 3), y2 = __ldg(r + 4);
+    const int SR = a.sampling_ratio;
+    int x0, nx, y0, ny;
+    float wx0, wx1, wy0, wy1;
+    axis_weights(lane, a.PW * SR, a.PW, SR, x1, x2, a.scale, a.aligned, a.W, lane, x0, nx, wx0, wx1);
+    axis_weights(lane, a.PH * SR, a.PH, SR, y1, y2, a.scale, a.aligned, a.H, lane, y0, ny, wy0, wy1);
+    AlignWeights* o = rec + k;
+    if (lane == 0) {
+        o->x0 = nx ? x0 : 0;
+        o->nx = ny ? nx : 0;  // either axis empty: nothing to add
+        o->y0 = ny ? y0 : 0;
+        o->ny = nx ? ny : 0;
+    }
+    o->wx[lane] = wx0;
+    o->wx[lane + 32] = wx1;
+    o->wy[lane] = wy0;
+    o->wy[lane + 32] = wy1;
+}
+
+constexpr int AM_THREADS = 512;
+
+__global__ void __launch_bounds__(AM_THREADS, 2) roi_align_mean_kernel(RoiArgs a, const AlignWeights* __restrict__ rec) {
+    constexpr int NW = AM_THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ float s_w[NW][2][AW_MAX];
+    float4* tab = reinterpret_cast<float4*>(smem_raw);
+    const int H = a.H, W = a.W, HW = H * W;
+    const int WP = a.pitch, HWp = (H * WP + 3) & ~3;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * 4;
+    const int cs = min(4, a.C - c0);
+    int r_begin, r_end;
+    roi_range(a, b, r_begin, r_end);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (r_begin + blockIdx.x * NW >= r_end) return;
+    float* raw = reinterpret_cast<float*>(tab + HWp);
+    stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
+    {
+        const int step_y = AM_THREADS / W, step_x = AM_THREADS - step_y * W;
+        int y = tid / W, x = tid - y * W;
+        for (int p = tid; p < HW; p += AM_THREADS) {
+            float4 v;
+            v.x = raw[p];
+            v.y = cs > 1 ? raw[HW + p] : 0.f;
+            v.z = cs > 2 ? raw[2 * HW + p] : 0.f;
+            v.w = cs > 3 ? raw[3 * HW + p] : 0.f;
+            tab[y * WP + x] = v;
+            x += step_x;
+            y += step_y;
+            if (x >= W) {
+                x -= W;
+                ++y;
+            }
+        }
+    }
+    __syncthreads();
+    const float norm = (float)(a.PH * a.PW) * (float)(a.sampling_ratio * a.sampling_ratio);
+    for (int r = r_begin + blockIdx.x * NW + warp; r < r_end; r += a.groups * NW) {
+        const int k = roi_at(a, r);
+        const AlignWeights* w = rec + k;
+        const int4 hdr = __ldg(reinterpret_cast<const int4*>(w));
+        const int x0 = hdr.x, nx = hdr.y, y0 = hdr.z, ny = hdr.w;
+        __syncwarp();  // previous RoI's weights no longer read
+        s_w[warp][0][lane] = __ldg(w->wx + lane);
+        s_w[warp][0][lane + 32] = __ldg(w->wx + lane + 32);
+        s_w[warp][1][lane] = __ldg(w->wy + lane);
+        s_w[warp][1][lane + 32] = __ldg(w->wy + lane + 32);
+        __syncwarp();
+        // lanes tile the window TY x TX with TX the smallest of 8 / 16 / 32 that covers its width
+        const int sh = nx <= 8 ? 3 : (nx <= 16 ? 4 : 5);
+        const int tx = 1 << sh, ty = 32 >> sh;
+        const int lx = lane & (tx - 1), ly = lane >> sh;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int yb = 0; yb < ny; yb += ty) {
+            const int yy = yb + ly;
+            const float wy = yy < ny ? s_w[warp][1][yy] : 0.f;
+            const float4* row = tab + (y0 + min(yy, ny - 1)) * WP + x0;
+            for (int xb = 0; xb < nx; xb += tx) {
+                const int xx = xb + lx;
+                const float wgt = xx < nx ? wy * s_w[warp][0][xx] : 0.f;
+                const float4 v = row[min(xx, nx - 1)];
+                acc.x += wgt * v.x;
+                acc.y += wgt * v.y;
+                acc.z += wgt * v.z;
+                acc.w += wgt * v.w;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) vxor_add(acc, d);
+        if (lane == 0) vmean_store(a.out + (size_t)k * a.C + c0, acc, norm, cs);
+    }
+}
+
 __global__ void roi_align_direct_kernel(RoiArgs a) {
     size_t total = (size_t)a.K * a.C * a.PH * a.PW;
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
@@ -1480,6 +1625,75 @@ int frcnn_roi_align_forward(const float* feat, int32_t B, int32_t C, int32_t H, 
                             size_t workspace_bytes, frcnn_stream_t stream) {
     return roi_forward_common(true, feat, B, C, H, W, rois5, K, per_image, PH, PW, scale, sampling_ratio, aligned, out,
                               nullptr, workspace, workspace_bytes, (cudaStream_t)stream, "frcnn_roi_align_forward");
+}
+
+size_t frcnn_roi_align_mean_workspace_bytes(int32_t batch, int32_t num_rois) {
+    Workspace ws(nullptr, 0);
+    roi_layout(ws, batch > 0 ? batch : 1, num_rois, nullptr);
+    ws.take<AlignWeights>(num_rois > 0 ? num_rois : 1);
+    return ws.off;
+}
+
+int frcnn_roi_align_mean_forward(const float* feat, int32_t B, int32_t C, int32_t H, int32_t W, const float* rois5,
+                                 int32_t K, int32_t per_image, int32_t PH, int32_t PW, float scale,
+                                 int32_t sampling_ratio, int32_t aligned, float* out, void* workspace,
+                                 size_t workspace_bytes, frcnn_stream_t stream_) {
+    const char* who = "frcnn_roi_align_mean_forward";
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_roi_common(feat, B, C, H, W, rois5, K, PH, PW, out, who);
+    if (rc) return rc;
+    if (K == 0) return FRCNN_OK;
+    const int pitch = (W % 2 == 0) ? W + 1 : W;  // odd pitch: the rows of a window start on different banks
+    const size_t smem = (size_t)2 * ((H * pitch + 3) & ~3) * sizeof(float4);
+    if (sampling_ratio <= 0 || PH * sampling_ratio > 32 || PW * sampling_ratio > 32 || H > AW_MAX || W > AW_MAX ||
+        smem > 200 * 1024 || B > 65535) {
+        set_error("%s: needs a fixed sampling grid with P*sampling_ratio <= 32 and a map of at most %dx%d", who, AW_MAX,
+                  AW_MAX);
+        return FRCNN_ERR_UNSUPPORTED;
+    }
+    RoiArgs a;
+    memset(&a, 0, sizeof(a));
+    a.feat = feat;
+    a.rois5 = rois5;
+    a.B = B;
+    a.C = C;
+    a.H = H;
+    a.W = W;
+    a.K = K;
+    a.PH = PH;
+    a.PW = PW;
+    a.scale = scale;
+    a.out = out;
+    a.sampling_ratio = sampling_ratio;
+    a.aligned = aligned;
+    a.pitch = pitch;
+    Workspace ws(workspace, workspace_bytes);
+    RoiWs w;
+    roi_layout(ws, B, K, &w);
+    AlignWeights* rec = ws.take<AlignWeights>(K);
+    if (!ws.ok()) {
+        set_error("%s: workspace too small or misaligned (%zu needed, %zu given)", who, ws.off, workspace_bytes);
+        return FRCNN_ERR_WORKSPACE;
+    }
+    if (per_image > 0) {
+        FRCNN_CHECK_ARG((int64_t)per_image * B == K, "%s: rois_per_image * batch != num_rois", who);
+        a.per_image = per_image;
+    } else {
+        roi_bucket_kernel<<<1, BUCKET_THREADS, 2 * B * sizeof(int), stream>>>(rois5, K, B, w.perm, w.offs);
+        FRCNN_LAUNCH_CHECK();
+        a.perm = w.perm;
+        a.offs = w.offs;
+    }
+    roi_align_weights_kernel<<<cdiv(K, 8), 256, 0, stream>>>(a, rec);
+    FRCNN_LAUNCH_CHECK();
+    const int slabs = cdiv(C, 4);
+    FRCNN_CHECK_ARG(slabs <= 65535, "%s: too many channel slabs", who);
+    const int nw = AM_THREADS / 32;
+    a.groups = std::max(1, std::min(cdiv(cdiv(K, B), 8 * nw), cdiv(8 * sm_count(), B * slabs)));
+    FRCNN_CUDA(cudaFuncSetAttribute(roi_align_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roi_align_mean_kernel<<<dim3(a.groups, slabs, B), AM_THREADS, smem, stream>>>(a, rec);
+    FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
 }
 
 int frcnn_roi_pool_backward(const float* grad_out, const int32_t* argmax, const float* rois5, int32_t K,

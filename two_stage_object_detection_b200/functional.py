@@ -394,6 +394,30 @@ def roi_pool_mean(feat, rois5, output_size, spatial_scale=1.0, rois_per_image=0)
     return out
 
 
+def roi_align_mean(feat, rois5, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=False, rois_per_image=0):
+    """mean over the bins of roi_align(feat, rois5) -> [K,C] (RoIAlign head + AdaptiveAvgPool2d(1) + Flatten) as a
+    separable weighted window sum; inference only.  Uncovered shapes (adaptive sampling grid, maps wider than
+    64 pixels) take the two steps."""
+    lib = _lib.load()
+    dev = _lib.require_cuda(feat, rois5)
+    f, r = f32c(feat), f32c(rois5).view(-1, 5)
+    B, Cc, H, W = f.shape
+    K = r.shape[0]
+    ph, pw = _pair(output_size)
+    out = torch.empty((K, Cc), dtype=torch.float32, device=dev)
+    nbytes = lib.frcnn_roi_align_mean_workspace_bytes(B, K)
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(dev, nbytes)
+        rc = lib.frcnn_roi_align_mean_forward(f.data_ptr(), B, Cc, H, W, r.data_ptr(), K, int(rois_per_image), ph, pw,
+                                              float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
+                                              out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+    if rc == _lib.ERR_UNSUPPORTED:
+        return roi_align_forward(f, r, output_size, spatial_scale, sampling_ratio, aligned,
+                                 rois_per_image=rois_per_image).mean((2, 3))
+    check(rc, "frcnn_roi_align_mean_forward")
+    return out
+
+
 def roi_align_forward(feat, rois5, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=False, out=None,
                       rois_per_image=0):
     lib = _lib.load()

@@ -78,7 +78,8 @@ class HarNetRoIHead(nn.Module):
         HarNetClassifier (AdaptiveAvgPool2d(1) + Flatten, models/hardnet.py:203-212) and nothing needs the
         pooled tensor for a backward pass."""
         seq = getattr(self.classifier, "clssifier", None)
-        return (self.fuse_mean and isinstance(self.roi, RoIPool) and isinstance(seq, nn.Sequential) and len(seq) == 2
+        return (self.fuse_mean and isinstance(self.roi, (RoIPool, RoIAlign)) and isinstance(seq, nn.Sequential)
+                and len(seq) == 2
                 and isinstance(seq[0], nn.AdaptiveAvgPool2d) and tuple(_pair2(seq[0].output_size)) == (1, 1)
                 and isinstance(seq[1], nn.Flatten) and not (torch.is_grad_enabled() and x.requires_grad))
 
@@ -91,7 +92,11 @@ class HarNetRoIHead(nn.Module):
                 roi_indices = torch.arange(n, dtype=torch.int32, device=x.device)
                 grouped = rois_.shape[1]
             r5 = F.roi_head_coords(rois_, roi_indices, img_size, (x.size()[2], x.size()[3]))
-            fc7 = F.roi_pool_mean(x, r5, self.roi.output_size, self.roi.spatial_scale, grouped)
+            if isinstance(self.roi, RoIPool):
+                fc7 = F.roi_pool_mean(x, r5, self.roi.output_size, self.roi.spatial_scale, grouped)
+            else:
+                fc7 = F.roi_align_mean(x, r5, self.roi.output_size, self.roi.spatial_scale, self.roi.sampling_ratio,
+                                       self.roi.aligned, grouped)
         else:
             pool = self.gather(x, rois, roi_indices, img_size)
             fc7 = self.classifier(pool)
