@@ -170,6 +170,26 @@ int frcnn_proposal_targets(const frcnn_proposal_target_params* p, const float* r
                            float* sample_roi, float* gt_loc, int64_t* out_label, int32_t* n_out,
                            int32_t* status, frcnn_stream_t stream);
 
+/* ---- after the head: detections --------------------------------------------------
+ * Post-head decode  nets/frcnn_training.py:311-320.  roi [T,4], roi_cls_loc [T,4*C], roi_score [T,C]
+ * (T = n*R rows), label [T] int64 or NULL: the loc row of class label[t] (the reference passes
+ * gt_roi_label) or, with NULL, of the best class is applied to the RoI with loc2bbox;
+ * cls_score / cls_index = torch.max(roi_score, dim=1) (first index on ties, NaN wins).
+ * bad_label [1] int32 (device) is set when a label is outside [0,C) (the reference's IndexError).   */
+int frcnn_detection_decode(const float* roi, const float* roi_cls_loc, const float* roi_score,
+                           const int64_t* label, int64_t total, int32_t n_class, float* boxes,
+                           float* cls_score, int64_t* cls_index, int32_t* bad_label,
+                           frcnn_stream_t stream);
+/* The evaluator's per-class NMS  nets/frcnn_training.py:441-454 (for each class c: torchvision nms on
+ * the rows with classes == c), all classes and images in one launch: boxes [B,R,4], scores [B,R],
+ * classes [B,R] int64 (NULL: one class = multi_inference.py:84), n_valid [B] (NULL: R rows each).
+ * keep [B,R] int32: kept original row indices ordered by (score desc, index asc), -1 padded -- the rows
+ * of class c, in that order, are the reference's keep list for c; n_keep [B].  R <= 1024 per image,
+ * else FRCNN_ERR_UNSUPPORTED (frcnn_nms handles long single-class lists).                            */
+int frcnn_nms_by_class(const float* boxes, const float* scores, const int64_t* classes,
+                       const int32_t* n_valid, int32_t batch, int32_t rows, double iou_threshold,
+                       int32_t* keep, int32_t* n_keep, frcnn_stream_t stream);
+
 /* ---- RoI head gather -------------------------------------------------------------------------
  * HarNetRoIHead.forward coordinate map + index concat  nets/classify.py:29-38:
  * rois [n*R,4] image coords, roi_indices [n] (int32) -> rois5 [n*R,5] = (idx, x/d1*Wf, y/d0*Hf..). */

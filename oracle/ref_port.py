@@ -212,6 +212,43 @@ def nms(boxes, scores, iou_threshold) -> np.ndarray:
     return keep[:k].copy()
 
 
+def detection_decode(roi, roi_cls_loc, roi_score, label=None):
+    """Post-head decode, nets/frcnn_training.py:311-320: class-specific loc rows gathered by `label`
+    (the reference passes gt_roi_label; None = the predicted class, plain inference), loc2bbox, and
+    torch.max over the class scores (first index on ties, NaN wins).
+    roi [R,4], roi_cls_loc [R,4C], roi_score [R,C] -> (boxes [R,4], cls_score [R], cls_index [R] int64)."""
+    r = _f32(roi)
+    sc = _f32(roi_score)
+    R, C = sc.shape
+    loc = _f32(roi_cls_loc).reshape(R, C, 4)
+    nan = np.isnan(sc)
+    cls_index = np.where(nan.any(1), nan.argmax(1), sc.argmax(1)).astype(np.int64)
+    cls_score = sc[np.arange(R), cls_index]
+    pick = cls_index if label is None else np.asarray(label).astype(np.int64)
+    boxes = decode(r, loc[np.arange(R), pick]) if R else np.zeros((0, 4), F32)
+    return boxes, cls_score, cls_index
+
+
+def nms_by_class(boxes, scores, classes, iou_threshold):
+    """The evaluator's per-class NMS, nets/frcnn_training.py:441-454: for every class c, torchvision nms on
+    the rows with classes == c.  Returns the kept ORIGINAL row indices of all classes merged, ordered by
+    (score desc, index asc) -- the rows of class c, in that order, are the reference's `keep` for c.
+    classes=None: one class (multi_inference.py:84)."""
+    b = _f32(boxes)
+    s = _f32(scores)
+    n = b.shape[0]
+    cl = np.zeros(n, np.int64) if classes is None else np.asarray(classes).astype(np.int64)
+    kept = []
+    for c in np.unique(cl):
+        idx = np.nonzero(cl == c)[0]
+        kept.append(idx[nms(b[idx], s[idx], iou_threshold)])
+    kept = np.concatenate(kept) if kept else np.zeros(0, np.int64)
+    order = argsort_desc_stable(s)
+    rank = np.empty(n, np.int64)
+    rank[order] = np.arange(n)
+    return kept[np.argsort(rank[kept], kind="stable")].astype(np.int64)
+
+
 def proposal_limits(mode, n_train_pre_nms=12000, n_train_post_nms=600, n_test_pre_nms=3000,
                     n_test_post_nms=300):
     """nets/rpn.py:37-42: only the exact string "train" selects the train limits."""

@@ -391,8 +391,61 @@ def gen_trainer():
     save("trainer", **arrs)
 
 
+def gen_detections():
+    """Post-head step: class-specific loc gather + loc2bbox + torch.max over the class scores
+    exactly as nets/frcnn_training.py:311-320 does them, then the evaluator's per-class NMS
+    (`where(classes_pred == c)` -> torchvision nms, :441-454) and multi_inference.py:84's class-agnostic
+    nms(iou_threshold=0.1)."""
+    g = torch.Generator().manual_seed(909)
+    arrs = {}
+    cases = [(128, 21, 320.0, "rand"), (300, 21, 600.0, "ties"), (600, 5, 600.0, "dense"), (1, 3, 100.0, "rand"),
+             (1024, 21, 800.0, "rand"), (800, 2, 300.0, "dense")]
+    for i, (R, C, size, kind) in enumerate(cases):
+        roi = rand_boxes(g, R, size, 16, size / 3 if kind != "dense" else size / 1.5)
+        cls_loc = torch.randn(R, C * 4, generator=g) * 0.3
+        score = torch.randn(R, C, generator=g)
+        if kind == "ties":
+            score = torch.round(score * 2) / 2          # exact ties between classes and between RoIs
+        label = torch.randint(0, C, (R,), generator=g)
+        # nets/frcnn_training.py:311-320
+        n_sample = R
+        roi_cls_loc = cls_loc.view(n_sample, -1, 4)
+        roi_loc = roi_cls_loc[torch.arange(0, n_sample).type_as(label), label]
+        boxes = ref_box.loc2bbox(roi, roi_loc)
+        cls_score_pred, cls_index_pred = torch.max(score, dim=1)
+        # the same with the predicted class instead of the ground-truth one (plain inference)
+        roi_loc_p = roi_cls_loc[torch.arange(0, n_sample), cls_index_pred]
+        boxes_p = ref_box.loc2bbox(roi, roi_loc_p)
+        arrs[f"roi{i}"] = npy(roi)
+        arrs[f"cls_loc{i}"] = npy(cls_loc)
+        arrs[f"score{i}"] = npy(score)
+        arrs[f"label{i}"] = npy(label)
+        arrs[f"boxes{i}"] = npy(boxes)
+        arrs[f"boxes_pred_class{i}"] = npy(boxes_p)
+        arrs[f"cls_score{i}"] = npy(cls_score_pred)
+        arrs[f"cls_index{i}"] = npy(cls_index_pred)
+        # evaluator: per class, nets/frcnn_training.py:441-454 (nms_iou_threshold default 0.7)
+        keep_all = []
+        for c in range(C):
+            idx = torch.where(cls_index_pred == c)[0]
+            k = tv_nms(boxes[idx], cls_score_pred[idx], 0.7)
+            keep_all.append(idx[k])
+            arrs[f"keep{i}_c{c}"] = npy(idx[k]).astype(np.int32)
+            arrs[f"keep03_{i}_c{c}"] = npy(idx[tv_nms(boxes[idx], cls_score_pred[idx], 0.3)]).astype(np.int32)
+        # multi_inference.py:84
+        arrs[f"keep_agnostic{i}"] = npy(tv_nms(boxes, cls_score_pred, 0.1)).astype(np.int32)
+        print(f"  detections case {i} ({kind}): R={R} C={C} kept {sum(len(k) for k in keep_all)} per class, "
+              f"{len(arrs[f'keep_agnostic{i}'])} agnostic")
+    arrs["n_cases"] = len(cases)
+    arrs["n_class"] = np.array([c[1] for c in cases])
+    save("detections", **arrs)
+
+
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for fn in (gen_anchors, gen_boxmath, gen_proposals, gen_nms, gen_anchor_targets,
-               gen_proposal_targets, gen_roi, gen_rpn_forward, gen_trainer):
+               gen_proposal_targets, gen_roi, gen_rpn_forward, gen_trainer, gen_detections):
+        if only and fn.__name__ not in only:
+            continue
         print(fn.__name__)
         fn()

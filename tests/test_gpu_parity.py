@@ -759,3 +759,53 @@ def test_ddp_training_step_two_gpus():
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "ddp ok" in out.stdout
+
+
+# ------------------------------------------------------------------------------------------------
+# after the head
+# ------------------------------------------------------------------------------------------------
+def test_detection_decode_and_per_class_nms_golden(F):
+    """Against fixtures made with the reference's loc2bbox / torch.max / torchvision nms: class index and
+    score exact, boxes 1e-5, per-class and class-agnostic keep lists exact (order included)."""
+    g = load_golden("detections")
+    for i in range(int(g["n_cases"])):
+        C = int(g["n_class"][i])
+        roi, cl, sc, lab = T(g[f"roi{i}"]), T(g[f"cls_loc{i}"]), T(g[f"score{i}"]), T(g[f"label{i}"])
+        boxes, cs, ci = F.detection_decode(roi, cl, sc, lab, check_labels=True)
+        assert np.array_equal(N(ci), g[f"cls_index{i}"]) and np.array_equal(N(cs), g[f"cls_score{i}"])
+        assert box_close(N(boxes), g[f"boxes{i}"], 800.0)
+        bp, _, _ = F.detection_decode(roi, cl, sc)
+        assert box_close(N(bp), g[f"boxes_pred_class{i}"], 800.0)
+        gb, gs, gc = T(g[f"boxes{i}"])[None], T(g[f"cls_score{i}"])[None], T(g[f"cls_index{i}"])[None]
+        for thr, tag in ((0.7, "keep"), (0.3, "keep03_")):
+            keep, nk = F.nms_by_class(gb, gs, gc, thr)
+            kept = N(keep[0, :int(nk[0])]).astype(np.int64)
+            assert (N(keep[0, int(nk[0]):]) == -1).all()
+            for c in range(C):
+                assert np.array_equal(kept[g[f"cls_index{i}"][kept] == c], g[f"{tag}{i}_c{c}"]), (i, c, thr)
+        keep, nk = F.nms_by_class(gb, gs, None, 0.1)
+        assert np.array_equal(N(keep[0, :int(nk[0])]), g[f"keep_agnostic{i}"])
+    with pytest.raises(IndexError):
+        F.detection_decode(roi, cl, sc, torch.full_like(lab, C), check_labels=True)
+
+
+def test_nms_by_class_batched_ragged_vs_oracle(F, O):
+    """Several images in one launch with different valid counts, duplicates, zero-area boxes and NaN scores."""
+    rng = np.random.default_rng(23)
+    B, R, C = 5, 257, 4
+    c = rng.uniform(0, 200, (B, R, 2)).astype(np.float32)
+    wh = rng.uniform(10, 90, (B, R, 2)).astype(np.float32)
+    boxes = np.concatenate([c - wh / 2, c + wh / 2], -1).astype(np.float32)
+    boxes[:, 50:60] = boxes[:, 40:50]
+    boxes[:, ::17, 2] = boxes[:, ::17, 0]
+    scores = (np.round(rng.uniform(0, 1, (B, R)) * 50) / 50).astype(np.float32)
+    cls = rng.integers(0, C, (B, R))
+    cls[:, 50:60] = cls[:, 40:50]
+    n_valid = np.array([R, 0, 1, 100, 256], np.int32)
+    keep, nk = F.nms_by_class(T(boxes), T(scores), T(cls), 0.5, T(n_valid))
+    for b in range(B):
+        n = int(n_valid[b])
+        ref = O.nms_by_class(boxes[b, :n], scores[b, :n], cls[b, :n], 0.5)
+        assert int(nk[b]) == len(ref) and np.array_equal(N(keep[b, :len(ref)]).astype(np.int64), ref), b
+    with pytest.raises(RuntimeError):
+        F.nms_by_class(torch.zeros(1, 1025, 4, device=DEV), torch.zeros(1, 1025, device=DEV), None, 0.5)

@@ -176,3 +176,23 @@ def test_rpn_forward_glue():
     roi = O.proposal_layer(g["rpn_locs"][0], g["fg"][0], anchor, img, mode="test",
                            n_test_pre_nms=500, n_test_post_nms=40)
     assert box_close(roi, g["rois"][0], float(max(img)))
+
+
+def test_detections_decode_and_per_class_nms():
+    """post-head decode (frcnn_training.py:311-320), the evaluator's per-class NMS (:441-454) and
+    multi_inference.py:84's class-agnostic NMS, against fixtures produced by the reference's own loc2bbox,
+    torch.max and torchvision.ops.nms."""
+    g = load_golden("detections")
+    for i in range(int(g["n_cases"])):
+        C = int(g["n_class"][i])
+        boxes, sc, ci = O.detection_decode(g[f"roi{i}"], g[f"cls_loc{i}"], g[f"score{i}"], g[f"label{i}"])
+        assert np.array_equal(ci, g[f"cls_index{i}"]) and np.array_equal(sc, g[f"cls_score{i}"])
+        assert box_close(boxes, g[f"boxes{i}"], 800.0)
+        boxes_p, _, _ = O.detection_decode(g[f"roi{i}"], g[f"cls_loc{i}"], g[f"score{i}"])
+        assert box_close(boxes_p, g[f"boxes_pred_class{i}"], 800.0)
+        for thr, tag in ((0.7, "keep"), (0.3, "keep03_")):
+            kept = O.nms_by_class(g[f"boxes{i}"], g[f"cls_score{i}"], g[f"cls_index{i}"], thr)
+            for c in range(C):
+                want = g[f"{tag}{i}_c{c}"]
+                assert np.array_equal(kept[g[f"cls_index{i}"][kept] == c], want), (i, c, thr)
+        assert np.array_equal(O.nms_by_class(g[f"boxes{i}"], g[f"cls_score{i}"], None, 0.1), g[f"keep_agnostic{i}"])

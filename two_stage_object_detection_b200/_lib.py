@@ -81,6 +81,8 @@ SIGNATURES = {
     "frcnn_roi_head_coords": (_I, [_P, _P, _I, _I, _F, _F, _I, _I, _P, _P]),
     "frcnn_roi_workspace_bytes": (_Z, [_I, _I]),
     "frcnn_roi_pool_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
+    "frcnn_detection_decode": (_I, [_P, _P, _P, _P, C.c_int64, _I, _P, _P, _P, _P, _P]),
+    "frcnn_nms_by_class": (_I, [_P, _P, _P, _P, _I, _I, C.c_double, _P, _P, _P]),
     "frcnn_roi_align_mean_workspace_bytes": (_Z, [_I, _I]),
     "frcnn_roi_align_mean_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _F, _I, _I, _P, _P, _Z, _P]),
     "frcnn_roi_pool_mean_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _F, _P, _P, _Z, _P]),

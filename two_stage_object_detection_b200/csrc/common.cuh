@@ -3,6 +3,7 @@
 // reference's ATen/torchvision CPU kernels do them.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -205,6 +206,26 @@ __device__ __forceinline__ float4 decode_box(const float4& a, const float4& l) {
     float nw = expf(l.z) * w, nh = expf(l.w) * h;
     float hw = 0.5f * nw, hh = 0.5f * nh;
     return make_float4(ncx - hw, ncy - hh, ncx + hw, ncy + hh);
+}
+
+// torchvision nms_kernel: inter / (area_i + area_j - inter) > thr  (no eps; NaN never suppresses).
+// `thr` is the largest float <= the double threshold, so (float)ovr > thr <=> (double)ovr > thr_d.
+__device__ __forceinline__ bool nms_suppresses(const float4& r, float ra, const float4& c, float ca, float thr) {
+    float xx1 = fmaxf(r.x, c.x), yy1 = fmaxf(r.y, c.y);
+    float xx2 = fminf(r.z, c.z), yy2 = fminf(r.w, c.w);
+    float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
+    float inter = w * h;
+    float uni = ra + ca;
+    uni = uni - inter;
+    return div_mostly_zero(inter, uni) > thr;
+}
+
+
+static inline float float_threshold(double thr) {
+    // largest float T with T <= thr, so that for every float x: x > T  <=>  (double)x > thr
+    float t = (float)thr;
+    if ((double)t > thr) t = nextafterf(t, -INFINITY);
+    return t;
 }
 
 }  // namespace frcnn

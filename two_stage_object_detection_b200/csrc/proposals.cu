@@ -506,18 +506,6 @@ constexpr int NMS_CB = 256;   // columns per CTA tile (8 warps x 32 lanes)
 constexpr int NMS_RB = 64;    // rows staged per in-block tile
 constexpr int NMS_KC = 256;   // kept boxes staged per prev tile
 
-// torchvision nms_kernel: inter / (area_i + area_j - inter) > thr  (no eps; NaN never suppresses).
-// `thr` is the largest float <= the double threshold, so (float)ovr > thr <=> (double)ovr > thr_d.
-__device__ __forceinline__ bool nms_suppresses(const float4& r, float ra, const float4& c, float ca, float thr) {
-    float xx1 = fmaxf(r.x, c.x), yy1 = fmaxf(r.y, c.y);
-    float xx2 = fminf(r.z, c.z), yy2 = fminf(r.w, c.w);
-    float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
-    float inter = w * h;
-    float uni = ra + ca;
-    uni = uni - inter;
-    return div_mostly_zero(inter, uni) > thr;
-}
-
 struct NmsArgs {
     const float4* boxes;   // [B,row_stride]
     const int* n_sel;      // [B]
@@ -783,13 +771,6 @@ __global__ void keep_to_index_kernel(const int* __restrict__ keep, const int* __
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static float float_threshold(double thr) {
-    // largest float T with T <= thr, so that for every float x: x > T  <=>  (double)x > thr
-    float t = (float)thr;
-    if ((double)t > thr) t = nextafterf(t, -INFINITY);
-    return t;
-}
-
 static int pick_superblock(int requested, int n_rows, int keep_cap) {
     // default: about twice the number of boxes wanted, so that the first super-block usually
     // finishes the job and little of the IoU mask is computed for nothing (measured on cfg2: a

@@ -507,3 +507,55 @@ def roi_align(feat, rois5, output_size, spatial_scale=1.0, sampling_ratio=-1, al
         return _RoIAlignFn.apply(feat, rois5, output_size, spatial_scale, sampling_ratio, aligned, rois_per_image)
     return roi_align_forward(feat, rois5, output_size, spatial_scale, sampling_ratio, aligned,
                              rois_per_image=rois_per_image)
+
+
+# ------------------------------------------------------------------------------------------------
+# after the head: detections
+# ------------------------------------------------------------------------------------------------
+def detection_decode(roi: torch.Tensor, roi_cls_loc: torch.Tensor, roi_score: torch.Tensor,
+                     label: Optional[torch.Tensor] = None, check_labels: bool = False):
+    """nets/frcnn_training.py:311-320 for any leading shape: roi [...,4], roi_cls_loc [...,4C],
+    roi_score [...,C], label [...] int64 or None (None: decode with the best class's loc row).
+    Returns (boxes [...,4], cls_score [...], cls_index [...] int64).  ``check_labels=True`` synchronises
+    and raises IndexError for a label outside [0,C), as the reference's gather does."""
+    lib = _lib.load()
+    dev = _lib.require_cuda(roi, roi_cls_loc, roi_score)
+    Cn = roi_score.shape[-1]
+    lead = tuple(roi_score.shape[:-1])
+    r, cl, sc = f32c(roi).view(-1, 4), f32c(roi_cls_loc).view(-1, 4 * Cn), f32c(roi_score).view(-1, Cn)
+    T = sc.shape[0]
+    if r.shape[0] != T or cl.shape[0] != T:
+        raise ValueError("detection_decode: roi / roi_cls_loc / roi_score disagree on the number of rows")
+    lab = None if label is None else label.detach().to(torch.int64).contiguous().view(-1)
+    boxes = torch.empty((T, 4), dtype=torch.float32, device=dev)
+    cs = torch.empty((T,), dtype=torch.float32, device=dev)
+    ci = torch.empty((T,), dtype=torch.int64, device=dev)
+    bad = torch.empty((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.frcnn_detection_decode(r.data_ptr(), cl.data_ptr(), sc.data_ptr(), ptr(lab), T, int(Cn),
+                                         boxes.data_ptr(), cs.data_ptr(), ci.data_ptr(), bad.data_ptr(),
+                                         _lib.stream_ptr(dev)), "frcnn_detection_decode")
+    if check_labels and lab is not None and int(bad.item()):
+        raise IndexError("detection_decode: label outside [0, n_class)")
+    return boxes.view(*lead, 4), cs.view(lead), ci.view(lead)
+
+
+def nms_by_class(boxes: torch.Tensor, scores: torch.Tensor, classes: Optional[torch.Tensor], iou_threshold: float,
+                 n_valid: Optional[torch.Tensor] = None):
+    """The evaluator's per-class NMS (nets/frcnn_training.py:441-454), batched: boxes [B,R,4], scores [B,R],
+    classes [B,R] int64 or None (class-agnostic, multi_inference.py:84), n_valid [B] or None.
+    Returns (keep [B,R] int32: kept row indices by (score desc, index asc), -1 padded; n_keep [B])."""
+    lib = _lib.load()
+    dev = _lib.require_cuda(boxes, scores)
+    b, s = f32c(boxes), f32c(scores)
+    if b.dim() != 3 or s.shape != b.shape[:2]:
+        raise ValueError("nms_by_class expects boxes [B,R,4] and scores [B,R]")
+    B, R = s.shape
+    cl = None if classes is None else classes.detach().to(torch.int64).contiguous()
+    nv = None if n_valid is None else n_valid.to(torch.int32).contiguous()
+    keep = torch.empty((B, R), dtype=torch.int32, device=dev)
+    n_keep = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.frcnn_nms_by_class(b.data_ptr(), s.data_ptr(), ptr(cl), ptr(nv), B, R, float(iou_threshold),
+                                     keep.data_ptr(), n_keep.data_ptr(), _lib.stream_ptr(dev)), "frcnn_nms_by_class")
+    return keep, n_keep
