@@ -148,8 +148,9 @@ class FasterRCNNTrainer(torch.nn.Module):
         lab = torch.where(valid, gt_roi_labels, torch.zeros_like(gt_roi_labels))
         roi_loc = roi_cls_locs.view(n, n_sample, -1, 4).gather(
             2, lab.view(n, n_sample, 1, 1).expand(n, n_sample, 1, 4)).squeeze(2)
-        anchors_pred = F.loc2bbox(sample_rois.reshape(-1, 4), roi_loc.detach().reshape(-1, 4)).view(n, n_sample, 4)
-        classes_score_pred, classes_pred = torch.max(roi_scores, dim=2)
+        # :311-320 for the whole batch in one kernel: class-specific loc row -> loc2bbox, torch.max over classes
+        anchors_pred, classes_score_pred, classes_pred = F.detection_decode(
+            sample_rois, roi_cls_locs.detach(), roi_scores.detach(), lab)
         roi_loc_loss = self._loc_loss(roi_loc, gt_roi_locs, torch.where(valid, gt_roi_labels, -torch.ones_like(lab)),
                                       self.roi_sigma)
         ce2 = TF.cross_entropy(roi_scores.reshape(-1, roi_scores.size(2)),
