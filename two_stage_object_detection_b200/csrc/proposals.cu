@@ -596,10 +596,58 @@ constexpr int NMS_MAX_WORDS = 256;  // S <= 8192
 
 // One CTA per image, one thread per 32-candidate column word t of the super-block.  Step u resolves
 // the 32 candidates of block u in warp 0 (serial over the 32 bits, diagonal mask word per lane), then
-// every thread t > u ORs the mask rows of the newly kept candidates into its removed word R[t].  The
-// 32 mask words thread t needs for step u+1 (M[t][32(u+1)..]) do not depend on the outcome of step u,
-// so they are loaded one step ahead and their latency hides behind the resolve.
-__device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const NmsState& st, uint32_t* R) {
+// every thread t > u ORs the mask rows of the newly kept candidates into its removed word R[t].
+//
+// The mask rows of step u (for every column word t >= u: 32 words, 128 contiguous bytes of the
+// column-word-major mask) do not depend on the outcome of earlier steps, so the whole CTA streams them
+// from L2 into a shared-memory ring with cp.async, NMS_RING_DEPTH steps ahead: a step then costs the
+// resolve chain plus two barriers instead of an L2 round trip (measured on the 2048-wide super-blocks of
+// the proposal-stress configuration: ~1 us per step with register prefetch one step ahead).
+constexpr int NMS_RING_WORDS = 64;   // ring path: super-blocks up to 2048 candidates
+constexpr int NMS_RING_DEPTH = 3;    // steps in flight
+constexpr int NMS_RING_STAGES = NMS_RING_DEPTH + 1;
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Greedy resolve of 32 consecutive candidates: `open` = candidates no earlier box removed, D (per lane) =
+// which later candidates of the word lane's candidate suppresses (strictly upper triangular).  Candidate i
+// is kept iff it is open and no KEPT j < i suppresses it.  The serial form is a 32-long dependent chain
+// (~25 cycles per bit through a predicate); this is its fixed-point form: start from "every open candidate
+// kept", let the kept ones vote their rows together (one REDUX.OR), drop what they suppress, repeat.  Bit i
+// depends only on bits < i, so after t rounds the first t bits are final and an unchanged word is the
+// greedy answer; typical suppression chains are 2-4 deep.
+__device__ __forceinline__ uint32_t nms_resolve_word(uint32_t open, uint32_t D, int lane) {
+    uint32_t kept = open;
+    for (;;) {
+        const uint32_t hit = __reduce_or_sync(0xFFFFFFFFu, ((kept >> lane) & 1u) ? D : 0u);
+        const uint32_t next = open & ~hit;
+        if (next == kept) return kept;
+        kept = next;
+    }
+}
+
+// Boxes of the candidates kept in this super-block, for the "suppress against the kept list" tiles of the
+// next ones.  Done once after the scan: a load -> store of the box inside a step made every step wait for
+// an L2 round trip (the store needs the loaded registers before the warp can reach the step's barrier).
+__device__ __forceinline__ void nms_copy_kept_boxes(const NmsArgs& a, int b, const float4* boxes, int first,
+                                                    const int* s_nkept) {
+    __syncthreads();  // keep[] of this scan written (same CTA), *s_nkept final
+    const int last = *s_nkept;
+    for (int i = first + (int)threadIdx.x; i < last; i += (int)blockDim.x)
+        a.kept_box[(size_t)b * a.keep_cap + i] = __ldg(boxes + __ldcg(a.keep + (size_t)b * a.keep_cap + i));
+    __syncthreads();  // thread 0 reads *s_nkept again below
+}
+
+__device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const NmsState& st, uint32_t* R,
+                                               uint32_t* ring) {
     __shared__ uint32_t s_kb;
     __shared__ int s_nkept, s_done;
     const int n = a.n_sel[b];
@@ -627,6 +675,109 @@ __device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const Nm
         s_nkept = st.n_kept;
         s_done = 0;
     }
+    const bool use_ring = nw <= NMS_RING_WORDS;
+    // ---- ring path -------------------------------------------------------------------------------
+    if (use_ring) {
+        // stage of step u: [t][32 words] for t in [u, nw); 16-byte chunk c -> column word u + c/8, part c%8
+        auto issue = [&](int u) {
+            if (u < nw) {
+                uint32_t* dst = ring + (u % NMS_RING_STAGES) * (NMS_RING_WORDS * 32);
+                const int chunks = (nw - u) * 8;
+                for (int c = t; c < chunks; c += NMS_MAX_WORDS) {
+                    const int tw = u + (c >> 3), part = c & 7;
+                    cp_async_16(dst + tw * 32 + part * 4, mask + (size_t)tw * a.S + 32 * u + part * 4);
+                }
+            }
+            cp_async_commit();  // one group per step, empty past the end: the wait count stays uniform
+        };
+#pragma unroll
+        for (int u = 0; u < NMS_RING_DEPTH; ++u) issue(u);
+#ifdef FRCNN_NMS_TIMING
+        long long tq0 = clock64(), tq_wait = 0, tq_res = 0, tq_s2 = 0, tq_or = 0, tq_iss = 0, tq_fix = 0, tq;
+        int tq_steps = 0;
+#define TQ(acc) do { asm volatile("" ::: "memory"); long long n_ = clock64(); asm volatile("" ::: "memory"); acc += n_ - tq; tq = n_; } while (0)
+#else
+#define TQ(acc)
+#endif
+        for (int u = 0; u < nw; ++u) {
+#ifdef FRCNN_NMS_TIMING
+            tq = clock64();
+            ++tq_steps;
+#endif
+            cp_async_wait<NMS_RING_DEPTH - 1>();
+            __syncthreads();  // stage u landed for every thread; R[] of step u-1 complete
+            TQ(tq_wait);
+            const uint32_t* stage = ring + (u % NMS_RING_STAGES) * (NMS_RING_WORDS * 32);
+            if (warp == 0) {
+                const int rowi = 32 * u + lane;
+                const uint32_t D = (rowi < ncol ? stage[u * 32 + lane] : 0u) & ~((2u << lane) - 1u);
+                uint32_t kb = nms_resolve_word(~R[u], D, lane);
+                TQ(tq_fix);
+                int nk = s_nkept;
+                int room = a.keep_cap - nk;
+                int cnt = __popc(kb);
+                int done = 0;
+                if (cnt >= room) {
+                    while (__popc(kb) > room) kb &= ~(0x80000000u >> __clz(kb));
+                    cnt = __popc(kb);
+                    done = 1;
+                }
+                if ((kb >> lane) & 1u) {
+                    int pos = nk + __popc(kb & ((1u << lane) - 1u));
+                    int row = c0 + 32 * u + lane;
+                    a.keep[(size_t)b * a.keep_cap + pos] = row;  // its box is copied after the loop
+                }
+                if (lane == 0) {
+                    s_kb = kb;
+                    s_nkept = nk + cnt;
+                    if (done) s_done = 1;
+                }
+            }
+            TQ(tq_res);
+            __syncthreads();
+            TQ(tq_s2);
+            if (s_done) break;
+            {
+                // rows of the kept candidates ORed into the removed words of the later column words: eight
+                // threads per column word (one 16-byte quarter of its 32 rows each, selected without
+                // predicates), combined by three xor shuffles; 32 column words per pass
+                const uint32_t kb = s_kb;
+                const int part = t & 7;
+                const uint32_t k4 = kb >> (4 * part);
+                const uint32_t s0 = 0u - (k4 & 1u), s1 = 0u - ((k4 >> 1) & 1u), s2 = 0u - ((k4 >> 2) & 1u),
+                               s3 = 0u - ((k4 >> 3) & 1u);
+                for (int tw = u + 1 + (t >> 3); tw - (t >> 3) < nw; tw += NMS_MAX_WORDS / 8) {  // warp-uniform trip count
+                    uint32_t acc = 0u;
+                    if (tw < nw) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(stage + tw * 32 + part * 4);
+                        acc = (v.x & s0) | (v.y & s1) | (v.z & s2) | (v.w & s3);
+                    }
+                    acc |= __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+                    acc |= __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+                    acc |= __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
+                    if (part == 0 && tw < nw) R[tw] |= acc;
+                }
+            }
+            TQ(tq_or);
+            issue(u + NMS_RING_DEPTH);  // into the stage step u-1 used: its readers passed this step's barrier
+            TQ(tq_iss);
+        }
+#ifdef FRCNN_NMS_TIMING
+        if (t == 0 && b == 0)
+            printf("nms scan c0=%d nw=%d steps=%d total=%lld wait=%lld resolve=%lld sync2=%lld or=%lld issue=%lld fix=%lld kept=%d\n", c0,
+                   nw, tq_steps, clock64() - tq0, tq_wait, tq_res, tq_s2, tq_or, tq_iss, tq_fix, s_nkept);
+#endif
+        cp_async_wait<0>();
+        nms_copy_kept_boxes(a, b, boxes, st.n_kept, &s_nkept);
+        if (t == 0) {
+            int done = s_done || (c1 >= n);
+            a.state[b].n_kept = s_nkept;
+            a.state[b].done = done;
+            a.n_keep[b] = s_nkept;
+        }
+        return;
+    }
+    // ---- wide super-blocks (only on request): rows prefetched into registers one step ahead ----------
     const uint32_t* mine = mask + (size_t)t * a.S;  // rows of my column word
     uint4 m[8];
     auto prefetch = [&](int u) {
@@ -646,19 +797,7 @@ __device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const Nm
     for (int u = 0; u < nw; ++u) {
         if (warp == 0) {
             const uint32_t Dn = diag(u + 1);  // in flight during the resolve
-            uint32_t rw = R[u];
-            uint32_t kb = 0;
-            // gather the 32 diagonal words first (independent shuffles), then run the serial chain on
-            // registers only
-            uint32_t dd[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dd[i] = __shfl_sync(0xFFFFFFFFu, D, i);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const bool alive = !((rw >> i) & 1u);
-                kb |= alive ? (1u << i) : 0u;
-                rw |= alive ? dd[i] : 0u;
-            }
+            uint32_t kb = nms_resolve_word(~R[u], D, lane);
             D = Dn;
             int nk = s_nkept;
             int room = a.keep_cap - nk;
@@ -672,8 +811,7 @@ __device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const Nm
             if ((kb >> lane) & 1u) {
                 int pos = nk + __popc(kb & ((1u << lane) - 1u));
                 int row = c0 + 32 * u + lane;
-                a.keep[(size_t)b * a.keep_cap + pos] = row;
-                a.kept_box[(size_t)b * a.keep_cap + pos] = __ldg(boxes + row);
+                a.keep[(size_t)b * a.keep_cap + pos] = row;  // its box is copied after the loop
             }
             if (lane == 0) {
                 s_kb = kb;
@@ -698,6 +836,7 @@ __device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const Nm
         prefetch(u + 1);
         __syncthreads();
     }
+    nms_copy_kept_boxes(a, b, boxes, st.n_kept, &s_nkept);
     if (t == 0) {
         int done = s_done || (c1 >= n);
         a.state[b].n_kept = s_nkept;
@@ -713,6 +852,7 @@ __global__ void __launch_bounds__(NMS_MAX_WORDS) nms_block_kernel(NmsArgs a) {
     __shared__ float4 srow[NMS_KC];
     __shared__ float sarea[NMS_KC];
     __shared__ uint32_t R[NMS_MAX_WORDS];
+    __shared__ __align__(16) uint32_t ring[NMS_RING_STAGES * NMS_RING_WORDS * 32];  // 32 KB
     __shared__ int s_last;
     const int b = blockIdx.y;
     const NmsState st = a.state[b];
@@ -728,7 +868,7 @@ __global__ void __launch_bounds__(NMS_MAX_WORDS) nms_block_kernel(NmsArgs a) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    nms_scan_image(a, b, st, R);
+    nms_scan_image(a, b, st, R, ring);
 }
 
 // nets/rpn.py:65-69: pad with arange, truncate, gather
