@@ -63,6 +63,7 @@ class ClockSampler:
         self.index = index
         self.sm, self.bits, self.max_mhz = [], 0, None
         self._stop = threading.Event()
+        self._ready = threading.Event()  # first sample taken: the timed region may start
         self._t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
@@ -83,6 +84,7 @@ class ClockSampler:
             while not self._stop.is_set():
                 self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
                 self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self._ready.set()
                 self._stop.wait(0.002)
         except Exception:
             self._smi_loop()
@@ -99,6 +101,7 @@ class ClockSampler:
                     r = [c.strip() for c in out.stdout.strip().splitlines()[0].split(",")]
                     self.sm.append(float(r[0]))
                     self.max_mhz = float(r[1])
+                    self._ready.set()
                     for i, n in enumerate(names):
                         if r[2 + i].lower().startswith("active"):
                             self.bits |= self.REASONS[n]
@@ -109,7 +112,8 @@ class ClockSampler:
 
     def __enter__(self):
         self._t.start()
-        time.sleep(0.02)  # let the sampler open NVML before the timed region starts
+        self._ready.wait(timeout=5.0)  # NVML opened and sampling before the timed region starts
+        self.sm.clear()  # idle-clock samples taken while waiting do not belong to the region
         return self
 
     def __exit__(self, *a):

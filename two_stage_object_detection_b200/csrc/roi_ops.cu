@@ -529,21 +529,23 @@ __device__ __forceinline__ void build_max_tables(V* tab, const float* raw, int c
 
 }
 
-template <int P, int TAB_THREADS, int CS, int MINB, bool ARGMAX, int LV>
+template <int P, int TAB_THREADS, int CS, int MINB, bool ARGMAX, int LV, int BPT = 1>
 __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs a) {
     typedef typename VecT<CS>::type V;
     constexpr int BINS = P * P;
-    constexpr int RPI = TAB_THREADS / BINS;      // RoIs per iteration
+    constexpr int SLOTS = BINS / BPT;            // thread slots per RoI: BPT horizontally adjacent bins per thread
+    constexpr int RPI = TAB_THREADS / SLOTS;     // RoIs per iteration
     constexpr int NB = TAB_THREADS / P;          // RoIs per batch: two table entries per thread
     constexpr int ITERS = NB / RPI;
+    static_assert(BPT == 1 || (BPT == 2 && P % 2 == 0 && CS == 4 && LV == 2 && !ARGMAX), "bin pairs: 14x14 inference");
     constexpr int NT = LV * LV;                  // tables: (row level, column level), levels 1, 2 (, 4)
     // 5..8-long bins through four 2-windows: 7x7 bins only (a 14x14 grid needs a RoI > 56 pixels wide for
     // one, and the extra call site costs the 14x14 fast path registers)
     constexpr bool MID = LV == 2 && P == 7;
-    static_assert(RPI * BINS == TAB_THREADS && NB * P == TAB_THREADS && ITERS * RPI == NB, "thread mapping");
+    static_assert(RPI * SLOTS == TAB_THREADS && NB * P == TAB_THREADS && ITERS * RPI == NB, "thread mapping");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int2 s_th[2][NB][P], s_tw[2][NB][P];  // per RoI: row / column corner offsets + flags
+    __shared__ __align__(16) int2 s_th[2][NB][P], s_tw[2][NB][P];  // per RoI: row / column corner offsets + flags
     __shared__ int s_hraw[2][NB][P], s_wraw[2][NB][P];
     __shared__ size_t s_ob[2][NB];                   // per RoI: byte offset of its [CS,P,P] output block
     V* tab = reinterpret_cast<V*>(smem_raw);
@@ -567,9 +569,11 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
     build_max_tables<V, LV, TAB_THREADS>(tab, raw, cs, H, W, WP, HWp, tid);
 
-    // compute role: bin e = (ph,pw) of the (tid / BINS)-th RoI of each iteration
-    const int e = tid % BINS, ej = tid / BINS;
-    const int ph = e / P, pw = e % P;
+    // compute role: bin e = (ph,pw) (and its right neighbour when BPT = 2) of the (tid / SLOTS)-th RoI of
+    // each iteration
+    const int slot = tid % SLOTS, ej = tid / SLOTS;
+    const int ph = slot / (P / BPT), pw = (slot % (P / BPT)) * BPT;
+    const int e = ph * P + pw;
     auto fill_tables = [&](int buf, int j, const RoiBox& q) {
         if (ti < P)
             s_th[buf][j][ti] = tab_entry<LV, MID>(ti, P, q.y1, q.y2, a.scale, H, WP, LV * HWp, sizeof(V),
@@ -649,13 +653,66 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
             if (full) vstore<true>(o, BINS, v, m, cs);
             else if (valid) vstore<false>(o, BINS, v, m, cs);
         };
+        // two horizontally adjacent bins (pw, pw+1) of RoI j, all four channels: one row entry, one 16-byte
+        // load for both column entries, one vote per decision, 8-byte stores (a 14x14 block is 784 bytes and
+        // even bins sit on 8-byte boundaries): ~20 % fewer instructions and a quarter fewer store wavefronts
+        // per output than two single bins
+        auto one_pair = [&](int j, bool full, bool valid) {
+          if constexpr (BPT == 2) {
+            const int2 h = s_th[cur][j][ph];
+            const int4 w = *reinterpret_cast<const int4*>(&s_tw[cur][j][pw]);  // (x0, y0 | flags, x1, y1 | flags)
+            const int hy = h.y & TAB_OFF_MASK, wy0 = w.y & TAB_OFF_MASK, wy1 = w.w & TAB_OFF_MASK;
+            const bool tall = h.x != hy, wide0 = w.x != wy0, wide1 = w.z != wy1;
+            const bool any_wide = __any_sync(0xFFFFFFFFu, wide0 || wide1), any_tall = __any_sync(0xFFFFFFFFu, tall);
+            float4 v0 = *reinterpret_cast<const float4*>(smem_raw + (w.x + h.x));
+            float4 v1 = *reinterpret_cast<const float4*>(smem_raw + (w.z + h.x));
+            if (any_wide) {
+                if (wide0) v0 = vmax(v0, *reinterpret_cast<const float4*>(smem_raw + (wy0 + h.x)));
+                if (wide1) v1 = vmax(v1, *reinterpret_cast<const float4*>(smem_raw + (wy1 + h.x)));
+            }
+            if (any_tall) {
+                if (tall) {
+                    v0 = vmax(v0, *reinterpret_cast<const float4*>(smem_raw + (w.x + hy)));
+                    v1 = vmax(v1, *reinterpret_cast<const float4*>(smem_raw + (w.z + hy)));
+                }
+                if (any_wide) {
+                    if (wide0 && tall) v0 = vmax(v0, *reinterpret_cast<const float4*>(smem_raw + (wy0 + hy)));
+                    if (wide1 && tall) v1 = vmax(v1, *reinterpret_cast<const float4*>(smem_raw + (wy1 + hy)));
+                }
+            }
+            const bool big0 = ((h.y | w.y) & TAB_BIG_BIT) != 0, big1 = ((h.y | w.w) & TAB_BIG_BIT) != 0;
+            if (__any_sync(0xFFFFFFFFu, big0 || big1)) {
+                if (big0) v0 = tab_big_bin<float4>(tab, s_hraw[cur][j][ph], s_wraw[cur][j][pw], WP);
+                if (big1) v1 = tab_big_bin<float4>(tab, s_hraw[cur][j][ph], s_wraw[cur][j][pw + 1], WP);
+            }
+            const unsigned m0 = (unsigned)((h.y & w.y) >> 31), m1 = (unsigned)((h.y & w.w) >> 31);
+            float2* o = reinterpret_cast<float2*>(
+                reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.out) + s_ob[cur][j]) + e);
+            auto put = [&](int c, float x0, float x1) {
+                o[c * (BINS / 2)] = make_float2(__uint_as_float(__float_as_uint(x0) & m0),
+                                                __uint_as_float(__float_as_uint(x1) & m1));
+            };
+            if (full || valid) {
+                put(0, v0.x, v1.x);
+                if (full || cs > 1) put(1, v0.y, v1.y);
+                if (full || cs > 2) put(2, v0.z, v1.z);
+                if (full || cs > 3) put(3, v0.w, v1.w);
+            }
+          }
+        };
         if (nb == NB && cs == CS) {
+            if constexpr (BPT == 2) {
+#pragma unroll 1
+                for (int it = 0; it < ITERS; ++it) one_pair(it * RPI + ej, true, true);
+            } else {
 #pragma unroll
-            for (int it = 0; it < ITERS; ++it) one_bin(it * RPI + ej, true, true);
+                for (int it = 0; it < ITERS; ++it) one_bin(it * RPI + ej, true, true);
+            }
         } else {
             for (int it = 0; it * RPI < nb; ++it) {
                 const int j = it * RPI + ej;
-                one_bin(j < nb ? j : 0, false, j < nb);
+                if (BPT == 2) one_pair(j < nb ? j : 0, false, j < nb);
+                else one_bin(j < nb ? j : 0, false, j < nb);
             }
         }
     }
@@ -1577,8 +1634,14 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             else if (smem4 <= 200 * 1024) tcs = 4, minb = 1;
             else if (smem2 <= 200 * 1024) tcs = 2, minb = 1;
             a.pitch = pitch_for(tcs ? tcs : 4);
+            static const int pairs = getenv("FRCNN_POOL14_PAIRS") ? atoi(getenv("FRCNN_POOL14_PAIRS")) : 1;
             if (tcs == 4 && minb == 2) {
                 if (PH == 7) FRCNN_TAB(7, 392, 4, 2, false, 2);
+                if (pairs) {
+                    set_groups(4, 392);
+                    return launch_tab(roi_pool_tab_kernel<14, 392, 4, 2, false, 2, 2>, a, table_bytes(2, 4, a.pitch), 392,
+                                      stream);
+                }
                 FRCNN_TAB(14, 392, 4, 2, false, 2);
             } else if (tcs == 2 && minb == 2) {
                 if (PH == 7) FRCNN_TAB(7, 392, 2, 2, false, 2);
