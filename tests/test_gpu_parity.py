@@ -616,7 +616,8 @@ def test_empty_inputs(F):
 def test_roi_pool_channel_tail_and_big_bins(F, O):
     """C not a multiple of the 4-channel slab, RoIs with bins longer than 4 (loop path), RoIs reaching
     past the map (empty bins), on maps that select the float4 / float2 / one-CTA-per-SM variants."""
-    for (B, Cc, H, W, P) in [(2, 7, 38, 38, 7), (1, 6, 64, 64, 14), (1, 5, 80, 76, 7), (1, 3, 120, 90, 7)]:
+    for (B, Cc, H, W, P) in [(2, 7, 38, 38, 7), (1, 6, 64, 64, 14), (1, 5, 80, 76, 7), (1, 3, 120, 90, 7),
+                             (2, 7, 38, 38, 14), (1, 5, 23, 60, 14), (1, 9, 60, 23, 14)]:  # bin-pair kernel: tail, long bins
         rng = np.random.default_rng(H * 7 + Cc)
         feat = rng.standard_normal((B, Cc, H, W)).astype(np.float32)
         K = 90
