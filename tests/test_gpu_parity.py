@@ -693,6 +693,98 @@ def test_step_is_cuda_graph_capturable(F):
         assert torch.equal(g_rois, e_rois) and torch.equal(g_pool, e_pool)
 
 
+def test_training_and_head_kernels_are_graph_capturable(F):
+    """The training-step and after-the-head kernels (anchor / proposal targets, RoIPool with argmax, the fused
+    gather + mean kernels, post-head decode, per-class NMS) also capture into one graph and replay
+    bit-identically: no host synchronisation, no allocation outside torch's allocator, all per-call state
+    (counters, column maxima) re-initialised on the stream."""
+    B, C, H, W, R, NC = 2, 8, 38, 38, 64, 5
+    base = F.base_anchors(device=DEV)
+    feat = torch.zeros(B, C, H, W, device=DEV)
+    rois = torch.zeros(B, R, 4, device=DEV)
+    gt = torch.zeros(B, 6, 4, device=DEV)
+    gl = torch.zeros(B, 6, dtype=torch.int64, device=DEV)
+    n_gt = torch.tensor([6, 4], dtype=torch.int32, device=DEV)
+    cls_loc = torch.zeros(B, R, NC * 4, device=DEV)
+    score = torch.zeros(B, R, NC, device=DEV)
+    idx = torch.arange(B, dtype=torch.int32, device=DEV)
+
+    def step():
+        loc, label = F.anchor_targets(gt, n_gt, base=base, feat_stride=16, feat_hw=(H, W))
+        sample, gloc, glab, n_out, st = F.proposal_targets(rois, gt, gl, n_gt, n_sample=32)
+        r5 = F.roi_head_coords(sample, idx, (600, 600), (H, W))
+        pool, am = F.roi_pool_forward(feat, r5, 7, 1.0, with_argmax=True, rois_per_image=32)
+        pm = F.roi_pool_mean(feat, r5, 7, 1.0, rois_per_image=32)
+        amn = F.roi_align_mean(feat, r5, 7, 1.0, 2, False, rois_per_image=32)
+        boxes, cs, ci = F.detection_decode(rois, cls_loc, score)
+        keep, nk = F.nms_by_class(boxes, cs, ci, 0.5)
+        return [loc, label, sample, gloc, glab, n_out, pool, am, pm, amn, boxes, cs, ci, keep, nk]
+
+    def fill(seed):
+        gg = torch.Generator().manual_seed(seed)
+        feat.copy_(torch.randn(B, C, H, W, generator=gg))
+        c = torch.rand(B, R, 2, generator=gg) * 600
+        wh = torch.rand(B, R, 2, generator=gg) * 200 + 16
+        rois.copy_(torch.cat([c - wh / 2, c + wh / 2], -1).clamp(0, 600))
+        c = torch.rand(B, 6, 2, generator=gg) * 600
+        wh = torch.rand(B, 6, 2, generator=gg) * 200 + 50
+        gt.copy_(torch.cat([c - wh / 2, c + wh / 2], -1).clamp(0, 600))
+        gl.copy_(torch.randint(0, 20, (B, 6), generator=gg))
+        cls_loc.copy_(torch.randn(B, R, NC * 4, generator=gg) * 0.2)
+        score.copy_(torch.round(torch.randn(B, R, NC, generator=gg) * 4) / 4)
+
+    fill(1)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_out = step()
+    for seed in (2, 3):
+        fill(seed)
+        graph.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(g_out, step()):
+            assert torch.equal(a, b, ) or (a.dtype.is_floating_point and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b)))
+
+
+def test_outputs_stay_inside_their_buffers(F):
+    """compute-sanitizer is closed on this pool: the kernels that take a caller-provided output are run into
+    buffers with NaN-patterned guard bands on both sides (odd sizes, channel tails, partial RoI batches)."""
+    rng = np.random.default_rng(8)
+    guard = 4096
+
+    def guarded(shape):
+        n = int(np.prod(shape))
+        buf = torch.full((n + 2 * guard,), float("nan"), device=DEV)
+        return buf, buf[guard:guard + n].view(*shape)
+
+    for (B, Cc, H, W, P, K) in [(2, 7, 38, 38, 14, 61), (1, 5, 38, 38, 7, 33), (2, 3, 64, 64, 7, 150), (1, 9, 50, 50, 7, 29)]:
+        feat = T(rng.standard_normal((B, Cc, H, W)).astype(np.float32))
+        c = rng.uniform(-4, W + 4, (K, 2))
+        wh = rng.uniform(0.5, W * 0.9, (K, 2))
+        r5 = T(np.concatenate([rng.integers(0, B, (K, 1)), c - wh / 2, c + wh / 2], 1).astype(np.float32))
+        for op in ("pool", "align"):
+            buf, out = guarded((K, Cc, P, P))
+            if op == "pool":
+                F.roi_pool_forward(feat, r5, P, 1.0, out=out)
+            else:
+                F.roi_align_forward(feat, r5, P, 1.0, 2, False, out=out)
+            torch.cuda.synchronize()
+            assert torch.isnan(buf[:guard]).all() and torch.isnan(buf[-guard:]).all(), (op, H, P)
+            assert not torch.isnan(out).any()
+    a = T(rng.uniform(0, 100, (1001, 4)).astype(np.float32))
+    for nb in (3, 8, 1100):
+        bq = T(rng.uniform(0, 100, (nb, 4)).astype(np.float32))
+        buf, out = guarded((1001, nb))
+        F.bbox_iou(a, bq, out=out)
+        torch.cuda.synchronize()
+        assert torch.isnan(buf[:guard]).all() and torch.isnan(buf[-guard:]).all() and not torch.isnan(out).any()
+
+
 def test_trainer_matches_reference_losses(F):
     """FasterRCNNTrainer.forward vs the reference trainer (golden: two batch-of-one runs on seeded features,
     weights and GT).  Batched here: both images in one call must give the mean of the two reference runs."""
