@@ -370,6 +370,8 @@ def run_ours(args):
     while c0 < rows:
         n_sb, c0, ln = n_sb + 1, c0 + ln, min(2 * ln, smax)
     launches = 1 + 1 + n_sb + 1 + 1 + 1  # decode, topk, nms block kernel per super-block, finalize, coords, gather
+    if train:
+        launches += 3  # anchor_iou, anchor_label, proposal_target
     # <P, threads, channels per CTA, CTAs per SM, argmax, table levels> as csrc/roi_ops.cu picks them
     kernel_name = "roi_pool_tab_kernel<14,392,4,2,false,2>" if (cfg["op"], P) == ("pool", 14) else (
         ("roi_pool_tab_kernel<7,392,4,2,true,1>" if train else

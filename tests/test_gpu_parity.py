@@ -900,5 +900,13 @@ def test_nms_by_class_batched_ragged_vs_oracle(F, O):
         n = int(n_valid[b])
         ref = O.nms_by_class(boxes[b, :n], scores[b, :n], cls[b, :n], 0.5)
         assert int(nk[b]) == len(ref) and np.array_equal(N(keep[b, :len(ref)]).astype(np.int64), ref), b
-    with pytest.raises(RuntimeError):
-        F.nms_by_class(torch.zeros(1, 1025, 4, device=DEV), torch.zeros(1, 1025, device=DEV), None, 0.5)
+    # more rows per image than the one-CTA kernel takes: the wrapper loops frcnn_nms over (image, class)
+    R2 = 1500
+    c = rng.uniform(0, 300, (1, R2, 2)).astype(np.float32)
+    wh = rng.uniform(10, 90, (1, R2, 2)).astype(np.float32)
+    b2 = np.concatenate([c - wh / 2, c + wh / 2], -1).astype(np.float32)
+    s2 = (np.round(rng.uniform(0, 1, (1, R2)) * 200) / 200).astype(np.float32)
+    c2 = rng.integers(0, 3, (1, R2))
+    keep, nk = F.nms_by_class(T(b2), T(s2), T(c2), 0.5)
+    ref = O.nms_by_class(b2[0], s2[0], c2[0], 0.5)
+    assert int(nk[0]) == len(ref) and np.array_equal(N(keep[0, :len(ref)]).astype(np.int64), ref)

@@ -556,6 +556,23 @@ def nms_by_class(boxes: torch.Tensor, scores: torch.Tensor, classes: Optional[to
     keep = torch.empty((B, R), dtype=torch.int32, device=dev)
     n_keep = torch.empty((B,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        check(lib.frcnn_nms_by_class(b.data_ptr(), s.data_ptr(), ptr(cl), ptr(nv), B, R, float(iou_threshold),
-                                     keep.data_ptr(), n_keep.data_ptr(), _lib.stream_ptr(dev)), "frcnn_nms_by_class")
+        rc = lib.frcnn_nms_by_class(b.data_ptr(), s.data_ptr(), ptr(cl), ptr(nv), B, R, float(iou_threshold),
+                                    keep.data_ptr(), n_keep.data_ptr(), _lib.stream_ptr(dev))
+    if rc != _lib.ERR_UNSUPPORTED:
+        check(rc, "frcnn_nms_by_class")
+        return keep, n_keep
+    # more than 1024 rows per image: the evaluator's own loop (one frcnn_nms per image and class; synchronises)
+    keep.fill_(-1)
+    for i in range(B):
+        n = R if nv is None else int(nv[i])
+        ci = torch.zeros(n, dtype=torch.int64, device=dev) if cl is None else cl[i, :n]
+        parts = [idx[nms(b[i, idx], s[i, idx], iou_threshold)] for idx in
+                 (torch.nonzero(ci == c).flatten() for c in torch.unique(ci).tolist())]
+        kept = torch.cat(parts) if parts else torch.zeros(0, dtype=torch.int64, device=dev)
+        # merge the per-class lists into (score desc, index asc) order: stable sort of the kept rows by
+        # index, then by descending score
+        kept = kept.sort().values
+        kept = kept[torch.sort(s[i, kept], descending=True, stable=True).indices]
+        keep[i, :kept.numel()] = kept.to(torch.int32)
+        n_keep[i] = kept.numel()
     return keep, n_keep
