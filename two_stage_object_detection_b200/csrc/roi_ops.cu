@@ -1283,16 +1283,41 @@ __global__ void __launch_bounds__(AM_THREADS, 2) roi_align_mean_kernel(RoiArgs a
     }
     __syncthreads();
     const float norm = (float)(a.PH * a.PW) * (float)(a.sampling_ratio * a.sampling_ratio);
-    for (int r = r_begin + blockIdx.x * NW + warp; r < r_end; r += a.groups * NW) {
-        const int k = roi_at(a, r);
-        const AlignWeights* w = rec + k;
-        const int4 hdr = __ldg(reinterpret_cast<const int4*>(w));
-        const int x0 = hdr.x, nx = hdr.y, y0 = hdr.z, ny = hdr.w;
+    // a RoI's record (header + 2 x 64 weights) is fetched one RoI ahead: its L2 round trip hides behind the
+    // window loop of the current one
+    struct Rec {
+        int k;
+        int4 hdr;
+        float wx0, wx1, wy0, wy1;
+    };
+    auto fetch = [&](int r) {
+        Rec q;
+        q.k = -1;
+        q.hdr = make_int4(0, 0, 0, 0);
+        q.wx0 = q.wx1 = q.wy0 = q.wy1 = 0.f;
+        if (r < r_end) {
+            q.k = roi_at(a, r);
+            const AlignWeights* w = rec + q.k;
+            q.hdr = __ldg(reinterpret_cast<const int4*>(w));
+            q.wx0 = __ldg(w->wx + lane);
+            q.wx1 = __ldg(w->wx + lane + 32);
+            q.wy0 = __ldg(w->wy + lane);
+            q.wy1 = __ldg(w->wy + lane + 32);
+        }
+        return q;
+    };
+    const int rstep = a.groups * NW;
+    Rec nxt = fetch(r_begin + blockIdx.x * NW + warp);
+    for (int r = r_begin + blockIdx.x * NW + warp; r < r_end; r += rstep) {
+        const Rec cur = nxt;
+        nxt = fetch(r + rstep);
+        const int k = cur.k;
+        const int x0 = cur.hdr.x, nx = cur.hdr.y, y0 = cur.hdr.z, ny = cur.hdr.w;
         __syncwarp();  // previous RoI's weights no longer read
-        s_w[warp][0][lane] = __ldg(w->wx + lane);
-        s_w[warp][0][lane + 32] = __ldg(w->wx + lane + 32);
-        s_w[warp][1][lane] = __ldg(w->wy + lane);
-        s_w[warp][1][lane + 32] = __ldg(w->wy + lane + 32);
+        s_w[warp][0][lane] = cur.wx0;
+        s_w[warp][0][lane + 32] = cur.wx1;
+        s_w[warp][1][lane] = cur.wy0;
+        s_w[warp][1][lane + 32] = cur.wy1;
         __syncwarp();
         // lanes tile the window TY x TX with TX the smallest of 8 / 16 / 32 that covers its width
         const int sh = nx <= 8 ? 3 : (nx <= 16 ? 4 : 5);
@@ -1307,10 +1332,10 @@ __global__ void __launch_bounds__(AM_THREADS, 2) roi_align_mean_kernel(RoiArgs a
                 const int xx = xb + lx;
                 const float wgt = xx < nx ? wy * s_w[warp][0][xx] : 0.f;
                 const float4 v = row[min(xx, nx - 1)];
-                acc.x += wgt * v.x;
-                acc.y += wgt * v.y;
-                acc.z += wgt * v.z;
-                acc.w += wgt * v.w;
+                acc.x = __fmaf_rn(wgt, v.x, acc.x);  // explicit FMA (the library is built with -fmad=false):
+                acc.y = __fmaf_rn(wgt, v.y, acc.y);  // this kernel's contract is 1e-5, not the reference's
+                acc.z = __fmaf_rn(wgt, v.z, acc.z);  // operation order
+                acc.w = __fmaf_rn(wgt, v.w, acc.w);
             }
         }
 #pragma unroll
