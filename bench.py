@@ -455,6 +455,7 @@ def cpu_step(cfg, O, loc, logits, feat, images):
 
 def cpu_baseline(cfg, images=2, reps=1):
     from oracle import ref_port as O
+    O.set_threads(len(os.sched_getaffinity(0)))
     loc, logits, feat = (t.numpy() for t in make_inputs(cfg, 7))
     images = min(images, cfg["batch"])
     cpu_step(cfg, O, loc, logits, feat, 2)  # warm-up (builds / loads the C library)
@@ -472,6 +473,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import ref_port as O
+    O.set_threads(len(os.sched_getaffinity(0)))  # torchrun exports OMP_NUM_THREADS=1: take the host's cores back
     cfg = WORKLOADS[args.workload]
     images = cfg["batch"]  # one full batch per step: OpenMP spreads images / RoIs over every host core
     loc, logits, feat = (t.numpy() for t in make_inputs(cfg, 7))

@@ -77,6 +77,8 @@ def lib():
             L.oracle_roi_align.argtypes = [f32p, i64, i64, i64, i64, f32p, i64, i64, i64,
                                            ctypes.c_float, ctypes.c_int, ctypes.c_int, f32p]
             L.oracle_max_threads.restype = ctypes.c_int
+            L.oracle_set_threads.restype = None
+            L.oracle_set_threads.argtypes = [ctypes.c_int]
             _lib = L
     return _lib
 
@@ -91,6 +93,13 @@ def _p(a, ct):
 
 def max_threads() -> int:
     return int(lib().oracle_max_threads())
+
+
+def set_threads(n: int) -> int:
+    """OpenMP threads of the C oracle (bench.py's CPU arm: all host cores, whatever OMP_NUM_THREADS a
+    launcher exported).  Returns the count now in effect."""
+    lib().oracle_set_threads(int(n))
+    return max_threads()
 
 
 # --------------------------------------------------------------------------------------------
