@@ -11,7 +11,6 @@
 
 #include <algorithm>
 
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -376,14 +375,14 @@ __device__ __forceinline__ int2 tab_entry(int i, int P, float c1, float c2, floa
     const int len = hi - lo;
     *raw = lo | (hi << 16);
     const bool empty = len <= 0;
-    // window level: the longest of 1, 2 (, 4) that fits; two such windows placed at both ends cover the run
-    const int lvl = (LV == 3 && len >= 4) ? 2 : ((LV >= 2 && len >= 2) ? 1 : 0);
+    // window level: 2 when the run is at least 2 long; two such windows placed at both ends cover up to 4
+    const int lvl = (LV >= 2 && len >= 2) ? 1 : 0;
     const int a = 1 << lvl;
     const int lo_ = empty ? 0 : lo, hi_ = empty ? a : hi;
     int2 r;
     r.x = (lvl * tsel + lo_ * unit) * esz;
     r.y = ((lvl * tsel + (hi_ - a) * unit) * esz) | (empty ? 0 : TAB_NE_BIT) |
-          (len > (LV == 1 ? 1 : ((LV == 3 || MID) ? 8 : 4)) ? TAB_BIG_BIT : 0) |
+          (len > (LV == 1 ? 1 : (MID ? 8 : 4)) ? TAB_BIG_BIT : 0) |
           ((MID && len > 4 && len <= 8) ? TAB_MID_BIT : 0);
     return r;
 }
@@ -487,12 +486,6 @@ __device__ __forceinline__ void build_max_tables(V* tab, const float* raw, int c
             }
         }
     };
-    auto level_up = [&](int dst, int src, int dy, int dx) {  // dst = max(src, src shifted by (dy,dx))
-        for_pixels([&](int, int y, int x, int q) {
-            const int qs = (y + dy < H ? q + dy * WP : q) + (x + dx < W ? dx : 0);
-            tab[dst * HWp + q] = vmax(tab[src * HWp + q], tab[src * HWp + qs]);
-        });
-    };
     for_pixels([&](int p, int, int, int q) {
         V v;
         vgather(v, raw, HW, p, cs);
@@ -513,20 +506,7 @@ __device__ __forceinline__ void build_max_tables(V* tab, const float* raw, int c
             const int qd = y + 1 < H ? q + WP : q;
             tab[3 * HWp + q] = vmax(tab[HWp + q], tab[HWp + qd]);  // 2 x 2
         });
-    } else {
-        level_up(1, 0, 0, 1);  // 1 x 2
-        level_up(3, 0, 1, 0);  // 2 x 1
-        __syncthreads();
-        level_up(2, 1, 0, 2);  // 1 x 4
-        level_up(6, 3, 2, 0);  // 4 x 1
-        level_up(4, 1, 1, 0);  // 2 x 2
-        __syncthreads();
-        level_up(5, 2, 1, 0);  // 2 x 4
-        level_up(7, 6, 0, 1);  // 4 x 2
-        __syncthreads();
-        level_up(8, 7, 0, 2);  // 4 x 4 (overwrites the staged planes, no longer needed)
     }
-
 }
 
 template <int P, int TAB_THREADS, int CS, int MINB, bool ARGMAX, int LV, int BPT = 1>
@@ -538,7 +518,8 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     constexpr int NB = TAB_THREADS / P;          // RoIs per batch: two table entries per thread
     constexpr int ITERS = NB / RPI;
     static_assert(BPT == 1 || (BPT == 2 && P % 2 == 0 && CS == 4 && LV == 2 && !ARGMAX), "bin pairs: 14x14 inference");
-    constexpr int NT = LV * LV;                  // tables: (row level, column level), levels 1, 2 (, 4)
+    constexpr int NT = LV * LV;                  // tables: (row level, column level), levels 1 (, 2)
+    static_assert(LV == 1 || LV == 2, "table levels");
     // 5..8-long bins through four 2-windows: 7x7 bins only (a 14x14 grid needs a RoI > 56 pixels wide for
     // one, and the extra call site costs the 14x14 fast path registers)
     constexpr bool MID = LV == 2 && P == 7;
@@ -1587,9 +1568,10 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
         return launch_staged(roi_align_staged_kernel, a, smem, stream);
     }
     // RoIPool 7x7 / 14x14: thread-per-bin kernel over shared-memory max tables (roi_pool_tab_kernel).
-    //   LV = 2 (windows 1,2: bins up to 4 long)  inference, 14x14 and 7x7 with small RoIs
-    //   LV = 3 (windows 1,2,4: bins up to 8)     inference 7x7 with many RoIs per image
-    //   LV = 1 (pixels only, every bin scanned)  training (value + argmax in one scan), few RoIs per image
+    //   LV = 2 (windows 1,2: bins up to 4 long; 5..8 through four 2-windows on the 7x7 grid)  inference
+    //   LV = 1 (pixels only, every bin scanned)  training: value + argmax in one scan
+    // (a three-level form -- windows 1,2,4, nine tables -- was measured and dropped: it only fits with one or
+    //  two channels per CTA, and the per-bin instruction overhead is paid per channel group)
     if (PH == PW && (PH == 7 || PH == 14)) {
         const int per_image_rois = cdiv(K, B);
         const size_t budget2 = 92 * 1024, budget1 = 180 * 1024;  // dynamic part for 2 / 1 CTAs per SM
@@ -1610,7 +1592,6 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
         return launch_tab(roi_pool_tab_kernel<PP_, TH_, CS_, MB_, AM_, LV_>, a, table_bytes(LV_, CS_, a.pitch), \
                           TH_, stream);                                                                     \
     } while (0)
-        static const int mode7 = getenv("FRCNN_POOL7_MODE") ? atoi(getenv("FRCNN_POOL7_MODE")) : 0;
         // rows whose byte length is a multiple of 64 would put vertically adjacent bins on the same banks
         // (64-wide maps: 45 % of the shared-memory wavefronts were conflicts): pad the pitch by one pixel
         auto pitch_for = [&](int tcs) { return (W * 4 * tcs) % 64 == 0 ? W + 1 : W; };
@@ -1645,11 +1626,6 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
                 if (PH == 7) FRCNN_TAB(7, 392, 1, 2, true, 1);
                 FRCNN_TAB(14, 392, 1, 2, true, 1);
             }
-        } else if (PH == 7 && (mode7 == 1 || mode7 == 3)) {
-            a.pitch = W | 1;
-            if (mode7 == 3 && table_bytes(1, 4, a.pitch) <= budget1) FRCNN_TAB(7, 392, 4, 2, false, 1);
-            if (table_bytes(3, 1, a.pitch) <= budget2 - 8 * 1024) FRCNN_TAB(7, 392, 1, 2, false, 3);
-            if (table_bytes(3, 1, a.pitch) <= budget1) FRCNN_TAB(7, 784, 1, 1, false, 3);
         }
         if (!argmax) {
             const size_t smem4 = table_bytes(2, 4, pitch_for(4)), smem2 = table_bytes(2, 2, pitch_for(2));
@@ -1659,15 +1635,11 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             else if (smem4 <= 200 * 1024) tcs = 4, minb = 1;
             else if (smem2 <= 200 * 1024) tcs = 2, minb = 1;
             a.pitch = pitch_for(tcs ? tcs : 4);
-            static const int pairs = getenv("FRCNN_POOL14_PAIRS") ? atoi(getenv("FRCNN_POOL14_PAIRS")) : 1;
             if (tcs == 4 && minb == 2) {
                 if (PH == 7) FRCNN_TAB(7, 392, 4, 2, false, 2);
-                if (pairs) {
-                    set_groups(4, 392);
-                    return launch_tab(roi_pool_tab_kernel<14, 392, 4, 2, false, 2, 2>, a, table_bytes(2, 4, a.pitch), 392,
-                                      stream);
-                }
-                FRCNN_TAB(14, 392, 4, 2, false, 2);
+                set_groups(4, 392);  // 14x14: two adjacent bins per thread
+                return launch_tab(roi_pool_tab_kernel<14, 392, 4, 2, false, 2, 2>, a, table_bytes(2, 4, a.pitch), 392,
+                                  stream);
             } else if (tcs == 2 && minb == 2) {
                 if (PH == 7) FRCNN_TAB(7, 392, 2, 2, false, 2);
                 FRCNN_TAB(14, 392, 2, 2, false, 2);
@@ -1676,7 +1648,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
                 FRCNN_TAB(14, 392, 4, 1, false, 2);
             } else if (tcs == 2) {
                 // one CTA per SM: twice the threads to keep the SM's latency hidden
-                if (PH == 7 && smem2 + 40 * 1024 <= 220 * 1024 && mode7 != 4) FRCNN_TAB(7, 784, 2, 1, false, 2);
+                if (PH == 7 && smem2 + 40 * 1024 <= 220 * 1024) FRCNN_TAB(7, 784, 2, 1, false, 2);
                 if (PH == 7) FRCNN_TAB(7, 392, 2, 1, false, 2);
                 FRCNN_TAB(14, 392, 2, 1, false, 2);
             }
