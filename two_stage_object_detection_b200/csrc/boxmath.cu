@@ -149,38 +149,57 @@ bbox_iou_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int6
 }
 
 // Fast path for Nb % 4 == 0 (and a 16-byte aligned output): a thread's four elements never cross a row,
-// so there is no per-element range or wrap test and the row index comes from one multiply-high.
-template <bool STAGED>
+// so there is no per-element range or wrap test and the row index comes from one multiply-high.  With
+// Nb % 8 == 0 (QUADS = 2) a thread takes two quads of one row (half a row apart): one index division and one a-box
+// load per eight outputs.  b boxes and their areas are staged once per CTA.
+template <bool STAGED, int QUADS>
 __global__ void __launch_bounds__(IOU_THREADS)
-bbox_iou_rows4_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int nb, FastDiv by_quads_per_row,
-                      int64_t quads, float* __restrict__ out) {
+bbox_iou_rows4_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int nb, FastDiv by_items_per_row,
+                      int64_t items, float* __restrict__ out) {
     __shared__ float4 sb[STAGED ? IOU_STAGE : 1];
-    const int qpr = by_quads_per_row.d;
+    __shared__ float sba[STAGED ? IOU_STAGE : 1];
+    const int ipr = by_items_per_row.d;  // items (QUADS quads each) per row
+    const int qpr = ipr * QUADS;
     if (STAGED) {  // box j lives at (j % 4) * qpr + j / 4: lanes reading their k-th box hit consecutive float4s
-        for (int j = threadIdx.x; j < nb; j += IOU_THREADS) sb[(j & 3) * qpr + (j >> 2)] = __ldg(b + j);
+        for (int j = threadIdx.x; j < nb; j += IOU_THREADS) {
+            const float4 v = __ldg(b + j);
+            sb[(j & 3) * qpr + (j >> 2)] = v;
+            sba[(j & 3) * qpr + (j >> 2)] = box_area(v);
+        }
         __syncthreads();
     }
-    for (int64_t q = (int64_t)blockIdx.x * IOU_THREADS + threadIdx.x; q < quads; q += (int64_t)gridDim.x * IOU_THREADS) {
+    for (int64_t t = (int64_t)blockIdx.x * IOU_THREADS + threadIdx.x; t < items; t += (int64_t)gridDim.x * IOU_THREADS) {
         int64_t i;
-        int jq;
-        if (quads < (1ll << 31)) {
-            const int ii = fast_div((int)q, by_quads_per_row);
+        int ji;
+        if (items < (1ll << 31)) {
+            const int ii = fast_div((int)t, by_items_per_row);
             i = ii;
-            jq = (int)q - ii * qpr;
+            ji = (int)t - ii * ipr;
         } else {
-            i = q / qpr;
-            jq = (int)(q - i * qpr);
+            i = t / ipr;
+            ji = (int)(t - i * ipr);
         }
         const float4 av = __ldg(a + i);
         const float aa = box_area(av);
-        const float4* bp = STAGED ? sb + jq : b + 4 * jq;
-        float r[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float4 bv = STAGED ? bp[k * qpr] : __ldg(bp + k);
-            r[k] = iou_eps(av, aa, bv, box_area(bv));
+        for (int u = 0; u < QUADS; ++u) {
+            const int jq = ji + u * ipr;  // lanes stay on consecutive quads: conflict-free LDS, coalesced stores
+            float r[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float4 bv;
+                float ba;
+                if (STAGED) {
+                    bv = sb[k * qpr + jq];
+                    ba = sba[k * qpr + jq];
+                } else {
+                    bv = __ldg(b + 4 * jq + k);
+                    ba = box_area(bv);
+                }
+                r[k] = iou_eps(av, aa, bv, ba);
+            }
+            __stcs(reinterpret_cast<float4*>(out) + (i * qpr + jq), make_float4(r[0], r[1], r[2], r[3]));
         }
-        __stcs(reinterpret_cast<float4*>(out) + q, make_float4(r[0], r[1], r[2], r[3]));
     }
 }
 
@@ -271,9 +290,17 @@ int frcnn_bbox_iou(const float* a, const float* b, int64_t na, int64_t nb, float
     auto* b4 = (const float4*)b;
     cudaStream_t st = (cudaStream_t)stream;
     if (vec && nb % 4 == 0) {
-        const FastDiv fd = make_fastdiv((int)(nb / 4));
-        if (staged) bbox_iou_rows4_kernel<true><<<grid, IOU_THREADS, 0, st>>>(a4, b4, (int)nb, fd, quads, out);
-        else bbox_iou_rows4_kernel<false><<<grid, IOU_THREADS, 0, st>>>(a4, b4, (int)nb, fd, quads, out);
+        const int quads_per_item = nb % 8 == 0 ? 2 : 1;
+        const int64_t items = quads / quads_per_item;
+        const FastDiv fd = make_fastdiv((int)(nb / (4 * quads_per_item)));
+        const int g2 = (int)std::min<int64_t>((items + IOU_THREADS - 1) / IOU_THREADS, (int64_t)sm_count() * 16);
+        if (quads_per_item == 2) {
+            if (staged) bbox_iou_rows4_kernel<true, 2><<<g2, IOU_THREADS, 0, st>>>(a4, b4, (int)nb, fd, items, out);
+            else bbox_iou_rows4_kernel<false, 2><<<g2, IOU_THREADS, 0, st>>>(a4, b4, (int)nb, fd, items, out);
+        } else {
+            if (staged) bbox_iou_rows4_kernel<true, 1><<<g2, IOU_THREADS, 0, st>>>(a4, b4, (int)nb, fd, items, out);
+            else bbox_iou_rows4_kernel<false, 1><<<g2, IOU_THREADS, 0, st>>>(a4, b4, (int)nb, fd, items, out);
+        }
         FRCNN_LAUNCH_CHECK();
         return FRCNN_OK;
     }
