@@ -737,30 +737,35 @@ __device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const Nm
             __syncthreads();
             TQ(tq_s2);
             if (s_done) break;
+            // next stage first: it overwrites the stage step u-1 used (its readers passed this step's barriers),
+            // and its issue latency then overlaps the OR phase instead of following it
+            issue(u + NMS_RING_DEPTH);
+            TQ(tq_iss);
             {
-                // rows of the kept candidates ORed into the removed words of the later column words: eight
-                // threads per column word (one 16-byte quarter of its 32 rows each, selected without
-                // predicates), combined by three xor shuffles; 32 column words per pass
+                // rows of the kept candidates ORed into the removed words of the later column words: four
+                // threads per column word (two 16-byte quarters of its 32 rows each, selected without
+                // predicates), combined by two xor shuffles; 64 column words per pass = one pass
                 const uint32_t kb = s_kb;
-                const int part = t & 7;
-                const uint32_t k4 = kb >> (4 * part);
-                const uint32_t s0 = 0u - (k4 & 1u), s1 = 0u - ((k4 >> 1) & 1u), s2 = 0u - ((k4 >> 2) & 1u),
-                               s3 = 0u - ((k4 >> 3) & 1u);
-                for (int tw = u + 1 + (t >> 3); tw - (t >> 3) < nw; tw += NMS_MAX_WORDS / 8) {  // warp-uniform trip count
+                const int part = t & 3;
+                const uint32_t ka = kb >> (8 * part), kc = ka >> 4;
+                const uint32_t a0 = 0u - (ka & 1u), a1 = 0u - ((ka >> 1) & 1u), a2 = 0u - ((ka >> 2) & 1u),
+                               a3 = 0u - ((ka >> 3) & 1u);
+                const uint32_t c0_ = 0u - (kc & 1u), c1_ = 0u - ((kc >> 1) & 1u), c2_ = 0u - ((kc >> 2) & 1u),
+                               c3_ = 0u - ((kc >> 3) & 1u);
+                for (int tw = u + 1 + (t >> 2); tw - (t >> 2) < nw; tw += NMS_MAX_WORDS / 4) {  // warp-uniform trip count
                     uint32_t acc = 0u;
                     if (tw < nw) {
-                        const uint4 v = *reinterpret_cast<const uint4*>(stage + tw * 32 + part * 4);
-                        acc = (v.x & s0) | (v.y & s1) | (v.z & s2) | (v.w & s3);
+                        const uint4* m = reinterpret_cast<const uint4*>(stage + tw * 32 + part * 8);
+                        const uint4 v = m[0], w = m[1];
+                        acc = (v.x & a0) | (v.y & a1) | (v.z & a2) | (v.w & a3) | (w.x & c0_) | (w.y & c1_) | (w.z & c2_) |
+                              (w.w & c3_);
                     }
                     acc |= __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
                     acc |= __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
-                    acc |= __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
                     if (part == 0 && tw < nw) R[tw] |= acc;
                 }
             }
             TQ(tq_or);
-            issue(u + NMS_RING_DEPTH);  // into the stage step u-1 used: its readers passed this step's barrier
-            TQ(tq_iss);
         }
 #ifdef FRCNN_NMS_TIMING
         if (t == 0 && b == 0)
