@@ -61,6 +61,15 @@ def test_host_side_argument_checks_need_no_gpu():
     assert rc == -1
     rc = lib.frcnn_roi_pool_forward(None, 0, 1, 1, 1, None, 0, 0, 7, 7, 1.0, None, None, None, 0, None)
     assert rc == -1
+    # the entry points added for SURVEY 8f-3 / 8f-4 validate the same way
+    assert lib.frcnn_roi_pool_mean_forward(None, 0, 1, 1, 1, None, 0, 0, 7, 7, 1.0, None, None, 0, None) == -1
+    assert lib.frcnn_roi_align_mean_forward(None, 0, 1, 1, 1, None, 0, 0, 7, 7, 1.0, 2, 0, None, None, 0, None) == -1
+    assert lib.frcnn_roi_align_mean_workspace_bytes(4, 1200) >= 1200 * 528 and \
+        lib.frcnn_roi_align_mean_workspace_bytes(4, 1200) % 256 == 0
+    assert lib.frcnn_detection_decode(None, None, None, None, -1, 3, None, None, None, None, None) == -1
+    assert lib.frcnn_detection_decode(None, None, None, None, 0, 3, None, None, None, None, None) == 0  # nothing to do
+    assert lib.frcnn_nms_by_class(None, None, None, None, 1, 5, 0.5, None, None, None) == -1
+    assert lib.frcnn_nms_by_class(None, None, None, None, 0, 5, 0.5, None, None, None) == 0
 
 
 def test_no_cpu_fallback():
