@@ -693,6 +693,29 @@ def test_step_is_cuda_graph_capturable(F):
         assert torch.equal(g_rois, e_rois) and torch.equal(g_pool, e_pool)
 
 
+def test_fused_softmax_special_values(F, O):
+    """The fused 2-way softmax evaluates one exponential (the larger logit's term is exp(0)); it must keep
+    the reference's results for equal, infinite and NaN logits."""
+    H, W = 2, 3
+    Nn = H * W * 9
+    vals = [0.0, -0.0, 1.5, -2.0, 80.0, -80.0, np.inf, -np.inf, np.nan, 1e-30]
+    pairs = np.array([(a, b) for a in vals for b in vals], np.float32)
+    logits = np.zeros((1, Nn, 2), np.float32)
+    logits[0, :min(len(pairs), Nn)] = pairs[:Nn]
+    rng = np.random.default_rng(2)
+    logits[0, len(pairs):] = rng.standard_normal((Nn - min(len(pairs), Nn), 2)).astype(np.float32) if Nn > len(pairs) else 0
+    loc = np.zeros((1, Nn, 4), np.float32)
+    base = F.base_anchors(device=DEV)
+    _, _, fg = F.decode_clip_score(T(loc), T(logits), clip_x_max=100, clip_y_max=100, base=base, feat_stride=16,
+                                   feat_hw=(H, W), score_is_logits=True)
+    with np.errstate(all="ignore"):
+        ref = O.fg_scores(logits)
+    got = N(fg)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.allclose(got[ok], ref[ok], rtol=1e-6, atol=1e-7)
+
+
 def test_training_and_head_kernels_are_graph_capturable(F):
     """The training-step and after-the-head kernels (anchor / proposal targets, RoIPool with argmax, the fused
     gather + mean kernels, post-head decode, per-class NMS) also capture into one graph and replay

@@ -54,8 +54,13 @@ __global__ void __launch_bounds__(256) decode_clip_key_kernel(DecodeArgs a) {
         s = __ldg(a.score + t);
     } else {
         float2 lg = __ldg(reinterpret_cast<const float2*>(a.score) + t);
-        float m = fmaxf(lg.x, lg.y);
-        float e0 = expf(lg.x - m), e1 = expf(lg.y - m);
+        // softmax([l0, l1])[1] = e1 / (e0 + e1) with e = exp(l - max): the larger logit's term is exp(0) = 1
+        // exactly, so one expf is enough and the bits are those of the two-exponential form
+        // (1 + (big - big) keeps the NaN an infinite logit produces there)
+        const bool fg_larger = lg.y >= lg.x;
+        const float big = fg_larger ? lg.y : lg.x, small = fg_larger ? lg.x : lg.y;
+        const float eb = 1.f + (big - big), es = expf(small - big);
+        const float e0 = fg_larger ? es : eb, e1 = fg_larger ? eb : es;
         s = e1 / (e0 + e1);
     }
     r.x = clamp_torch(r.x, a.xmax);
