@@ -260,25 +260,35 @@ __global__ void __launch_bounds__(ROI_THREADS, 2) roi_pool_staged_kernel(RoiArgs
 }
 
 // ---------------------------------------------------------------------------------------------
-// RoIPool forward, table kernel (inference: no argmax).
+// RoIPool forward, table kernel: roi_pool_tab_kernel<P, threads, CS, MINB, ARGMAX, LV, BPT>.
 //
-// A bin's max over [hs,he) x [ws,we) is the max of four lookups into 2-D "sparse max tables":
+// LV = 2 (inference).  A bin's max over [hs,he) x [ws,we) is the max of four lookups into 2-D "sparse max
+// tables":
 //   T[a][b][y][x] = max of the a x b window anchored at (y,x),  a,b in {1,2}
 // because any window up to 4 x 4 is covered by the (at most) four a x b windows placed in its corners
-// (max is idempotent, overlaps do not matter).  The CTA builds the four tables once for its 4-channel
-// slab -- channel-interleaved, one float4 per pixel, so one LDS.128 serves four channels -- and then a
-// bin costs 1-4 LDS.128 + FMNMX instead of a data-dependent double loop.  Bins larger than 4 in either
-// direction take a loop path over T[1][1].  Values are first clamped with fmaxf(v, -FLT_MAX), which
-// reproduces the reference's `v > best` scan exactly (NaN / -inf never win); empty bins give 0.
+// (max is idempotent, overlaps do not matter).  The CTA builds the four tables once for its CS-channel
+// slab -- channel-interleaved, one float4 (CS = 4) / float2 / float per pixel, so one LDS.128 serves four
+// channels -- and then a bin costs 1-4 LDS.128 + FMNMX instead of a data-dependent double loop.  On the 7x7
+// grid bins 5..8 long take four 2-windows per axis (tab_mid_bin); longer ones a scan of T[1][1]
+// (tab_big_bin).  Values are first clamped with fmaxf(v, -FLT_MAX), which reproduces the reference's
+// `v > best` scan exactly (NaN / -inf never win); empty bins give 0.
 //
-// smem: 4 tables x HWp float4 (HW=38x38: 92 KB, two CTAs per SM).  The raw NCHW planes are TMA-staged
-// into the region that later holds T[2][2], the last table built.
+// LV = 1 (training, ARGMAX).  Only the interleaved pixels are kept; one scan per bin tracks the maximum and
+// the first position attaining it (the reference's order).  With the 128 sampled RoIs per image of a
+// training step the table build would cost more than it saves.
 //
-// Thread mapping: TAB_THREADS = 784 = 4 * 14*14 = 16 * 7*7.  A thread owns ONE output bin (ph,pw) for
-// good and walks the CTA's RoIs; consecutive threads are consecutive bins of the same RoI, so every
-// warp-level store is a contiguous 128-byte run of the [K,C,P,P] output (measured: the store pattern,
-// not the lookups, bounds this kernel).  Per-RoI bin geometry is precomputed for a batch of RoIs into
-// shared-memory tables (one entry per thread), and the next batch's RoI boxes are prefetched.
+// smem: LV*LV tables x HWp elements (38x38, float4, LV = 2: 92 KB, two CTAs per SM).  The raw NCHW planes
+// are TMA-staged into the region that later holds the last table built (LV = 1: a region of their own).
+// The row pitch is padded by one pixel when a row's byte length is a multiple of 64 (vertically adjacent
+// bins would share banks).
+//
+// Thread mapping: 392 threads = 2 * 14*14 = 8 * 7*7 (784 when only one CTA fits per SM).  A thread owns
+// ONE output bin (ph,pw) -- or, BPT = 2 on the 14x14 grid, two horizontally adjacent ones -- for good and
+// walks the CTA's RoIs; consecutive threads are consecutive bins of the same RoI, so every warp-level
+// store is a contiguous 128-byte (BPT = 2: 256-byte, 8 bytes per lane) run of the [K,C,P,P] output
+// (measured: the store pattern, not the lookups, bounded the first versions).  Per-RoI bin geometry is
+// precomputed for a batch of RoIs into double-buffered shared-memory tables (two entries per thread, one
+// barrier per batch), and the next batch's RoI boxes are prefetched.
 // ---------------------------------------------------------------------------------------------
 constexpr int TAB_NE_BIT = 0x80000000;   // entry .y bit 31: bin row / column is non-empty
 constexpr int TAB_BIG_BIT = 0x40000000;  // entry .y bit 30: longer than the tables cover -> loop path
