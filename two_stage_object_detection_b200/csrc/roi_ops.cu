@@ -519,7 +519,21 @@ __device__ __forceinline__ void build_max_tables(V* tab, const float* raw, int c
     }
 }
 
-template <int P, int TAB_THREADS, int CS, int MINB, bool ARGMAX, int LV, int BPT = 1>
+// Recovers [lo,hi) of a bin axis from its table entry (PIPE variant: the raw extents are not kept in shared
+// memory).  o1 / o2 = the two corner offsets in bytes, tsel / unit as given to tab_entry, esz = element size.
+__device__ __forceinline__ int tab_decode_range(int o1, int o2, int tsel, int unit, int esz) {
+    o1 /= esz;
+    o2 /= esz;
+    const int lvl = o1 >= tsel ? 1 : 0;
+    const int base = lvl ? tsel : 0;
+    const int lo = (o1 - base) / unit, hi = (o2 - base) / unit + (lvl ? 2 : 1);
+    return lo | (hi << 16);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int P, int TAB_THREADS, int CS, int MINB, bool ARGMAX, int LV, int BPT = 1, bool PIPE = false>
 __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs a) {
     typedef typename VecT<CS>::type V;
     constexpr int BINS = P * P;
@@ -528,6 +542,12 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     constexpr int NB = TAB_THREADS / P;          // RoIs per batch: two table entries per thread
     constexpr int ITERS = NB / RPI;
     static_assert(BPT == 1 || (BPT == 2 && P % 2 == 0 && CS == 4 && LV == 2 && !ARGMAX), "bin pairs: 14x14 inference");
+    static_assert(!PIPE || BPT == 2, "the pipelined geometry hand-off is implemented for the bin-pair variant");
+    // PIPE: three geometry buffers and one mbarrier per buffer instead of a CTA barrier per batch.  A thread
+    // waits for batch b's geometry, computes batch b+1's, then pools batch b: warps may drift one batch apart
+    // (measured upper bound of removing the per-batch barrier on the 14x14 configuration: ~10 %).
+    constexpr int NBUF = PIPE ? 3 : 2;
+    constexpr int NWARPS = (TAB_THREADS + 31) / 32;
     constexpr int NT = LV * LV;                  // tables: (row level, column level), levels 1 (, 2)
     static_assert(LV == 1 || LV == 2, "table levels");
     // 5..8-long bins through four 2-windows: 7x7 bins only (a 14x14 grid needs a RoI > 56 pixels wide for
@@ -536,9 +556,10 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     static_assert(RPI * SLOTS == TAB_THREADS && NB * P == TAB_THREADS && ITERS * RPI == NB, "thread mapping");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ __align__(16) int2 s_th[2][NB][P], s_tw[2][NB][P];  // per RoI: row / column corner offsets + flags
-    __shared__ int s_hraw[2][NB][P], s_wraw[2][NB][P];
-    __shared__ size_t s_ob[2][NB];                   // per RoI: byte offset of its [CS,P,P] output block
+    __shared__ __align__(16) int2 s_th[NBUF][NB][P], s_tw[NBUF][NB][P];  // per RoI: row / column corner offsets + flags
+    __shared__ int s_hraw[PIPE ? 1 : 2][PIPE ? 1 : NB][PIPE ? 1 : P], s_wraw[PIPE ? 1 : 2][PIPE ? 1 : NB][PIPE ? 1 : P];
+    __shared__ size_t s_ob[NBUF][NB];                // per RoI: byte offset of its [CS,P,P] output block
+    __shared__ __align__(8) uint64_t s_full[PIPE ? 3 : 1];  // PIPE: geometry of buffer i complete
     V* tab = reinterpret_cast<V*>(smem_raw);
     const int H = a.H, W = a.W, HW = H * W;
     const int WP = a.pitch, HWp = (H * WP + 3) & ~3;  // row pitch (odd when rows would alias banks), table stride
@@ -557,6 +578,9 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
 
     // staged planes [cs][HW]: where the last-built table will be (LV = 1: a region of their own)
     float* raw = reinterpret_cast<float*>(tab + (LV == 1 ? 1 : NT - 1) * HWp);
+    if (PIPE && tid == 0) {
+        for (int i = 0; i < 3; ++i) mbar_init(&s_full[i], NWARPS);  // one arrival per warp; visible after the
+    }                                                                // barriers inside stage_slab
     stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
     build_max_tables<V, LV, TAB_THREADS>(tab, raw, cs, H, W, WP, HWp, tid);
 
@@ -566,12 +590,14 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     const int ph = slot / (P / BPT), pw = (slot % (P / BPT)) * BPT;
     const int e = ph * P + pw;
     auto fill_tables = [&](int buf, int j, const RoiBox& q) {
+        int unused;
         if (ti < P)
             s_th[buf][j][ti] = tab_entry<LV, MID>(ti, P, q.y1, q.y2, a.scale, H, WP, LV * HWp, sizeof(V),
-                                                  &s_hraw[buf][j][ti]);
+                                                  PIPE ? &unused : &s_hraw[PIPE ? 0 : buf][PIPE ? 0 : j][PIPE ? 0 : ti]);
         else
             s_tw[buf][j][ti - P] = tab_entry<LV, MID>(ti - P, P, q.x1, q.x2, a.scale, W, 1, HWp, sizeof(V),
-                                                      &s_wraw[buf][j][ti - P]);
+                                                      PIPE ? &unused
+                                                           : &s_wraw[PIPE ? 0 : buf][PIPE ? 0 : j][PIPE ? 0 : ti - P]);
         if (ti == 0)
             s_ob[buf][j] = (((size_t)max(q.k, 0) * a.C + c0) * BINS) * sizeof(float);
     };
@@ -580,10 +606,31 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     nx0 = load_roi(a, r0 + stride + tj, r_end);
     nx1 = load_roi(a, r0 + stride + tj + NB / 2, r_end);
     int cur = 0;
-    for (; r0 < r_end; r0 += stride, cur ^= 1) {
-        __syncthreads();  // tables[cur] (and, first time, T22) complete; tables[cur^1] no longer read
-        fill_tables(cur ^ 1, tj, nx0);  // geometry of the next batch
-        fill_tables(cur ^ 1, tj + NB / 2, nx1);
+    uint32_t batch = 0;
+    if (PIPE) {
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&s_full[0]);  // this warp's share of batch 0's geometry is written
+        __syncthreads();                               // the last table pass is complete
+    }
+    for (; r0 < r_end; r0 += stride, ++batch) {
+        int nxt;
+        if (PIPE) {
+            // every warp has written batch `batch` (so it has also finished pooling batch - 2, whose buffer
+            // batch + 1 overwrites below); warps may be one batch apart, never two
+            cur = (int)(batch % 3u);
+            nxt = (int)((batch + 1u) % 3u);
+            mbar_wait(&s_full[cur], (batch / 3u) & 1u);
+        } else {
+            cur = (int)(batch & 1u);
+            nxt = cur ^ 1;
+            __syncthreads();  // tables[cur] (and, first time, T22) complete; tables[cur^1] no longer read
+        }
+        fill_tables(nxt, tj, nx0);  // geometry of the next batch
+        fill_tables(nxt, tj + NB / 2, nx1);
+        if (PIPE) {
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&s_full[nxt]);
+        }
         nx0 = load_roi(a, r0 + 2 * stride + tj, r_end);  // boxes of the batch after that
         nx1 = load_roi(a, r0 + 2 * stride + tj + NB / 2, r_end);
         const int nb = min(NB, r_end - r0);
@@ -673,8 +720,13 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
             }
             const bool big0 = ((h.y | w.y) & TAB_BIG_BIT) != 0, big1 = ((h.y | w.w) & TAB_BIG_BIT) != 0;
             if (__any_sync(0xFFFFFFFFu, big0 || big1)) {
-                if (big0) v0 = tab_big_bin<float4>(tab, s_hraw[cur][j][ph], s_wraw[cur][j][pw], WP);
-                if (big1) v1 = tab_big_bin<float4>(tab, s_hraw[cur][j][ph], s_wraw[cur][j][pw + 1], WP);
+                const int hr = PIPE ? tab_decode_range(h.x, hy, LV * HWp, WP, sizeof(V)) : s_hraw[PIPE ? 0 : cur][PIPE ? 0 : j][PIPE ? 0 : ph];
+                if (big0)
+                    v0 = tab_big_bin<float4>(tab, hr, PIPE ? tab_decode_range(w.x, wy0, HWp, 1, sizeof(V))
+                                                           : s_wraw[PIPE ? 0 : cur][PIPE ? 0 : j][PIPE ? 0 : pw], WP);
+                if (big1)
+                    v1 = tab_big_bin<float4>(tab, hr, PIPE ? tab_decode_range(w.z, wy1, HWp, 1, sizeof(V))
+                                                           : s_wraw[PIPE ? 0 : cur][PIPE ? 0 : j][PIPE ? 0 : pw + 1], WP);
             }
             const unsigned m0 = (unsigned)((h.y & w.y) >> 31), m1 = (unsigned)((h.y & w.w) >> 31);
             float2* o = reinterpret_cast<float2*>(
@@ -1648,7 +1700,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             if (tcs == 4 && minb == 2) {
                 if (PH == 7) FRCNN_TAB(7, 392, 4, 2, false, 2);
                 set_groups(4, 392);  // 14x14: two adjacent bins per thread
-                return launch_tab(roi_pool_tab_kernel<14, 392, 4, 2, false, 2, 2>, a, table_bytes(2, 4, a.pitch), 392,
+                return launch_tab(roi_pool_tab_kernel<14, 392, 4, 2, false, 2, 2, true>, a, table_bytes(2, 4, a.pitch), 392,
                                   stream);
             } else if (tcs == 2 && minb == 2) {
                 if (PH == 7) FRCNN_TAB(7, 392, 2, 2, false, 2);
