@@ -542,7 +542,6 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     constexpr int NB = TAB_THREADS / P;          // RoIs per batch: two table entries per thread
     constexpr int ITERS = NB / RPI;
     static_assert(BPT == 1 || (BPT == 2 && P % 2 == 0 && CS == 4 && LV == 2 && !ARGMAX), "bin pairs: 14x14 inference");
-    static_assert(!PIPE || BPT == 2, "the pipelined geometry hand-off is implemented for the bin-pair variant");
     // PIPE: three geometry buffers and one mbarrier per buffer instead of a CTA barrier per batch.  A thread
     // waits for batch b's geometry, computes batch b+1's, then pools batch b: warps may drift one batch apart
     // (measured upper bound of removing the per-batch barrier on the 14x14 configuration: ~10 %).
@@ -557,7 +556,10 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(16) int2 s_th[NBUF][NB][P], s_tw[NBUF][NB][P];  // per RoI: row / column corner offsets + flags
-    __shared__ int s_hraw[PIPE ? 1 : 2][PIPE ? 1 : NB][PIPE ? 1 : P], s_wraw[PIPE ? 1 : 2][PIPE ? 1 : NB][PIPE ? 1 : P];
+    // raw [lo,hi) extents: kept for the training scan (every bin uses them); the inference kernels recover them
+    // from the entries on their rare long-bin path, which leaves room for the third geometry buffer
+    constexpr bool RAW = ARGMAX || !PIPE;
+    __shared__ int s_hraw[RAW ? NBUF : 1][RAW ? NB : 1][RAW ? P : 1], s_wraw[RAW ? NBUF : 1][RAW ? NB : 1][RAW ? P : 1];
     __shared__ size_t s_ob[NBUF][NB];                // per RoI: byte offset of its [CS,P,P] output block
     __shared__ __align__(8) uint64_t s_full[PIPE ? 3 : 1];  // PIPE: geometry of buffer i complete
     V* tab = reinterpret_cast<V*>(smem_raw);
@@ -593,11 +595,11 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
         int unused;
         if (ti < P)
             s_th[buf][j][ti] = tab_entry<LV, MID>(ti, P, q.y1, q.y2, a.scale, H, WP, LV * HWp, sizeof(V),
-                                                  PIPE ? &unused : &s_hraw[PIPE ? 0 : buf][PIPE ? 0 : j][PIPE ? 0 : ti]);
+                                                  RAW ? &s_hraw[RAW ? buf : 0][RAW ? j : 0][RAW ? ti : 0] : &unused);
         else
             s_tw[buf][j][ti - P] = tab_entry<LV, MID>(ti - P, P, q.x1, q.x2, a.scale, W, 1, HWp, sizeof(V),
-                                                      PIPE ? &unused
-                                                           : &s_wraw[PIPE ? 0 : buf][PIPE ? 0 : j][PIPE ? 0 : ti - P]);
+                                                      RAW ? &s_wraw[RAW ? buf : 0][RAW ? j : 0][RAW ? ti - P : 0]
+                                                          : &unused);
         if (ti == 0)
             s_ob[buf][j] = (((size_t)max(q.k, 0) * a.C + c0) * BINS) * sizeof(float);
     };
@@ -644,11 +646,15 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
                 typename IdxT<CS>::type idx;
                 vsplat(v, -FLT_MAX);
                 vneg(idx);
-                const int hr = s_hraw[cur][j][ph], wr = s_wraw[cur][j][pw];
+                const unsigned m = (unsigned)((h.y & w.y) >> 31);  // all ones iff the bin is non-empty
+                int hr = 0, wr = 0;  // empty range unless the bin is non-empty
+                if (m) {
+                    hr = s_hraw[RAW ? cur : 0][RAW ? j : 0][RAW ? ph : 0];
+                    wr = s_wraw[RAW ? cur : 0][RAW ? j : 0][RAW ? pw : 0];
+                }
                 const int x0 = wr & 0xFFFF, x1 = wr >> 16;
                 for (int y = hr & 0xFFFF; y < (hr >> 16); ++y)
                     for (int x = x0; x < x1; ++x) scan_first_max(v, idx, tab[y * WP + x], y * W + x);
-                const unsigned m = (unsigned)((h.y & w.y) >> 31);  // all ones iff the bin is non-empty
                 float* o = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.out) + s_ob[cur][j]) + e;
                 if (valid) {
                     vstore<false>(o, BINS, v, m, cs);
@@ -684,7 +690,13 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
             }
             const bool big = ((h.y | w.y) & TAB_BIG_BIT) != 0;
             if (__any_sync(0xFFFFFFFFu, big)) {
-                if (big) v = tab_big_bin<V>(tab, s_hraw[cur][j][ph], s_wraw[cur][j][pw], WP);
+                if (big)
+                    v = tab_big_bin<V>(tab,
+                                       RAW ? s_hraw[RAW ? cur : 0][RAW ? j : 0][RAW ? ph : 0]
+                                           : tab_decode_range(h.x, hy, LV * HWp, WP, sizeof(V)),
+                                       RAW ? s_wraw[RAW ? cur : 0][RAW ? j : 0][RAW ? pw : 0]
+                                           : tab_decode_range(w.x, wy, HWp, 1, sizeof(V)),
+                                       WP);
             }
             const unsigned m = (unsigned)((h.y & w.y) >> 31);  // all ones iff the bin is non-empty
             float* o = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.out) + s_ob[cur][j]) + e;
@@ -720,13 +732,14 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
             }
             const bool big0 = ((h.y | w.y) & TAB_BIG_BIT) != 0, big1 = ((h.y | w.w) & TAB_BIG_BIT) != 0;
             if (__any_sync(0xFFFFFFFFu, big0 || big1)) {
-                const int hr = PIPE ? tab_decode_range(h.x, hy, LV * HWp, WP, sizeof(V)) : s_hraw[PIPE ? 0 : cur][PIPE ? 0 : j][PIPE ? 0 : ph];
+                const int hr = RAW ? s_hraw[RAW ? cur : 0][RAW ? j : 0][RAW ? ph : 0]
+                                   : tab_decode_range(h.x, hy, LV * HWp, WP, sizeof(V));
                 if (big0)
-                    v0 = tab_big_bin<float4>(tab, hr, PIPE ? tab_decode_range(w.x, wy0, HWp, 1, sizeof(V))
-                                                           : s_wraw[PIPE ? 0 : cur][PIPE ? 0 : j][PIPE ? 0 : pw], WP);
+                    v0 = tab_big_bin<float4>(tab, hr, RAW ? s_wraw[RAW ? cur : 0][RAW ? j : 0][RAW ? pw : 0]
+                                                          : tab_decode_range(w.x, wy0, HWp, 1, sizeof(V)), WP);
                 if (big1)
-                    v1 = tab_big_bin<float4>(tab, hr, PIPE ? tab_decode_range(w.z, wy1, HWp, 1, sizeof(V))
-                                                           : s_wraw[PIPE ? 0 : cur][PIPE ? 0 : j][PIPE ? 0 : pw + 1], WP);
+                    v1 = tab_big_bin<float4>(tab, hr, RAW ? s_wraw[RAW ? cur : 0][RAW ? j : 0][RAW ? pw + 1 : 0]
+                                                          : tab_decode_range(w.z, wy1, HWp, 1, sizeof(V)), WP);
             }
             const unsigned m0 = (unsigned)((h.y & w.y) >> 31), m1 = (unsigned)((h.y & w.w) >> 31);
             float2* o = reinterpret_cast<float2*>(
@@ -1631,7 +1644,8 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
     }
     // RoIPool 7x7 / 14x14: thread-per-bin kernel over shared-memory max tables (roi_pool_tab_kernel).
     //   LV = 2 (windows 1,2: bins up to 4 long; 5..8 through four 2-windows on the 7x7 grid)  inference
-    //   LV = 1 (pixels only, every bin scanned)  training: value + argmax in one scan
+    //   LV = 1 (pixels only, every bin scanned)  training: value + argmax in one scan (small tables, several
+    //          CTAs per SM: the plain two-buffer / CTA-barrier hand-off, a third buffer would cost a CTA)
     // (a three-level form -- windows 1,2,4, nine tables -- was measured and dropped: it only fits with one or
     //  two channels per CTA, and the per-bin instruction overhead is paid per channel group)
     if (PH == PW && (PH == 7 || PH == 14)) {
@@ -1651,7 +1665,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
 #define FRCNN_TAB(PP_, TH_, CS_, MB_, AM_, LV_)                                                             \
     do {                                                                                                    \
         set_groups(CS_, TH_);                                                                               \
-        return launch_tab(roi_pool_tab_kernel<PP_, TH_, CS_, MB_, AM_, LV_>, a, table_bytes(LV_, CS_, a.pitch), \
+        return launch_tab(roi_pool_tab_kernel<PP_, TH_, CS_, MB_, AM_, LV_, 1, !(AM_)>, a, table_bytes(LV_, CS_, a.pitch), \
                           TH_, stream);                                                                     \
     } while (0)
         // rows whose byte length is a multiple of 64 would put vertically adjacent bins on the same banks
