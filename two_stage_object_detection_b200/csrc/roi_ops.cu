@@ -372,6 +372,25 @@ __device__ __forceinline__ RoiBox load_roi(const RoiArgs& a, int r, int r_end) {
     return q;
 }
 
+// What one geometry thread needs of a RoI: the two coordinates of ITS axis (rows: y1,y2; columns: x1,x2) and
+// the RoI id -- 3 registers per prefetched RoI instead of the 5 of a whole box.
+struct RoiAxis {
+    int k;
+    float c1, c2;
+};
+__device__ __forceinline__ RoiAxis load_roi_axis(const RoiArgs& a, int r, int r_end, bool rows) {
+    RoiAxis q;
+    q.k = -1;
+    q.c1 = q.c2 = 0.f;
+    if (r < r_end) {
+        q.k = roi_at(a, r);
+        const float* rp = a.rois5 + (size_t)q.k * 5 + (rows ? 2 : 1);
+        q.c1 = __ldg(rp);
+        q.c2 = __ldg(rp + 2);
+    }
+    return q;
+}
+
 // One axis of the bin grid: [lo,hi) of bin `i`, as (byte offset of first corner, byte offset of second
 // corner | flags); `unit` = table elements per step along this axis (row pitch for rows, 1 for columns),
 // `tsel` = table stride per window level along this axis, `esz` = bytes per table element.
@@ -576,7 +595,8 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     const int tid = threadIdx.x;
     // table-entry role: axis entry ti (rows first, then columns) of RoIs tj and tj + NB/2 of the batch
     const int tj = tid / (2 * P), ti = tid % (2 * P);
-    RoiBox nx0 = load_roi(a, r0 + tj, r_end), nx1 = load_roi(a, r0 + tj + NB / 2, r_end);
+    const bool trow = ti < P;  // this thread computes a row (else a column) entry
+    RoiAxis nx0 = load_roi_axis(a, r0 + tj, r_end, trow), nx1 = load_roi_axis(a, r0 + tj + NB / 2, r_end, trow);
 
     // staged planes [cs][HW]: where the last-built table will be (LV = 1: a region of their own)
     float* raw = reinterpret_cast<float*>(tab + (LV == 1 ? 1 : NT - 1) * HWp);
@@ -591,13 +611,13 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     const int slot = tid % SLOTS, ej = tid / SLOTS;
     const int ph = slot / (P / BPT), pw = (slot % (P / BPT)) * BPT;
     const int e = ph * P + pw;
-    auto fill_tables = [&](int buf, int j, const RoiBox& q) {
+    auto fill_tables = [&](int buf, int j, const RoiAxis& q) {
         int unused;
-        if (ti < P)
-            s_th[buf][j][ti] = tab_entry<LV, MID>(ti, P, q.y1, q.y2, a.scale, H, WP, LV * HWp, sizeof(V),
+        if (trow)
+            s_th[buf][j][ti] = tab_entry<LV, MID>(ti, P, q.c1, q.c2, a.scale, H, WP, LV * HWp, sizeof(V),
                                                   RAW ? &s_hraw[RAW ? buf : 0][RAW ? j : 0][RAW ? ti : 0] : &unused);
         else
-            s_tw[buf][j][ti - P] = tab_entry<LV, MID>(ti - P, P, q.x1, q.x2, a.scale, W, 1, HWp, sizeof(V),
+            s_tw[buf][j][ti - P] = tab_entry<LV, MID>(ti - P, P, q.c1, q.c2, a.scale, W, 1, HWp, sizeof(V),
                                                       RAW ? &s_wraw[RAW ? buf : 0][RAW ? j : 0][RAW ? ti - P : 0]
                                                           : &unused);
         if (ti == 0)
@@ -605,8 +625,8 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     };
     fill_tables(0, tj, nx0);
     fill_tables(0, tj + NB / 2, nx1);
-    nx0 = load_roi(a, r0 + stride + tj, r_end);
-    nx1 = load_roi(a, r0 + stride + tj + NB / 2, r_end);
+    nx0 = load_roi_axis(a, r0 + stride + tj, r_end, trow);
+    nx1 = load_roi_axis(a, r0 + stride + tj + NB / 2, r_end, trow);
     int cur = 0;
     uint32_t batch = 0;
     if (PIPE) {
@@ -633,8 +653,8 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&s_full[nxt]);
         }
-        nx0 = load_roi(a, r0 + 2 * stride + tj, r_end);  // boxes of the batch after that
-        nx1 = load_roi(a, r0 + 2 * stride + tj + NB / 2, r_end);
+        nx0 = load_roi_axis(a, r0 + 2 * stride + tj, r_end, trow);  // boxes of the batch after that
+        nx1 = load_roi_axis(a, r0 + 2 * stride + tj + NB / 2, r_end, trow);
         const int nb = min(NB, r_end - r0);
         // one bin (this thread's ph,pw) of RoI j of the batch, all CS channels
         auto one_bin = [&](int j, bool full, bool valid) {
@@ -758,6 +778,7 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
         };
         if (nb == NB && cs == CS) {
             if constexpr (BPT == 2) {
+                // not unrolled (registers); prefetching the next RoI's entries by hand was measured slower too
 #pragma unroll 1
                 for (int it = 0; it < ITERS; ++it) one_pair(it * RPI + ej, true, true);
             } else {
