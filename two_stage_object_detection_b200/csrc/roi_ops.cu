@@ -1125,15 +1125,19 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs
     constexpr int BINS = P * P;
     constexpr int RPI = AL_THREADS / BINS;                  // RoIs per iteration
     constexpr int EPR = 2 * P * SR;                         // table entries per RoI (rows then columns)
-    constexpr int EPT = 4;                                  // table entries per thread and batch
+    constexpr int EPT = 3;                                  // table entries per thread and batch
     constexpr int NB = (EPT * AL_THREADS / EPR) / RPI * RPI;  // RoIs per batch
     constexpr int ITERS = NB / RPI;
     static_assert(RPI * BINS == AL_THREADS && NB > 0 && NB <= AL_THREADS, "thread mapping");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ __align__(16) AlignEntry s_ent[2][NB][EPR];
-    __shared__ size_t s_ob[2][NB];
+    // geometry in three buffers handed over through one mbarrier each (see roi_pool_tab_kernel): a warp waits
+    // for batch b's entries, computes batch b+1's, then gathers batch b; warps may drift one batch apart
+    constexpr int NWARPS = (AL_THREADS + 31) / 32;
+    __shared__ __align__(16) AlignEntry s_ent[3][NB][EPR];
+    __shared__ size_t s_ob[3][NB];
     __shared__ RoiBox s_box[2][NB];
+    __shared__ __align__(8) uint64_t s_full[3];
     float4* tab = reinterpret_cast<float4*>(smem_raw);
     const int H = a.H, W = a.W, HW = H * W, HWp = (HW + 3) & ~3;
     const int b = blockIdx.z;
@@ -1153,6 +1157,9 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs
     RoiBox nxt = load_roi(a, r0 + 2 * stride + (tid < NB ? tid : 0), r_end);
 
     float* raw = reinterpret_cast<float*>(tab + HWp);  // [cs][HW] planes, staged next to the table
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) mbar_init(&s_full[i], NWARPS);  // visible after the barriers inside stage_slab
+    }
     stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
     for (int p = tid; p < HW; p += AL_THREADS) {
         float4 v;
@@ -1166,13 +1173,13 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs
 
     const int e = tid % BINS, ej = tid / BINS;
     const int ph = e / P, pw = e % P;
-    auto fill_tables = [&](int buf) {  // geometry of the batch whose boxes sit in s_box[buf]
+    auto fill_tables = [&](int buf, int bbuf) {  // geometry buffer `buf` from the boxes in s_box[bbuf]
 #pragma unroll
         for (int q = 0; q < EPT; ++q) {
             const int idx = tid + q * AL_THREADS;
             if (idx < NB * EPR) {
                 const int j = idx / EPR, ent = idx % EPR;
-                const RoiBox box = s_box[buf][j];
+                const RoiBox box = s_box[bbuf][j];
                 const bool is_row = ent < P * SR;
                 const int pe = is_row ? ent : ent - P * SR;
                 s_ent[buf][j][ent] = is_row ? align_entry(pe / SR, pe % SR, P, SR, box.y1, box.y2, a.scale, a.aligned, H, W)
@@ -1181,12 +1188,19 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs
             }
         }
     };
-    fill_tables(0);
-    int cur = 0;
-    for (; r0 < r_end; r0 += stride, cur ^= 1) {
-        __syncthreads();  // tables[cur] complete; tables[cur^1] and s_box[cur] no longer read
-        fill_tables(cur ^ 1);  // next batch (ALU only: its boxes are already in shared memory)
-        if (tid < NB) s_box[cur][tid] = nxt;  // boxes of the batch after next
+    fill_tables(0, 0);
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&s_full[0]);
+    uint32_t batch = 0;
+    for (; r0 < r_end; r0 += stride, ++batch) {
+        const int cur = (int)(batch % 3u), nbuf = (int)((batch + 1u) % 3u);
+        // every warp has written batch `batch` (hence finished gathering batch - 2 and reading the boxes of
+        // batch `batch`): buffer batch + 1 and the box slot of batch + 2 may be overwritten
+        mbar_wait(&s_full[cur], (batch / 3u) & 1u);
+        if (tid < NB) s_box[batch & 1u][tid] = nxt;  // boxes of the batch after next (ordered by the arrive below)
+        fill_tables(nbuf, (int)((batch + 1u) & 1u));  // next batch (ALU only: its boxes are already in shared memory)
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&s_full[nbuf]);
         nxt = load_roi(a, r0 + 3 * stride + (tid < NB ? tid : 0), r_end);
         const int nb = min(NB, r_end - r0);
         for (int it = 0; it < ITERS; ++it) {
