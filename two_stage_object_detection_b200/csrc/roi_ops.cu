@@ -653,8 +653,13 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&s_full[nxt]);
         }
-        nx0 = load_roi_axis(a, r0 + 2 * stride + tj, r_end, trow);  // boxes of the batch after that
-        nx1 = load_roi_axis(a, r0 + 2 * stride + tj + NB / 2, r_end, trow);
+        bool prefetched = false;
+        auto prefetch_boxes = [&]() {  // boxes of the batch after the next one
+            nx0 = load_roi_axis(a, r0 + 2 * stride + tj, r_end, trow);
+            nx1 = load_roi_axis(a, r0 + 2 * stride + tj + NB / 2, r_end, trow);
+            prefetched = true;
+        };
+        if (!(BPT == 2 && PIPE)) prefetch_boxes();
         const int nb = min(NB, r_end - r0);
         // one bin (this thread's ph,pw) of RoI j of the batch, all CS channels
         auto one_bin = [&](int j, bool full, bool valid) {
@@ -780,7 +785,12 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
             if constexpr (BPT == 2) {
                 // not unrolled (registers); prefetching the next RoI's entries by hand was measured slower too
 #pragma unroll 1
-                for (int it = 0; it < ITERS; ++it) one_pair(it * RPI + ej, true, true);
+                for (int it = 0; it < ITERS; ++it) {
+                    // issued after the first RoI: at the top of the batch the loads shared a scoreboard with
+                    // the loop's first constant loads, which then waited an L2 round trip every batch
+                    if (PIPE && it == 1) prefetch_boxes();
+                    one_pair(it * RPI + ej, true, true);
+                }
             } else {
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it) one_bin(it * RPI + ej, true, true);
@@ -792,6 +802,7 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
                 else one_bin(j < nb ? j : 0, false, j < nb);
             }
         }
+        if (!prefetched) prefetch_boxes();
     }
 }
 
