@@ -391,10 +391,11 @@ def run_ours(args):
     launches = 1 + 1 + n_sb + 1 + 1 + 1  # decode, topk, nms block kernel per super-block, finalize, coords, gather
     if train:
         launches += 3  # anchor_iou, anchor_label, proposal_target
-    # <P, threads, channels per CTA, CTAs per SM, argmax, table levels[, bins per thread]> as csrc/roi_ops.cu picks them
-    kernel_name = "roi_pool_tab_kernel<14,392,4,2,false,2,2>" if (cfg["op"], P) == ("pool", 14) else (
+    # <P, threads, channels per CTA, CTAs per SM, argmax, table levels[, bins per thread, mbarrier hand-off]> as
+    # csrc/roi_ops.cu picks them
+    kernel_name = "roi_pool_tab_kernel<14,392,4,2,false,2,2,true>" if (cfg["op"], P) == ("pool", 14) else (
         ("roi_pool_tab_kernel<7,392,4,2,true,1>" if train else
-         ("roi_pool_tab_kernel<7,784,2,1,false,2>" if H * W > 3000 else "roi_pool_tab_kernel<7,392,4,2,false,2>"))
+         ("roi_pool_tab_kernel<7,784,2,1,false,2,1,true>" if H * W > 3000 else "roi_pool_tab_kernel<7,392,4,2,false,2,1,true>"))
         if cfg["op"] == "pool" else "roi_align_tab_kernel<7,2,392,2>")
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from one ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
