@@ -395,7 +395,7 @@ def run_ours(args):
     # csrc/roi_ops.cu picks them
     kernel_name = "roi_pool_tab_kernel<14,392,4,2,false,2,2,true>" if (cfg["op"], P) == ("pool", 14) else (
         ("roi_pool_tab_kernel<7,392,4,2,true,1>" if train else
-         ("roi_pool_tab_kernel<7,784,2,1,false,2,1,true>" if H * W > 3000 else "roi_pool_tab_kernel<7,392,4,2,false,2,1,true>"))
+         ("roi_pool_tab_kernel<7,784,4,1,false,2,1,true,true>" if H * W > 3000 else "roi_pool_tab_kernel<7,392,4,2,false,2,1,true>"))
         if cfg["op"] == "pool" else "roi_align_tab_kernel<7,2,392,2>")
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from one ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "traffic.json")

@@ -632,6 +632,34 @@ def test_roi_pool_channel_tail_and_big_bins(F, O):
                               O.roi_align(feat, rois, P, 1.0, 2, False)), (H, W, P)
 
 
+@pytest.mark.parametrize("shape", [(1, 9, 64, 64, 7), (2, 6, 50, 50, 7), (1, 5, 50, 50, 14), (1, 6, 64, 64, 14),
+                                   (1, 4, 60, 52, 7)])
+def test_roi_pool_two_table_variants(F, O, shape):
+    """Maps whose four 4-channel max tables do not fit in shared memory use two tables (pixels and 2 x 2
+    windows): bins 1 thick and 2..4 long read the pixels along the long axis, 5..8-long thin bins are scanned.
+    RoI families: thin-and-long both ways, small, medium, larger than the map, degenerate."""
+    B, Cc, H, W, P = shape
+    rng = np.random.default_rng(H * 131 + W * 7 + P)
+    feat = rng.standard_normal((B, Cc, H, W)).astype(np.float32)
+    fam = []
+    n = 60
+    for (wlo, whi, hlo, hhi) in [(0.5, 6, P * 1.5, P * 9), (P * 1.5, P * 9, 0.5, 6), (0.5, P, 0.5, P),
+                                 (P, 4 * P, P, 4 * P), (W * 0.6, W * 1.4, H * 0.6, H * 1.4), (0, 0.4, 0, 0.4)]:
+        c = np.stack([rng.uniform(-3, W + 3, n), rng.uniform(-3, H + 3, n)], 1)
+        wh = np.stack([rng.uniform(wlo, whi, n), rng.uniform(hlo, hhi, n)], 1)
+        fam.append(np.concatenate([c - wh / 2, c + wh / 2], 1))
+    boxes = np.concatenate(fam)
+    rois = np.concatenate([rng.integers(0, B, (len(boxes), 1)), boxes], 1).astype(np.float32)
+    for scale in (1.0, 0.5):
+        assert np.array_equal(N(F.roi_pool_forward(T(feat), T(rois), P, scale)), O.roi_pool(feat, rois, P, scale)), scale
+    # grouped (rois_per_image) launch of the same kernel
+    order = np.argsort(rois[:, 0], kind="stable")
+    per = np.bincount(rois[:, 0].astype(int), minlength=B).min()
+    grouped = np.concatenate([rois[order][rois[order][:, 0] == b][:per] for b in range(B)])
+    assert np.array_equal(N(F.roi_pool_forward(T(feat), T(grouped), P, 1.0, rois_per_image=int(per))),
+                          O.roi_pool(feat, grouped, P, 1.0))
+
+
 def test_nan_and_inf_features_in_roi_pool(F, O):
     """The reference's `v > best` scan never selects NaN / -inf; all-NaN bins give -FLT_MAX."""
     rng = np.random.default_rng(3)

@@ -294,6 +294,8 @@ constexpr int TAB_NE_BIT = 0x80000000;   // entry .y bit 31: bin row / column is
 constexpr int TAB_BIG_BIT = 0x40000000;  // entry .y bit 30: longer than the tables cover -> loop path
 constexpr int TAB_MID_BIT = 0x20000000;  // entry .y bit 29 (tables 1,2 only): 5..8 long -> four 2-windows
 constexpr int TAB_OFF_MASK = 0x1FFFFFFF;
+constexpr int TAB_LVL_BIT = 0x10000000;  // entry .y bit 28 (DIAG tables only): this axis uses the 2-long window
+constexpr int TAB_DIAG_MASK = 0x0FFFFFFF;
 
 // CS channel-interleaved floats per pixel: float4 (LDS.128) for CS = 4, float2 (LDS.64) for CS = 2.
 // Native vector types on purpose: a struct-of-array wrapper made ptxas split the predicated loads.
@@ -394,7 +396,7 @@ __device__ __forceinline__ RoiAxis load_roi_axis(const RoiArgs& a, int r, int r_
 // One axis of the bin grid: [lo,hi) of bin `i`, as (byte offset of first corner, byte offset of second
 // corner | flags); `unit` = table elements per step along this axis (row pitch for rows, 1 for columns),
 // `tsel` = table stride per window level along this axis, `esz` = bytes per table element.
-template <int LV, bool MID = false>
+template <int LV, bool MID = false, bool DIAG = false>
 __device__ __forceinline__ int2 tab_entry(int i, int P, float c1, float c2, float scale, int limit, int unit,
                                           int tsel, int esz, int* raw) {
     const int s = round_half_away(c1 * scale), e = round_half_away(c2 * scale);
@@ -409,27 +411,28 @@ __device__ __forceinline__ int2 tab_entry(int i, int P, float c1, float c2, floa
     const int a = 1 << lvl;
     const int lo_ = empty ? 0 : lo, hi_ = empty ? a : hi;
     int2 r;
-    r.x = (lvl * tsel + lo_ * unit) * esz;
-    r.y = ((lvl * tsel + (hi_ - a) * unit) * esz) | (empty ? 0 : TAB_NE_BIT) |
+    // DIAG: the level is a flag, not a table offset (the table is chosen per bin from both axes' levels)
+    const int tbase = DIAG ? 0 : lvl * tsel;
+    r.x = (tbase + lo_ * unit) * esz;
+    r.y = ((tbase + (hi_ - a) * unit) * esz) | (empty ? 0 : TAB_NE_BIT) |
           (len > (LV == 1 ? 1 : (MID ? 8 : 4)) ? TAB_BIG_BIT : 0) |
-          ((MID && len > 4 && len <= 8) ? TAB_MID_BIT : 0);
+          ((MID && len > 4 && len <= 8) ? TAB_MID_BIT : 0) | ((DIAG && lvl) ? TAB_LVL_BIT : 0);
     return r;
 }
 
 // A run of 5..8 pixels is covered by the 2-long windows at lo, lo+2, hi-4, hi-2 (the first and the last are
 // the regular two lookups).  `h0,h1` / `w0,w1` are the regular corner offsets, `hm` / `wm` say which axis is
-// 5..8 long, `rstep` / `cstep` = byte distance of two pixels along the axis.  Twelve extra lookups at most;
-// on an axis that is not long the extra positions repeat the regular ones (max is idempotent).
+// 5..8 long, `rstep` / `cstep` = byte distance of two pixels along the axis.  Twelve extra lookups at most.
 template <typename V>
 __device__ __noinline__ V tab_mid_bin(V v, const unsigned char* smem, int h0, int h1, bool hm, int w0, int w1,
                                          bool wm, int rstep, int cstep) {
-    const int hp[4] = {h0, h1, hm ? h0 + rstep : h0, hm ? h1 - rstep : h1};
-    const int wp[4] = {w0, w1, wm ? w0 + cstep : w0, wm ? w1 - cstep : w1};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (i >= 2 || j >= 2) v = vmax(v, *reinterpret_cast<const V*>(smem + (hp[i] + wp[j])));
+    // only the positions an axis really adds are read: four lookups when one axis is long (the usual case),
+    // twelve when both are
+    const int h2 = h0 + rstep, h3 = h1 - rstep, w2 = w0 + cstep, w3 = w1 - cstep;
+    auto at = [&](int o) { return *reinterpret_cast<const V*>(smem + o); };
+    if (hm) v = vmax(vmax(v, vmax(at(h2 + w0), at(h2 + w1))), vmax(at(h3 + w0), at(h3 + w1)));
+    if (wm) v = vmax(vmax(v, vmax(at(h0 + w2), at(h0 + w3))), vmax(at(h1 + w2), at(h1 + w3)));
+    if (hm && wm) v = vmax(vmax(v, vmax(at(h2 + w2), at(h2 + w3))), vmax(at(h3 + w2), at(h3 + w3)));
     return v;
 }
 
@@ -493,7 +496,7 @@ struct IdxT<1> {
 // Builds the max tables of one channel slab from the staged planes `raw` [cs][H*W]:
 // T[lr][lc][y][x] = max of the (1<<lr) x (1<<lc) window anchored at (y,x), at tab + (lr*LV + lc)*HWp, row
 // pitch WP.  Pixels are first clamped with fmaxf(., -FLT_MAX).  Ends without a barrier.
-template <typename V, int LV, int THREADS>
+template <typename V, int LV, int THREADS, bool DIAG = false>
 __device__ __forceinline__ void build_max_tables(V* tab, const float* raw, int cs, int H, int W, int WP, int HWp,
                                                  int tid) {
     const int HW = H * W;
@@ -523,6 +526,12 @@ __device__ __forceinline__ void build_max_tables(V* tab, const float* raw, int c
     __syncthreads();
     if (LV == 1) {
         // raw pixels only: every bin is scanned
+    } else if (DIAG) {
+        // two tables only: pixels and 2 x 2 windows (the mixed 1 x 2 / 2 x 1 cases read the pixels twice)
+        for_pixels([&](int, int y, int x, int q) {
+            const int dx = x + 1 < W ? 1 : 0, qd = y + 1 < H ? q + WP : q;
+            tab[HWp + q] = vmax(vmax(tab[q], tab[q + dx]), vmax(tab[qd], tab[qd + dx]));
+        });
     } else if (LV == 2) {
         for_pixels([&](int, int y, int x, int q) {
             const int qr = x + 1 < W ? q + 1 : q, qd = y + 1 < H ? q + WP : q;
@@ -540,6 +549,9 @@ __device__ __forceinline__ void build_max_tables(V* tab, const float* raw, int c
 
 // Recovers [lo,hi) of a bin axis from its table entry (PIPE variant: the raw extents are not kept in shared
 // memory).  o1 / o2 = the two corner offsets in bytes, tsel / unit as given to tab_entry, esz = element size.
+__device__ __forceinline__ int tab_decode_range_diag(int o1, int o2, bool lvl, int unit, int esz) {
+    return (o1 / (unit * esz)) | ((o2 / (unit * esz) + (lvl ? 2 : 1)) << 16);
+}
 __device__ __forceinline__ int tab_decode_range(int o1, int o2, int tsel, int unit, int esz) {
     o1 /= esz;
     o2 /= esz;
@@ -552,7 +564,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int P, int TAB_THREADS, int CS, int MINB, bool ARGMAX, int LV, int BPT = 1, bool PIPE = false>
+template <int P, int TAB_THREADS, int CS, int MINB, bool ARGMAX, int LV, int BPT = 1, bool PIPE = false,
+          bool DIAG = false>
 __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs a) {
     typedef typename VecT<CS>::type V;
     constexpr int BINS = P * P;
@@ -566,8 +579,12 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     // (measured upper bound of removing the per-batch barrier on the 14x14 configuration: ~10 %).
     constexpr int NBUF = PIPE ? 3 : 2;
     constexpr int NWARPS = (TAB_THREADS + 31) / 32;
-    constexpr int NT = LV * LV;                  // tables: (row level, column level), levels 1 (, 2)
+    // tables: (row level, column level), levels 1 (, 2); DIAG keeps only (1,1) and (2,2) -- half the shared
+    // memory, so a map too large for four 4-channel tables still gets four channels per lookup -- and a bin
+    // with one axis 1 long and the other 2..4 reads the pixels along the long axis instead
+    constexpr int NT = DIAG ? 2 : LV * LV;
     static_assert(LV == 1 || LV == 2, "table levels");
+    static_assert(!DIAG || (LV == 2 && BPT == 1 && !ARGMAX && PIPE), "two-table form: single-bin inference kernels");
     // 5..8-long bins through four 2-windows: 7x7 bins only (a 14x14 grid needs a RoI > 56 pixels wide for
     // one, and the extra call site costs the 14x14 fast path registers)
     constexpr bool MID = LV == 2 && P == 7;
@@ -604,7 +621,7 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
         for (int i = 0; i < 3; ++i) mbar_init(&s_full[i], NWARPS);  // one arrival per warp; visible after the
     }                                                                // barriers inside stage_slab
     stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
-    build_max_tables<V, LV, TAB_THREADS>(tab, raw, cs, H, W, WP, HWp, tid);
+    build_max_tables<V, LV, TAB_THREADS, DIAG>(tab, raw, cs, H, W, WP, HWp, tid);
 
     // compute role: bin e = (ph,pw) (and its right neighbour when BPT = 2) of the (tid / SLOTS)-th RoI of
     // each iteration
@@ -614,10 +631,10 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     auto fill_tables = [&](int buf, int j, const RoiAxis& q) {
         int unused;
         if (trow)
-            s_th[buf][j][ti] = tab_entry<LV, MID>(ti, P, q.c1, q.c2, a.scale, H, WP, LV * HWp, sizeof(V),
+            s_th[buf][j][ti] = tab_entry<LV, MID, DIAG>(ti, P, q.c1, q.c2, a.scale, H, WP, LV * HWp, sizeof(V),
                                                   RAW ? &s_hraw[RAW ? buf : 0][RAW ? j : 0][RAW ? ti : 0] : &unused);
         else
-            s_tw[buf][j][ti - P] = tab_entry<LV, MID>(ti - P, P, q.c1, q.c2, a.scale, W, 1, HWp, sizeof(V),
+            s_tw[buf][j][ti - P] = tab_entry<LV, MID, DIAG>(ti - P, P, q.c1, q.c2, a.scale, W, 1, HWp, sizeof(V),
                                                       RAW ? &s_wraw[RAW ? buf : 0][RAW ? j : 0][RAW ? ti - P : 0]
                                                           : &unused);
         if (ti == 0)
@@ -688,9 +705,26 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
                 }
                 return;
             }
-            const int hy = h.y & TAB_OFF_MASK, wy = w.y & TAB_OFF_MASK;
-            V v = *reinterpret_cast<const V*>(smem_raw + (w.x + h.x));
-            if (LV > 1) {
+            const int hy = h.y & (DIAG ? TAB_DIAG_MASK : TAB_OFF_MASK), wy = w.y & (DIAG ? TAB_DIAG_MASK : TAB_OFF_MASK);
+            // DIAG: both axes 2-windows -> table (2,2); otherwise the pixels, and the axis that is 2..4 long is
+            // covered by the pixel pairs at its two anchors (dr / dc = one pixel along that axis)
+            const bool lr = DIAG && (h.y & TAB_LVL_BIT) != 0, lc = DIAG && (w.y & TAB_LVL_BIT) != 0;
+            const unsigned char* tb = smem_raw + ((lr && lc) ? HWp * (int)sizeof(V) : 0);
+            V v = *reinterpret_cast<const V*>(tb + (w.x + h.x));
+            if (DIAG) {
+                const int dr = (lr && !lc) ? WP * (int)sizeof(V) : 0, dc = (lc && !lr) ? (int)sizeof(V) : 0;
+                const bool wide = w.x != wy || dr != 0, tall = h.x != hy || dc != 0;
+                const bool any_wide = __any_sync(0xFFFFFFFFu, wide), any_tall = __any_sync(0xFFFFFFFFu, tall);
+                if (any_wide) {
+                    if (wide) v = vmax(v, *reinterpret_cast<const V*>(tb + (wy + h.x + dr)));
+                }
+                if (any_tall) {
+                    if (tall) v = vmax(v, *reinterpret_cast<const V*>(tb + (w.x + hy + dc)));
+                    if (any_wide) {
+                        if (wide && tall) v = vmax(v, *reinterpret_cast<const V*>(tb + (wy + hy + dr + dc)));
+                    }
+                }
+            } else if (LV > 1) {
                 // lookups that coincide with the first one are skipped: warp-uniformly when no lane needs
                 // them (saves the issue slots), per lane otherwise (idle lanes cost no LSU wavefronts)
                 const bool wide = w.x != wy, tall = h.x != hy;
@@ -705,23 +739,30 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
                     }
                 }
             }
+            // DIAG: the four 2-windows per axis need table (2,2); a 5..8-long bin that is 1 thick is scanned
+            const bool mid_ok = !DIAG || (lr && lc);
             if (MID) {
-                const bool mid = ((h.y | w.y) & TAB_MID_BIT) != 0;
+                const bool mid = ((h.y | w.y) & TAB_MID_BIT) != 0 && mid_ok;
                 if (__any_sync(0xFFFFFFFFu, mid)) {
                     if (mid)
-                        v = tab_mid_bin<V>(v, smem_raw, h.x, hy, (h.y & TAB_MID_BIT) != 0, w.x, wy,
+                        v = tab_mid_bin<V>(v, tb, h.x, hy, (h.y & TAB_MID_BIT) != 0, w.x, wy,
                                            (w.y & TAB_MID_BIT) != 0, 2 * WP * (int)sizeof(V), 2 * (int)sizeof(V));
                 }
             }
-            const bool big = ((h.y | w.y) & TAB_BIG_BIT) != 0;
+            const bool big = ((h.y | w.y) & TAB_BIG_BIT) != 0 || (MID && !mid_ok && ((h.y | w.y) & TAB_MID_BIT) != 0);
             if (__any_sync(0xFFFFFFFFu, big)) {
-                if (big)
-                    v = tab_big_bin<V>(tab,
-                                       RAW ? s_hraw[RAW ? cur : 0][RAW ? j : 0][RAW ? ph : 0]
-                                           : tab_decode_range(h.x, hy, LV * HWp, WP, sizeof(V)),
-                                       RAW ? s_wraw[RAW ? cur : 0][RAW ? j : 0][RAW ? pw : 0]
-                                           : tab_decode_range(w.x, wy, HWp, 1, sizeof(V)),
-                                       WP);
+                if (big) {
+                    if (DIAG)
+                        v = tab_big_bin<V>(tab, tab_decode_range_diag(h.x, hy, lr, WP, sizeof(V)),
+                                           tab_decode_range_diag(w.x, wy, lc, 1, sizeof(V)), WP);
+                    else
+                        v = tab_big_bin<V>(tab,
+                                           RAW ? s_hraw[RAW ? cur : 0][RAW ? j : 0][RAW ? ph : 0]
+                                               : tab_decode_range(h.x, hy, LV * HWp, WP, sizeof(V)),
+                                           RAW ? s_wraw[RAW ? cur : 0][RAW ? j : 0][RAW ? pw : 0]
+                                               : tab_decode_range(w.x, wy, HWp, 1, sizeof(V)),
+                                           WP);
+                }
             }
             const unsigned m = (unsigned)((h.y & w.y) >> 31);  // all ones iff the bin is non-empty
             float* o = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.out) + s_ob[cur][j]) + e;
@@ -1757,6 +1798,25 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             else if (smem4 <= 200 * 1024) tcs = 4, minb = 1;
             else if (smem2 <= 200 * 1024) tcs = 2, minb = 1;
             a.pitch = pitch_for(tcs ? tcs : 4);
+            // maps whose four 4-channel tables do not fit: two tables (pixels, 2 x 2 windows) with four
+            // channels per lookup instead of four tables with two
+            const size_t smemd = (size_t)2 * (size_t)((H * pitch_for(4) + 3) & ~3) * 16;
+            if (tcs == 2 && smemd + 40 * 1024 <= 220 * 1024) {
+                a.pitch = pitch_for(4);
+                const bool two = smemd <= budget2;
+#define FRCNN_TABD(PP_, TH_, MB_)                                                                            \
+    do {                                                                                                    \
+        set_groups(4, TH_);                                                                                 \
+        return launch_tab(roi_pool_tab_kernel<PP_, TH_, 4, MB_, false, 2, 1, true, true>, a, smemd, TH_, stream); \
+    } while (0)
+                if (PH == 7) {
+                    if (two) FRCNN_TABD(7, 392, 2);
+                    FRCNN_TABD(7, 784, 1);
+                }
+                if (two) FRCNN_TABD(14, 392, 2);
+                FRCNN_TABD(14, 392, 1);
+#undef FRCNN_TABD
+            }
             if (tcs == 4 && minb == 2) {
                 if (PH == 7) FRCNN_TAB(7, 392, 4, 2, false, 2);
                 set_groups(4, 392);  // 14x14: two adjacent bins per thread
