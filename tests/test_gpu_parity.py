@@ -381,7 +381,7 @@ def test_roi_ops_vs_oracle(F, O, shape):
 
 
 @pytest.mark.parametrize("shape", [(3, 40, 38, 38, 14), (2, 24, 50, 50, 7), (2, 13, 37, 41, 7), (1, 6, 64, 64, 14),
-                                   (1, 5, 120, 90, 7)])
+                                   (1, 5, 120, 90, 7), (1, 9, 64, 64, 7), (1, 5, 60, 66, 7)])
 def test_roi_pool_mean_fused_vs_oracle(F, O, shape):
     """Fused RoIPool + global average against mean(oracle RoIPool) in float64: 1e-5 of the
     largest pooled magnitude (summation order differs from AdaptiveAvgPool2d; every bin value is exact).
@@ -652,6 +652,10 @@ def test_roi_pool_two_table_variants(F, O, shape):
     rois = np.concatenate([rng.integers(0, B, (len(boxes), 1)), boxes], 1).astype(np.float32)
     for scale in (1.0, 0.5):
         assert np.array_equal(N(F.roi_pool_forward(T(feat), T(rois), P, scale)), O.roi_pool(feat, rois, P, scale)), scale
+    # the fused pool + mean kernel has the same two-table form on the large maps
+    full = O.roi_pool(feat, rois, P, 1.0)
+    assert np.abs(N(F.roi_pool_mean(T(feat), T(rois), P, 1.0)) - full.astype(np.float64).mean((2, 3))).max() \
+        <= 1e-5 * np.abs(full).max()
     # grouped (rois_per_image) launch of the same kernel
     order = np.argsort(rois[:, 0], kind="stable")
     per = np.bincount(rois[:, 0].astype(int), minlength=B).min()

@@ -894,14 +894,15 @@ __device__ __forceinline__ void vmean_store(float* o, const float2& s, float n, 
     if (cs > 1) o[1] = s.y / n;
 }
 
-template <int P, int CS, int LV>
-__global__ void __launch_bounds__(PM_THREADS, 2) roi_pool_mean_kernel(RoiArgs a) {
+template <int P, int CS, int LV, bool DIAG = false, int THREADS = PM_THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) roi_pool_mean_kernel(RoiArgs a) {
     typedef typename VecT<CS>::type V;
     constexpr int LPR = P <= 8 ? 8 : 16;  // lanes per RoI
     constexpr int RPW = 32 / LPR;         // RoIs per warp
-    constexpr int NW = PM_THREADS / 32;
-    constexpr int NT = LV * LV;
+    constexpr int NW = THREADS / 32;
+    constexpr int NT = DIAG ? 2 : LV * LV;  // DIAG: pixels + 2 x 2 windows only (see roi_pool_tab_kernel)
     constexpr bool MID = LV == 2 && P == 7;
+    constexpr int OFF_MASK = DIAG ? TAB_DIAG_MASK : TAB_OFF_MASK;
     static_assert(P <= 16, "one lane per bin column");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -917,7 +918,7 @@ __global__ void __launch_bounds__(PM_THREADS, 2) roi_pool_mean_kernel(RoiArgs a)
     if (r_begin + blockIdx.x * NW * RPW >= r_end) return;
     float* raw = reinterpret_cast<float*>(tab + (NT - 1) * HWp);
     stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
-    build_max_tables<V, LV, PM_THREADS>(tab, raw, cs, H, W, WP, HWp, tid);
+    build_max_tables<V, LV, THREADS, DIAG>(tab, raw, cs, H, W, WP, HWp, tid);
     __syncthreads();
 
     const int sub = lane / LPR, l = lane % LPR, le = min(l, P - 1);
@@ -925,39 +926,47 @@ __global__ void __launch_bounds__(PM_THREADS, 2) roi_pool_mean_kernel(RoiArgs a)
     for (int rw = r_begin + (blockIdx.x * NW + warp) * RPW; rw < r_end; rw += stride) {  // warp-uniform
         const RoiBox q = load_roi(a, rw + sub, r_end);
         int hraw, wraw;
-        const int2 row = tab_entry<LV, MID>(le, P, q.y1, q.y2, a.scale, H, WP, LV * HWp, sizeof(V), &hraw);
-        const int2 w = tab_entry<LV, MID>(le, P, q.x1, q.x2, a.scale, W, 1, HWp, sizeof(V), &wraw);
-        const int wy = w.y & TAB_OFF_MASK;
-        const bool wide = w.x != wy;
-        const bool any_wide = __any_sync(0xFFFFFFFFu, wide);
+        const int2 row = tab_entry<LV, MID, DIAG>(le, P, q.y1, q.y2, a.scale, H, WP, LV * HWp, sizeof(V), &hraw);
+        const int2 w = tab_entry<LV, MID, DIAG>(le, P, q.x1, q.x2, a.scale, W, 1, HWp, sizeof(V), &wraw);
+        const int wy = w.y & OFF_MASK;
+        const bool lc = DIAG && (w.y & TAB_LVL_BIT) != 0;
+        const bool wide_ = w.x != wy;
+        const bool any_wide_ = __any_sync(0xFFFFFFFFu, wide_);
         V acc;
         vsplat(acc, 0.f);
 #pragma unroll
         for (int ph = 0; ph < P; ++ph) {
             const int src = sub * LPR + ph;
             const int hx = __shfl_sync(0xFFFFFFFFu, row.x, src), hyf = __shfl_sync(0xFFFFFFFFu, row.y, src);
-            const int hy = hyf & TAB_OFF_MASK;
-            const bool tall = hx != hy;
+            const int hy = hyf & OFF_MASK;
+            // DIAG: table (2,2) when both axes are 2-windows, else the pixels, the 2..4-long axis covered by the
+            // pixel pairs at its two anchors (dr / dc = one pixel along that axis)
+            const bool lr = DIAG && (hyf & TAB_LVL_BIT) != 0;
+            const unsigned char* tb = smem_raw + ((lr && lc) ? HWp * (int)sizeof(V) : 0);
+            const int dr = (lr && !lc) ? WP * (int)sizeof(V) : 0, dc = (lc && !lr) ? (int)sizeof(V) : 0;
+            const bool wide = DIAG ? (wide_ || dr != 0) : wide_, tall = hx != hy || dc != 0;
+            const bool any_wide = DIAG ? __any_sync(0xFFFFFFFFu, wide) : any_wide_;
             const bool any_tall = __any_sync(0xFFFFFFFFu, tall);
-            V v = *reinterpret_cast<const V*>(smem_raw + (w.x + hx));
+            V v = *reinterpret_cast<const V*>(tb + (w.x + hx));
             if (any_wide) {
-                if (wide) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (wy + hx)));
+                if (wide) v = vmax(v, *reinterpret_cast<const V*>(tb + (wy + hx + dr)));
             }
             if (any_tall) {
-                if (tall) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (w.x + hy)));
+                if (tall) v = vmax(v, *reinterpret_cast<const V*>(tb + (w.x + hy + dc)));
                 if (any_wide) {
-                    if (wide && tall) v = vmax(v, *reinterpret_cast<const V*>(smem_raw + (wy + hy)));
+                    if (wide && tall) v = vmax(v, *reinterpret_cast<const V*>(tb + (wy + hy + dr + dc)));
                 }
             }
+            const bool mid_ok = !DIAG || (lr && lc);  // the four 2-windows per axis need table (2,2)
             if (MID) {
-                const bool mid = ((hyf | w.y) & TAB_MID_BIT) != 0;
+                const bool mid = ((hyf | w.y) & TAB_MID_BIT) != 0 && mid_ok;
                 if (__any_sync(0xFFFFFFFFu, mid)) {
                     if (mid)
-                        v = tab_mid_bin<V>(v, smem_raw, hx, hy, (hyf & TAB_MID_BIT) != 0, w.x, wy,
+                        v = tab_mid_bin<V>(v, tb, hx, hy, (hyf & TAB_MID_BIT) != 0, w.x, wy,
                                            (w.y & TAB_MID_BIT) != 0, 2 * WP * (int)sizeof(V), 2 * (int)sizeof(V));
                 }
             }
-            const bool big = ((hyf | w.y) & TAB_BIG_BIT) != 0;
+            const bool big = ((hyf | w.y) & TAB_BIG_BIT) != 0 || (MID && !mid_ok && ((hyf | w.y) & TAB_MID_BIT) != 0);
             if (__any_sync(0xFFFFFFFFu, big)) {
                 const int hr = __shfl_sync(0xFFFFFFFFu, hraw, src);
                 if (big) v = tab_big_bin<V>(tab, hr, wraw, WP);
@@ -1759,25 +1768,30 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
         // (64-wide maps: 45 % of the shared-memory wavefronts were conflicts): pad the pitch by one pixel
         auto pitch_for = [&](int tcs) { return (W * 4 * tcs) % 64 == 0 ? W + 1 : W; };
         if (mean) {  // [K,C] = mean over the bins of RoIPool, never materialising [K,C,P,P]
-            int tcs = 0;
-            if (table_bytes(2, 4, pitch_for(4)) <= 200 * 1024) tcs = 4;
-            else if (table_bytes(2, 2, pitch_for(2)) <= 200 * 1024) tcs = 2;
-            a.pitch = pitch_for(tcs ? tcs : 4);
-            if (!tcs) {
+            // four 4-channel tables when they fit, else two (pixels, 2 x 2 windows: same bytes as four 2-channel
+            // tables, twice the channels per lookup); one CTA per SM when the tables are that large -> 1024 threads
+            a.pitch = pitch_for(4);
+            const size_t smem4 = table_bytes(2, 4, a.pitch);
+            const bool diag = smem4 > 200 * 1024;
+            const size_t smem = diag ? smem4 / 2 : smem4;
+            if (smem > 200 * 1024) {
                 set_error("%s: feature map too large for the fused pool + mean kernel", who);
                 return FRCNN_ERR_UNSUPPORTED;
             }
-            const int per_iter = (PM_THREADS / 32) * (PH <= 8 ? 4 : 2);  // RoIs per CTA pass
-            const int slabs = cdiv(C, tcs);
-            a.CS = tcs;
-            a.groups = std::max(1, std::min(cdiv(per_image_rois, 4 * per_iter), cdiv(8 * sm_count(), B * slabs)));
-            const size_t smem = table_bytes(2, tcs, a.pitch);
+            const int threads = smem > 100 * 1024 ? 1024 : PM_THREADS;
+            const int per_iter = (threads / 32) * (PH <= 8 ? 4 : 2);  // RoIs per CTA pass
+            a.CS = 4;
+            a.groups = std::max(1, std::min(cdiv(per_image_rois, 4 * per_iter), cdiv(8 * sm_count(), B * cdiv(C, 4))));
+#define FRCNN_MEAN(PP_, DG_, TH_) return launch_tab(roi_pool_mean_kernel<PP_, 4, 2, DG_, TH_>, a, smem, TH_, stream)
             if (PH == 7) {
-                if (tcs == 4) return launch_tab(roi_pool_mean_kernel<7, 4, 2>, a, smem, PM_THREADS, stream);
-                return launch_tab(roi_pool_mean_kernel<7, 2, 2>, a, smem, PM_THREADS, stream);
+                if (diag) { if (threads == 1024) FRCNN_MEAN(7, true, 1024); FRCNN_MEAN(7, true, PM_THREADS); }
+                if (threads == 1024) FRCNN_MEAN(7, false, 1024);
+                FRCNN_MEAN(7, false, PM_THREADS);
             }
-            if (tcs == 4) return launch_tab(roi_pool_mean_kernel<14, 4, 2>, a, smem, PM_THREADS, stream);
-            return launch_tab(roi_pool_mean_kernel<14, 2, 2>, a, smem, PM_THREADS, stream);
+            if (diag) { if (threads == 1024) FRCNN_MEAN(14, true, 1024); FRCNN_MEAN(14, true, PM_THREADS); }
+            if (threads == 1024) FRCNN_MEAN(14, false, 1024);
+            FRCNN_MEAN(14, false, PM_THREADS);
+#undef FRCNN_MEAN
         }
         if (argmax) {
             a.pitch = W | 1;
