@@ -121,6 +121,40 @@ def test_nms_superblocks_agree(F, O, superblock):
         assert np.array_equal(N(keep[0, :k]).astype(np.int64), ref[:k])
 
 
+def test_nms_adaptive_superblocks_mixed_keep_rates(F, O):
+    """Long candidate lists (>= 4 super-blocks) let the device cut a later super-block to what an image still
+    needs.  One batch mixes images whose keep rate is high (the cut block is enough), low (cut blocks run out
+    of slack and full-width ones follow), collapsing after the first block (the keep-rate estimate is far off),
+    short lists and an empty one: keep lists must equal the oracle's prefix for every cap."""
+    rng = np.random.default_rng(77)
+    R = 12000
+
+    def boxes_for(n, extent, wlo, whi):
+        c = rng.uniform(0, extent, (n, 2)).astype(np.float32)
+        wh = rng.uniform(wlo, whi, (n, 2)).astype(np.float32)
+        return np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+
+    imgs = [boxes_for(R, 4000, 20, 60),                       # sparse: nearly everything kept
+            boxes_for(R, 300, 40, 120),                       # dense: a few percent kept
+            np.concatenate([boxes_for(2048, 4000, 20, 60),    # sparse head, then near-duplicates of one box
+                            np.tile(np.array([[10, 10, 50, 50]], np.float32), (R - 2048, 1))
+                            + rng.uniform(0, 1, (R - 2048, 4)).astype(np.float32)]),
+            boxes_for(R, 900, 30, 90), boxes_for(700, 500, 30, 90), np.zeros((0, 4), np.float32)]
+    n_sel = np.array([len(b) for b in imgs], np.int32)
+    batch = np.zeros((len(imgs), R, 4), np.float32)
+    for i, b in enumerate(imgs):
+        batch[i, :len(b)] = b
+    refs = [O.nms(b, np.arange(len(b), 0, -1, dtype=np.float32), 0.7) if len(b) else np.zeros(0, np.int64) for b in imgs]
+    for cap in (2000, 1100, 100):  # 2 * cap > 2048: the adaptive schedule; 100: the fixed one
+        keep, n_keep = F.nms_sorted(T(batch), T(n_sel), 0.7, cap)
+        fixed, n_fixed = F.nms_sorted(T(batch), T(n_sel), 0.7, cap, superblock=1024)  # fixed schedule, same answer
+        for i, ref in enumerate(refs):
+            k = int(n_keep[i])
+            assert k == min(cap, ref.shape[0]), (cap, i, k, ref.shape[0])
+            assert np.array_equal(N(keep[i, :k]).astype(np.int64), ref[:k]), (cap, i)
+            assert int(n_fixed[i]) == k and np.array_equal(N(fixed[i, :k]), N(keep[i, :k])), (cap, i)
+
+
 PROPOSAL_CASES = ["proposal_small_train", "proposal_small_overlap", "proposal_small_ties", "proposal_small_pad",
                   "proposal_small_error", "proposal_small_scale", "proposal_600_test", "proposal_600_train"]
 

@@ -12,6 +12,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -505,6 +506,8 @@ topk_sort_dsmem_kernel(const uint32_t* __restrict__ keys_all, const float4* __re
 struct NmsState {
     int n_kept;
     int done;
+    int c_next;  // first sorted position not yet scanned (super-block boundaries are per image, see nms_block_len)
+    int pad;
 };
 
 constexpr int NMS_CB = 256;   // columns per CTA tile (8 warps x 32 lanes)
@@ -516,7 +519,9 @@ struct NmsArgs {
     const int* n_sel;      // [B]
     int row_stride, keep_cap;
     int S;                 // mask row stride = largest super-block
-    int c0, len;           // current super-block: sorted positions [c0, c0+len)
+    int len;               // this launch's super-block: at most `len` sorted positions from the image's c_next
+    int cover_after;       // sum of `len` over the launches that follow this one
+    int adaptive;          // later super-blocks may be cut to what the image still needs (nms_block_len)
     float thr;
     uint32_t* mask;        // [B][S/32][S]
     uint32_t* removed;     // [B][S/32]
@@ -528,13 +533,31 @@ struct NmsArgs {
     int tri_tiles;
 };
 
+// Length of an image's super-block in this launch.  The first block is sized by the host for keep_cap; a
+// later one only has to supply the keep_cap - n_kept boxes still missing, so it is cut to twice what the
+// keep rate so far predicts for them (a 2048-wide mask of which the scan reads 300 columns is the single
+// largest item of the proposal-stress configuration) -- but never below what the remaining launches need
+// this one to cover, so every candidate is still seen in the worst case.  Same value in every CTA of the
+// image: the state is only written by the scan, after all tiles of the launch.
+__device__ __forceinline__ int nms_block_len(const NmsArgs& a, const NmsState& st, int n) {
+    int L = a.len;
+    if (a.adaptive && st.c_next > 0) {
+        const int need = a.keep_cap - st.n_kept;
+        const long long want = 2ll * need * st.c_next / max(st.n_kept, 1);
+        const int must = n - st.c_next - a.cover_after;
+        const long long lo = max((long long)must, max(want, (long long)NMS_CB));
+        if (lo < L) L = (int)((lo + NMS_CB - 1) / NMS_CB * NMS_CB);
+    }
+    return L;
+}
+
 // one mask tile (in-block triangle tile, or suppression of a column block by a chunk of the kept list)
 __device__ __forceinline__ void nms_mask_tile(const NmsArgs& a, int b, const NmsState& st, float4* srow,
                                               float* sarea) {
     const int n = a.n_sel[b];
-    const int c0 = a.c0;
+    const int c0 = st.c_next;
     if (c0 >= n) return;
-    const int c1 = min(c0 + a.len, n);
+    const int c1 = min(c0 + nms_block_len(a, st, n), n);
     const float4* boxes = a.boxes + (size_t)b * a.row_stride;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int t = blockIdx.x;
@@ -656,7 +679,7 @@ __device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const Nm
     __shared__ uint32_t s_kb;
     __shared__ int s_nkept, s_done;
     const int n = a.n_sel[b];
-    const int c0 = a.c0;
+    const int c0 = st.c_next;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (c0 >= n) {
         if (t == 0) {
@@ -665,7 +688,7 @@ __device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const Nm
         }
         return;
     }
-    const int c1 = min(c0 + a.len, n);
+    const int c1 = min(c0 + nms_block_len(a, st, n), n);
     const int ncol = c1 - c0, nw = (ncol + 31) / 32;
     const float4* boxes = a.boxes + (size_t)b * a.row_stride;
     uint32_t* removed = a.removed + (size_t)b * (a.S / 32);
@@ -783,6 +806,7 @@ __device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const Nm
             int done = s_done || (c1 >= n);
             a.state[b].n_kept = s_nkept;
             a.state[b].done = done;
+            a.state[b].c_next = c1;
             a.n_keep[b] = s_nkept;
         }
         return;
@@ -851,6 +875,7 @@ __device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const Nm
         int done = s_done || (c1 >= n);
         a.state[b].n_kept = s_nkept;
         a.state[b].done = done;
+        a.state[b].c_next = c1;
         a.n_keep[b] = s_nkept;
     }
 }
@@ -992,18 +1017,33 @@ static int run_nms_sorted(const float* sorted_boxes, const int32_t* n_sel, int b
     // super-block schedule: the first block is sized for keep_cap (pick_superblock); later blocks double
     // up to the mask stride, so a run that finishes early launches few no-op kernels
     const int s0 = pick_superblock(superblock, row_stride, keep_cap);
-    int c0 = 0, len = s0;
-    while (c0 < row_stride) {
-        a.c0 = c0;
+    std::vector<int> lens;
+    int n_launch = 0, total = 0;
+    for (int len = s0; total < row_stride; ++n_launch) {
+        lens.push_back(len);
+        total += len;
+        if (superblock <= 0) len = std::min(2 * len, a.S);
+    }
+    // Long schedules get one spare launch: its coverage is the slack that lets the device cut later super-blocks
+    // to what an image still needs (nms_block_len); a no-op launch costs ~2 us, a needless 2048-wide mask ~100
+    // (only where the first block is too narrow to finish the job: otherwise launch 2 onwards are no-ops anyway)
+    a.adaptive = superblock <= 0 && n_launch >= 4 && s0 < 2 * keep_cap;
+    if (a.adaptive) {
+        lens.push_back(a.S);
+        ++n_launch;
+        total += a.S;
+    }
+    for (int i = 0, after = total; i < n_launch; ++i) {
+        const int len = lens[i];
+        after -= len;
         a.len = len;
+        a.cover_after = after;
         int ncb = len / NMS_CB;
         a.tri_tiles = 2 * ncb * (ncb + 1);
-        int prev_tiles = c0 > 0 ? ncb * cdiv(keep_cap, NMS_KC) : 0;
+        int prev_tiles = i > 0 ? ncb * cdiv(keep_cap, NMS_KC) : 0;
         dim3 grid(a.tri_tiles + prev_tiles, batch);
         nms_block_kernel<<<grid, NMS_CB, 0, stream>>>(a);
         FRCNN_LAUNCH_CHECK();
-        c0 += len;
-        if (superblock <= 0) len = std::min(2 * len, a.S);
     }
     return FRCNN_OK;
 }

@@ -159,6 +159,7 @@ struct RoiArgs {
     int sampling_ratio, aligned;
     int per_image;   // > 0: RoIs are grouped, rows [b*per_image, (b+1)*per_image) belong to image b
     int pitch;       // table kernels: row pitch of the shared-memory tables (>= W)
+    const int2* ent; // inference table kernels: per-RoI bin geometry [K][2P] from roi_pool_entries_kernel
 };
 
 __device__ __forceinline__ int round_half_away(float v) { return (int)roundf(v); }
@@ -393,6 +394,22 @@ __device__ __forceinline__ RoiAxis load_roi_axis(const RoiArgs& a, int r, int r_
     return q;
 }
 
+// Inference table kernels: the geometry entry `ti` of RoI row r was computed once for all channel slabs by
+// roi_pool_entries_kernel; it travels in the RoiAxis registers (bit patterns).  Only the thread that writes
+// the RoI's output offset (ti == 0) needs the RoI id.
+__device__ __forceinline__ RoiAxis load_roi_entry(const RoiArgs& a, int r, int r_end, int ti, int per_roi) {
+    RoiAxis q;
+    q.k = -1;
+    q.c1 = q.c2 = 0.f;
+    if (r < r_end) {
+        q.k = ti == 0 ? roi_at(a, r) : 0;
+        const int2 e = __ldg(a.ent + (size_t)r * per_roi + ti);
+        q.c1 = __int_as_float(e.x);
+        q.c2 = __int_as_float(e.y);
+    }
+    return q;
+}
+
 // One axis of the bin grid: [lo,hi) of bin `i`, as (byte offset of first corner, byte offset of second
 // corner | flags); `unit` = table elements per step along this axis (row pitch for rows, 1 for columns),
 // `tsel` = table stride per window level along this axis, `esz` = bytes per table element.
@@ -564,6 +581,22 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Bin geometry of every RoI row, once for all channel slabs: ent[r][0..P) = row entries, [P..2P) = column entries,
+// exactly what the table kernel's geometry threads used to compute per CTA (same tab_entry, same constants).
+template <int LV, bool MID, bool DIAG>
+__global__ void __launch_bounds__(256) roi_pool_entries_kernel(RoiArgs a, int2* __restrict__ ent, int P, int esz,
+                                                               int HWp) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= a.K * 2 * P) return;
+    const int r = idx / (2 * P), ti = idx - r * 2 * P;
+    const float* rp = a.rois5 + (size_t)roi_at(a, r) * 5;
+    int unused;
+    ent[idx] = ti < P ? tab_entry<LV, MID, DIAG>(ti, P, __ldg(rp + 2), __ldg(rp + 4), a.scale, a.H, a.pitch, LV * HWp,
+                                                 esz, &unused)
+                      : tab_entry<LV, MID, DIAG>(ti - P, P, __ldg(rp + 1), __ldg(rp + 3), a.scale, a.W, 1, HWp, esz,
+                                                 &unused);
+}
+
 template <int P, int TAB_THREADS, int CS, int MINB, bool ARGMAX, int LV, int BPT = 1, bool PIPE = false,
           bool DIAG = false>
 __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs a) {
@@ -588,6 +621,12 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     // 5..8-long bins through four 2-windows: 7x7 bins only (a 14x14 grid needs a RoI > 56 pixels wide for
     // one, and the extra call site costs the 14x14 fast path registers)
     constexpr bool MID = LV == 2 && P == 7;
+    // inference: the per-RoI geometry is the same for every channel slab, so it is computed once per RoI by
+    // roi_pool_entries_kernel and only copied into the shared-memory buffers here (computing it per CTA was
+    // 28 % of this kernel's instructions on the 7x7 grid)
+    // (not the 14x14 bin-pair kernel: its geometry is 11 % of the instructions, it is bound by the LSU pipe and
+    // HBM instead, and loading the entries measured 5 % slower than computing them there)
+    constexpr bool PRE = PIPE && !ARGMAX && BPT == 1;
     static_assert(RPI * SLOTS == TAB_THREADS && NB * P == TAB_THREADS && ITERS * RPI == NB, "thread mapping");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -613,7 +652,10 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     // table-entry role: axis entry ti (rows first, then columns) of RoIs tj and tj + NB/2 of the batch
     const int tj = tid / (2 * P), ti = tid % (2 * P);
     const bool trow = ti < P;  // this thread computes a row (else a column) entry
-    RoiAxis nx0 = load_roi_axis(a, r0 + tj, r_end, trow), nx1 = load_roi_axis(a, r0 + tj + NB / 2, r_end, trow);
+    auto load_geo = [&](int r) {
+        return PRE ? load_roi_entry(a, r, r_end, ti, 2 * P) : load_roi_axis(a, r, r_end, trow);
+    };
+    RoiAxis nx0 = load_geo(r0 + tj), nx1 = load_geo(r0 + tj + NB / 2);
 
     // staged planes [cs][HW]: where the last-built table will be (LV = 1: a region of their own)
     float* raw = reinterpret_cast<float*>(tab + (LV == 1 ? 1 : NT - 1) * HWp);
@@ -630,7 +672,11 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     const int e = ph * P + pw;
     auto fill_tables = [&](int buf, int j, const RoiAxis& q) {
         int unused;
-        if (trow)
+        if (PRE) {
+            const int2 e = make_int2(__float_as_int(q.c1), __float_as_int(q.c2));
+            if (trow) s_th[buf][j][ti] = e;
+            else s_tw[buf][j][ti - P] = e;
+        } else if (trow)
             s_th[buf][j][ti] = tab_entry<LV, MID, DIAG>(ti, P, q.c1, q.c2, a.scale, H, WP, LV * HWp, sizeof(V),
                                                   RAW ? &s_hraw[RAW ? buf : 0][RAW ? j : 0][RAW ? ti : 0] : &unused);
         else
@@ -642,8 +688,8 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     };
     fill_tables(0, tj, nx0);
     fill_tables(0, tj + NB / 2, nx1);
-    nx0 = load_roi_axis(a, r0 + stride + tj, r_end, trow);
-    nx1 = load_roi_axis(a, r0 + stride + tj + NB / 2, r_end, trow);
+    nx0 = load_geo(r0 + stride + tj);
+    nx1 = load_geo(r0 + stride + tj + NB / 2);
     int cur = 0;
     uint32_t batch = 0;
     if (PIPE) {
@@ -672,8 +718,8 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
         }
         bool prefetched = false;
         auto prefetch_boxes = [&]() {  // boxes of the batch after the next one
-            nx0 = load_roi_axis(a, r0 + 2 * stride + tj, r_end, trow);
-            nx1 = load_roi_axis(a, r0 + 2 * stride + tj + NB / 2, r_end, trow);
+            nx0 = load_geo(r0 + 2 * stride + tj);
+            nx1 = load_geo(r0 + 2 * stride + tj + NB / 2);
             prefetched = true;
         };
         if (!(BPT == 2 && PIPE)) prefetch_boxes();
@@ -1566,12 +1612,14 @@ __global__ void roi_align_backward_kernel(const float* __restrict__ go, RoiArgs 
 struct RoiWs {
     int* perm;
     int* offs;
+    int2* ent;  // [num_rois][2*14] bin geometry of the inference table kernels (roi_pool_entries_kernel)
 };
 
 static size_t roi_layout(Workspace& ws, int batch, int num_rois, RoiWs* out) {
     RoiWs w;
     w.perm = ws.take<int>(num_rois > 0 ? num_rois : 1);
     w.offs = ws.take<int>(batch + 1);
+    w.ent = ws.take<int2>((size_t)(num_rois > 0 ? num_rois : 1) * 28);
     if (out) *out = w;
     return ws.off;
 }
@@ -1636,6 +1684,29 @@ static int launch_tab(KernelT kernel, const RoiArgs& a, size_t smem, int threads
     dim3 grid(a.groups, slabs, a.B);
     kernel<<<grid, threads, smem, stream>>>(a);
     FRCNN_LAUNCH_CHECK();
+    return FRCNN_OK;
+}
+
+// geometry entries for an inference table kernel with CS_ channels per table element (see roi_pool_tab_kernel)
+static int launch_entries(RoiArgs& a, int P, bool diag, int cs, void* workspace, size_t workspace_bytes,
+                          cudaStream_t stream, const char* who) {
+    Workspace ws(workspace, workspace_bytes);
+    RoiWs w;
+    roi_layout(ws, a.B, a.K, &w);
+    if (!ws.ok()) {
+        set_error("%s: workspace too small or misaligned (%zu needed, %zu given)", who, ws.off, workspace_bytes);
+        return FRCNN_ERR_WORKSPACE;
+    }
+    const int HWp = (a.H * a.pitch + 3) & ~3, esz = cs * 4, blocks = cdiv(a.K * 2 * P, 256);
+    if (diag) {
+        if (P == 7) roi_pool_entries_kernel<2, true, true><<<blocks, 256, 0, stream>>>(a, w.ent, P, esz, HWp);
+        else roi_pool_entries_kernel<2, false, true><<<blocks, 256, 0, stream>>>(a, w.ent, P, esz, HWp);
+    } else {
+        if (P == 7) roi_pool_entries_kernel<2, true, false><<<blocks, 256, 0, stream>>>(a, w.ent, P, esz, HWp);
+        else roi_pool_entries_kernel<2, false, false><<<blocks, 256, 0, stream>>>(a, w.ent, P, esz, HWp);
+    }
+    FRCNN_LAUNCH_CHECK();
+    a.ent = w.ent;
     return FRCNN_OK;
 }
 
@@ -1761,6 +1832,10 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
 #define FRCNN_TAB(PP_, TH_, CS_, MB_, AM_, LV_)                                                             \
     do {                                                                                                    \
         set_groups(CS_, TH_);                                                                               \
+        if (!(AM_)) {                                                                                       \
+            const int rc_ = launch_entries(a, PP_, false, CS_, workspace, workspace_bytes, stream, who);   \
+            if (rc_) return rc_;                                                                            \
+        }                                                                                                   \
         return launch_tab(roi_pool_tab_kernel<PP_, TH_, CS_, MB_, AM_, LV_, 1, !(AM_)>, a, table_bytes(LV_, CS_, a.pitch), \
                           TH_, stream);                                                                     \
     } while (0)
@@ -1821,6 +1896,8 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
 #define FRCNN_TABD(PP_, TH_, MB_)                                                                            \
     do {                                                                                                    \
         set_groups(4, TH_);                                                                                 \
+        const int rc_ = launch_entries(a, PP_, true, 4, workspace, workspace_bytes, stream, who);          \
+        if (rc_) return rc_;                                                                                \
         return launch_tab(roi_pool_tab_kernel<PP_, TH_, 4, MB_, false, 2, 1, true, true>, a, smemd, TH_, stream); \
     } while (0)
                 if (PH == 7) {
