@@ -1227,6 +1227,20 @@ __device__ __forceinline__ AlignEntry align_entry(int p, int i, int P, int SR, f
     return e;
 }
 
+// Sample geometry of every RoI row, once for all channel slabs (like roi_pool_entries_kernel): ent[r][0..P*SR) =
+// row samples, [P*SR..2*P*SR) = column samples.  Computing it per CTA was 18 % of the gather's instructions.
+__global__ void __launch_bounds__(256) roi_align_entries_kernel(RoiArgs a, AlignEntry* __restrict__ ent, int P, int SR) {
+    const int EPR = 2 * P * SR;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= a.K * EPR) return;
+    const int r = idx / EPR, e = idx - r * EPR;
+    const float* rp = a.rois5 + (size_t)roi_at(a, r) * 5;
+    const bool is_row = e < P * SR;
+    const int pe = is_row ? e : e - P * SR;
+    ent[idx] = is_row ? align_entry(pe / SR, pe % SR, P, SR, __ldg(rp + 2), __ldg(rp + 4), a.scale, a.aligned, a.H, a.W)
+                      : align_entry(pe / SR, pe % SR, P, SR, __ldg(rp + 1), __ldg(rp + 3), a.scale, a.aligned, a.W, 1);
+}
+
 template <int P, int SR, int AL_THREADS, int MINB>
 __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs a) {
     constexpr int BINS = P * P;
@@ -1243,7 +1257,6 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs
     constexpr int NWARPS = (AL_THREADS + 31) / 32;
     __shared__ __align__(16) AlignEntry s_ent[3][NB][EPR];
     __shared__ size_t s_ob[3][NB];
-    __shared__ RoiBox s_box[2][NB];
     __shared__ __align__(8) uint64_t s_full[3];
     float4* tab = reinterpret_cast<float4*>(smem_raw);
     const int H = a.H, W = a.W, HW = H * W, HWp = (HW + 3) & ~3;
@@ -1256,12 +1269,22 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs
     int r0 = r_begin + blockIdx.x * NB;
     if (r0 >= r_end) return;
     const int tid = threadIdx.x;
-    // boxes: batch 0 and 1 go to shared memory now, batch 2 waits in a register
-    if (tid < NB) {
-        s_box[0][tid] = load_roi(a, r0 + tid, r_end);
-        s_box[1][tid] = load_roi(a, r0 + stride + tid, r_end);
-    }
-    RoiBox nxt = load_roi(a, r0 + 2 * stride + (tid < NB ? tid : 0), r_end);
+    // The entries of a batch are EPR * nb consecutive 8-byte words of a.ent (roi_align_entries_kernel): a thread
+    // carries its (at most EPT) words of the NEXT batch in registers, loaded one batch ahead, and thread j < NB
+    // the id of RoI j for the output offset.
+    const int2* gent = reinterpret_cast<const int2*>(a.ent);
+    int2 pre[EPT];
+    int prek;
+    auto load_entries = [&](int rr) {  // batch starting at RoI row rr
+        const int lim = rr < r_end ? min(NB, r_end - rr) * EPR : 0;
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            const int idx = tid + q * AL_THREADS;
+            pre[q] = idx < lim ? __ldg(gent + (size_t)rr * EPR + idx) : make_int2((int)0x80000000, 0);
+        }
+        prek = (tid < NB && rr + tid < r_end) ? roi_at(a, rr + tid) : 0;
+    };
+    load_entries(r0);
 
     float* raw = reinterpret_cast<float*>(tab + HWp);  // [cs][HW] planes, staged next to the table
     if (tid == 0) {
@@ -1276,39 +1299,33 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs
         v.w = cs > 3 ? raw[3 * HW + p] : 0.f;
         tab[p] = v;
     }
-    __syncthreads();  // s_box[0..1] visible
+    __syncthreads();
 
     const int e = tid % BINS, ej = tid / BINS;
     const int ph = e / P, pw = e % P;
-    auto fill_tables = [&](int buf, int bbuf) {  // geometry buffer `buf` from the boxes in s_box[bbuf]
+    auto fill_tables = [&](int buf) {  // geometry buffer `buf` from the prefetched registers
+        int2* dst = reinterpret_cast<int2*>(&s_ent[buf][0][0]);
 #pragma unroll
         for (int q = 0; q < EPT; ++q) {
             const int idx = tid + q * AL_THREADS;
-            if (idx < NB * EPR) {
-                const int j = idx / EPR, ent = idx % EPR;
-                const RoiBox box = s_box[bbuf][j];
-                const bool is_row = ent < P * SR;
-                const int pe = is_row ? ent : ent - P * SR;
-                s_ent[buf][j][ent] = is_row ? align_entry(pe / SR, pe % SR, P, SR, box.y1, box.y2, a.scale, a.aligned, H, W)
-                                            : align_entry(pe / SR, pe % SR, P, SR, box.x1, box.x2, a.scale, a.aligned, W, 1);
-                if (ent == 0) s_ob[buf][j] = (((size_t)max(box.k, 0) * a.C + c0) * BINS) * sizeof(float);
-            }
+            if (idx < NB * EPR) dst[idx] = pre[q];
         }
+        if (tid < NB) s_ob[buf][tid] = (((size_t)prek * a.C + c0) * BINS) * sizeof(float);
     };
-    fill_tables(0, 0);
+    fill_tables(0);
+    load_entries(r0 + stride);
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&s_full[0]);
     uint32_t batch = 0;
     for (; r0 < r_end; r0 += stride, ++batch) {
         const int cur = (int)(batch % 3u), nbuf = (int)((batch + 1u) % 3u);
-        // every warp has written batch `batch` (hence finished gathering batch - 2 and reading the boxes of
-        // batch `batch`): buffer batch + 1 and the box slot of batch + 2 may be overwritten
+        // every warp has written batch `batch` (hence finished gathering batch - 2): buffer batch + 1 may be
+        // overwritten
         mbar_wait(&s_full[cur], (batch / 3u) & 1u);
-        if (tid < NB) s_box[batch & 1u][tid] = nxt;  // boxes of the batch after next (ordered by the arrive below)
-        fill_tables(nbuf, (int)((batch + 1u) & 1u));  // next batch (ALU only: its boxes are already in shared memory)
+        fill_tables(nbuf);  // next batch: its entries were loaded one batch ago
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&s_full[nbuf]);
-        nxt = load_roi(a, r0 + 3 * stride + (tid < NB ? tid : 0), r_end);
+        load_entries(r0 + 2 * stride);
         const int nb = min(NB, r_end - r0);
         for (int it = 0; it < ITERS; ++it) {
             const int j = it * RPI + ej;
@@ -1321,23 +1338,8 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs
 #pragma unroll
             for (int ix = 0; ix < SR; ++ix) cx[ix] = cols[ix];
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            // the four taps of the previous sample stay in registers; a sample reloads them only if its
-            // pixel quad differs (per lane: idle lanes cost no shared-memory wavefronts).  Neighbouring
-            // samples of a small bin usually share their quad.
-            float4 v1, v2, v3, v4;
-            int qlo = -1, qhi = -1;  // pixel indices (ylo+xlo, yhi+xhi) of the cached quad
-            auto sample = [&](const int2& ry, const int2& rx) -> float4 {
-                const int ylo = ry.x & 0xFFFF, yhi = (ry.x >> 16) & 0x7FFF;
-                const int xlo = rx.x & 0xFFFF, xhi = (rx.x >> 16) & 0x7FFF;
-                // (row offset + column offset) identifies the pixel: column offsets are < one row
-                if (ylo + xlo != qlo || yhi + xhi != qhi) {
-                    v1 = tab[ylo + xlo];
-                    v2 = tab[ylo + xhi];
-                    v3 = tab[yhi + xlo];
-                    v4 = tab[yhi + xhi];
-                    qlo = ylo + xlo;
-                    qhi = yhi + xhi;
-                }
+            float4 v1, v2, v3, v4;  // the pixel quad of the current sample: (ylo,xlo) (ylo,xhi) (yhi,xlo) (yhi,xhi)
+            auto interp = [&](const int2& ry, const int2& rx) -> float4 {
                 const float ly = __int_as_float(ry.y), lx = __int_as_float(rx.y);
                 const float hy = ry.x < 0 ? 0.f : 1.f - ly, hx = rx.x < 0 ? 0.f : 1.f - lx;
                 const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
@@ -1348,16 +1350,86 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs
                 t.w = w1 * v1.w; t.w = t.w + w2 * v2.w; t.w = t.w + w3 * v3.w; t.w = t.w + w4 * v4.w;
                 return t;
             };
+            auto add = [&](const float4& t) {
+                acc.x = acc.x + t.x;
+                acc.y = acc.y + t.y;
+                acc.z = acc.z + t.z;
+                acc.w = acc.w + t.w;
+            };
+            if constexpr (SR == 2) {
+                // The four samples of a bin are visited (0,0) (0,1) (1,1) (1,0): every move changes one axis, and
+                // the next sample's pixel cell along that axis is usually the same or the neighbouring one, so
+                // half of the quad (or all of it) is already in registers.  ~8 loads per bin instead of ~12 with
+                // whole-quad reuse only (16 without any).  The values and the order of the additions are the
+                // reference's -- (0,0) + (0,1) + (1,0) + (1,1) -- so the result is unchanged bit for bit.
+                const int2 ry0 = rows[0], ry1 = rows[1];
+                const int y0l = ry0.x & 0xFFFF, y0h = (ry0.x >> 16) & 0x7FFF, y1l = ry1.x & 0xFFFF, y1h = (ry1.x >> 16) & 0x7FFF;
+                const int x0l = cx[0].x & 0xFFFF, x0h = (cx[0].x >> 16) & 0x7FFF;
+                const int x1l = cx[1].x & 0xFFFF, x1h = (cx[1].x >> 16) & 0x7FFF;
+                v1 = tab[y0l + x0l];
+                v2 = tab[y0l + x0h];
+                v3 = tab[y0h + x0l];
+                v4 = tab[y0h + x0h];
+                add(interp(ry0, cx[0]));
+                if (!(x1l == x0l && x1h == x0h)) {  // columns x0 -> x1 on rows y0
+                    if (x1l == x0h) {
+                        v1 = v2;
+                        v3 = v4;
+                    } else {
+                        v1 = tab[y0l + x1l];
+                        v3 = tab[y0h + x1l];
+                    }
+                    v2 = tab[y0l + x1h];
+                    v4 = tab[y0h + x1h];
+                }
+                add(interp(ry0, cx[1]));
+                if (!(y1l == y0l && y1h == y0h)) {  // rows y0 -> y1 on columns x1
+                    if (y1l == y0h) {
+                        v1 = v3;
+                        v2 = v4;
+                    } else {
+                        v1 = tab[y1l + x1l];
+                        v2 = tab[y1l + x1h];
+                    }
+                    v3 = tab[y1h + x1l];
+                    v4 = tab[y1h + x1h];
+                }
+                const float4 t11 = interp(ry1, cx[1]);
+                if (!(x1l == x0l && x1h == x0h)) {  // columns x1 -> x0 on rows y1
+                    if (x0h == x1l) {
+                        v2 = v1;
+                        v4 = v3;
+                    } else {
+                        v2 = tab[y1l + x0h];
+                        v4 = tab[y1h + x0h];
+                    }
+                    v1 = tab[y1l + x0l];
+                    v3 = tab[y1h + x0l];
+                }
+                add(interp(ry1, cx[0]));
+                add(t11);
+            } else {
+                // the four taps of the previous sample stay in registers; a sample reloads them only if its
+                // pixel quad differs (per lane: idle lanes cost no shared-memory wavefronts)
+                int qlo = -1, qhi = -1;  // pixel indices (ylo+xlo, yhi+xhi) of the cached quad
 #pragma unroll
-            for (int iy = 0; iy < SR; ++iy) {
-                const int2 ry = rows[iy];
+                for (int iy = 0; iy < SR; ++iy) {
+                    const int2 ry = rows[iy];
 #pragma unroll
-                for (int ix = 0; ix < SR; ++ix) {
-                    const float4 t = sample(ry, cx[ix]);
-                    acc.x = acc.x + t.x;
-                    acc.y = acc.y + t.y;
-                    acc.z = acc.z + t.z;
-                    acc.w = acc.w + t.w;
+                    for (int ix = 0; ix < SR; ++ix) {
+                        const int2 rx = cx[ix];
+                        const int ylo = ry.x & 0xFFFF, yhi = (ry.x >> 16) & 0x7FFF;
+                        const int xlo = rx.x & 0xFFFF, xhi = (rx.x >> 16) & 0x7FFF;
+                        if (ylo + xlo != qlo || yhi + xhi != qhi) {
+                            v1 = tab[ylo + xlo];
+                            v2 = tab[ylo + xhi];
+                            v3 = tab[yhi + xlo];
+                            v4 = tab[yhi + xhi];
+                            qlo = ylo + xlo;
+                            qhi = yhi + xhi;
+                        }
+                        add(interp(ry, rx));
+                    }
                 }
             }
             if (valid) {
@@ -1612,14 +1684,15 @@ __global__ void roi_align_backward_kernel(const float* __restrict__ go, RoiArgs 
 struct RoiWs {
     int* perm;
     int* offs;
-    int2* ent;  // [num_rois][2*14] bin geometry of the inference table kernels (roi_pool_entries_kernel)
+    int2* ent;  // [num_rois][<= 56] bin / sample geometry of the inference table kernels (roi_pool_entries_kernel: 2*P
+                // words per RoI, roi_align_entries_kernel: 2*P*SR)
 };
 
 static size_t roi_layout(Workspace& ws, int batch, int num_rois, RoiWs* out) {
     RoiWs w;
     w.perm = ws.take<int>(num_rois > 0 ? num_rois : 1);
     w.offs = ws.take<int>(batch + 1);
-    w.ent = ws.take<int2>((size_t)(num_rois > 0 ? num_rois : 1) * 28);
+    w.ent = ws.take<int2>((size_t)(num_rois > 0 ? num_rois : 1) * 56);
     if (out) *out = w;
     return ws.off;
 }
@@ -1796,11 +1869,23 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
         if (sampling_ratio == 2 && PH == PW && (PH == 7 || PH == 14) && al_smem <= 200 * 1024) {
             a.CS = 4;
             const int minb = al_smem <= 100 * 1024 ? 2 : 1;
-            const int nbatch = PH == 7 ? 56 : 28;  // NB of the kernel template
+            const int nbatch = PH == 7 ? 40 : 20;  // NB of the kernel template
             int slabs = cdiv(C, 4);
             int g = cdiv(cdiv(K, B), 4 * nbatch);
             int want = cdiv(8 * sm_count(), B * slabs);
             a.groups = std::max(1, std::min(g, want));
+            {
+                Workspace ews(workspace, workspace_bytes);
+                RoiWs w;
+                roi_layout(ews, B, K, &w);
+                if (!ews.ok()) {
+                    set_error("%s: workspace too small or misaligned (%zu needed, %zu given)", who, ews.off, workspace_bytes);
+                    return FRCNN_ERR_WORKSPACE;
+                }
+                roi_align_entries_kernel<<<cdiv(K * 2 * PH * 2, 256), 256, 0, stream>>>(a, (AlignEntry*)w.ent, PH, 2);
+                FRCNN_LAUNCH_CHECK();
+                a.ent = w.ent;
+            }
             if (PH == 7)
                 return minb == 2 ? launch_align(roi_align_tab_kernel<7, 2, 392, 2>, a, al_smem, stream)
                                  : launch_align(roi_align_tab_kernel<7, 2, 392, 1>, a, al_smem, stream);
