@@ -969,11 +969,30 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) roi_pool_mean_kernel(
 
     const int sub = lane / LPR, l = lane % LPR, le = min(l, P - 1);
     const int stride = a.groups * NW * RPW;
-    for (int rw = r_begin + (blockIdx.x * NW + warp) * RPW; rw < r_end; rw += stride) {  // warp-uniform
-        const RoiBox q = load_roi(a, rw + sub, r_end);
-        int hraw, wraw;
-        const int2 row = tab_entry<LV, MID, DIAG>(le, P, q.y1, q.y2, a.scale, H, WP, LV * HWp, sizeof(V), &hraw);
-        const int2 w = tab_entry<LV, MID, DIAG>(le, P, q.x1, q.x2, a.scale, W, 1, HWp, sizeof(V), &wraw);
+    // bin geometry from roi_pool_entries_kernel (once per RoI, not once per channel slab): lane l carries the row
+    // entry l and the column entry l of its RoI, loaded one RoI ahead
+    struct Geo {
+        int2 row, col;
+        int k;
+    };
+    auto load_geo = [&](int r) {
+        Geo g;
+        g.row = g.col = make_int2(0, 0);
+        g.k = -1;
+        if (r < r_end) {
+            const int2* e = a.ent + (size_t)r * (2 * P);
+            g.row = __ldg(e + le);
+            g.col = __ldg(e + P + le);
+            g.k = roi_at(a, r);
+        }
+        return g;
+    };
+    const int rw0 = r_begin + (blockIdx.x * NW + warp) * RPW;
+    Geo nxt = load_geo(rw0 + sub);
+    for (int rw = rw0; rw < r_end; rw += stride) {  // warp-uniform
+        const Geo q = nxt;
+        nxt = load_geo(rw + stride + sub);
+        const int2 row = q.row, w = q.col;
         const int wy = w.y & OFF_MASK;
         const bool lc = DIAG && (w.y & TAB_LVL_BIT) != 0;
         const bool wide_ = w.x != wy;
@@ -1014,8 +1033,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) roi_pool_mean_kernel(
             }
             const bool big = ((hyf | w.y) & TAB_BIG_BIT) != 0 || (MID && !mid_ok && ((hyf | w.y) & TAB_MID_BIT) != 0);
             if (__any_sync(0xFFFFFFFFu, big)) {
-                const int hr = __shfl_sync(0xFFFFFFFFu, hraw, src);
-                if (big) v = tab_big_bin<V>(tab, hr, wraw, WP);
+                if (big)
+                    v = DIAG ? tab_big_bin<V>(tab, tab_decode_range_diag(hx, hy, lr, WP, sizeof(V)),
+                                              tab_decode_range_diag(w.x, wy, lc, 1, sizeof(V)), WP)
+                             : tab_big_bin<V>(tab, tab_decode_range(hx, hy, LV * HWp, WP, sizeof(V)),
+                                              tab_decode_range(w.x, wy, HWp, 1, sizeof(V)), WP);
             }
             vacc(acc, v, (unsigned)((hyf & w.y) >> 31));  // empty bins pool to 0
         }
@@ -1942,6 +1964,10 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             const int per_iter = (threads / 32) * (PH <= 8 ? 4 : 2);  // RoIs per CTA pass
             a.CS = 4;
             a.groups = std::max(1, std::min(cdiv(per_image_rois, 4 * per_iter), cdiv(8 * sm_count(), B * cdiv(C, 4))));
+            {
+                const int rc_ = launch_entries(a, PH, diag, 4, workspace, workspace_bytes, stream, who);
+                if (rc_) return rc_;
+            }
 #define FRCNN_MEAN(PP_, DG_, TH_) return launch_tab(roi_pool_mean_kernel<PP_, 4, 2, DG_, TH_>, a, smem, TH_, stream)
             if (PH == 7) {
                 if (diag) { if (threads == 1024) FRCNN_MEAN(7, true, 1024); FRCNN_MEAN(7, true, PM_THREADS); }
