@@ -592,14 +592,21 @@ __device__ __forceinline__ void nms_mask_tile(const NmsArgs& a, int b, const Nms
         }
     } else {
         // suppression by boxes kept in earlier super-blocks
+        // The launch has (len / NMS_CB) * ceil(keep_cap / NMS_KC) of these tiles per image.  They are dealt over
+        // the column blocks the image really has (a cut super-block has fewer): the kept list is then split into
+        // more, shorter chunks, and a chunk is a serial loop of exact IoUs per column thread -- the latency of
+        // the launch when only a few column blocks are live.
         t -= a.tri_tiles;
-        int ncb = a.len / NMS_CB;
-        int cb = t % ncb, kc = t / ncb;
-        int k0 = kc * NMS_KC;
+        const int ntile = (int)gridDim.x - a.tri_tiles;
+        const int ncb = (c1 - c0 + NMS_CB - 1) / NMS_CB;
+        const int nchunk = ntile / ncb;  // >= ceil(keep_cap / NMS_KC), so a chunk has at most NMS_KC rows
+        const int cb = t % ncb, kc = t / ncb;
+        if (kc >= nchunk) return;
+        const int per = (st.n_kept + nchunk - 1) / nchunk;
+        const int k0 = kc * per;
         if (k0 >= st.n_kept) return;
-        int col0 = c0 + cb * NMS_CB;
-        if (col0 >= c1) return;
-        int kn = min(NMS_KC, st.n_kept - k0);
+        const int col0 = c0 + cb * NMS_CB;
+        const int kn = min(per, st.n_kept - k0);
         if (threadIdx.x < kn) {
             float4 v = a.kept_box[(size_t)b * a.keep_cap + k0 + threadIdx.x];
             srow[threadIdx.x] = v;
