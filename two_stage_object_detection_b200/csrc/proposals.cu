@@ -652,6 +652,14 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// named barriers (ids 1..15; 0 is __syncthreads): `count` threads in all, arriving or waiting
+__device__ __forceinline__ void nms_bar_sync(int id, int count) {
+    asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void nms_bar_arrive(int id, int count) {
+    asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 // Greedy resolve of 32 consecutive candidates: `open` = candidates no earlier box removed, D (per lane) =
 // which later candidates of the word lane's candidate suppresses (strictly upper triangular).  Candidate i
 // is kept iff it is open and no KEPT j < i suppresses it.  The serial form is a 32-long dependent chain
@@ -711,103 +719,129 @@ __device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const Nm
         s_done = 0;
     }
     const bool use_ring = nw <= NMS_RING_WORDS;
-    // ---- ring path -------------------------------------------------------------------------------
+    // ---- ring path: resolver warp + helper warps ----------------------------------------------------
+    // Warp 0 walks the words; all it needs of the mask are two words per lane and step -- the diagonal word
+    // (rows 32u.., column word u) and the same rows' word of column u+1 -- which do not depend on earlier
+    // outcomes and are prefetched into registers four steps ahead.  The removed word of step u is
+    //   R[u]  (everything kept up to word u-2, ORed in by the helper warps, see below)
+    //   | the rows of the candidates kept in word u-1 (one REDUX.OR in warp 0, no round trip through the helpers).
+    // Warps 1..7 stream the mask rows through the shared-memory ring and OR the rows of word v's kept candidates
+    // into R[v+2..]; they have the whole of step v+1 to do it.  Hand-offs are named barriers (ids by step
+    // parity): kb_v ready (resolver arrives, helpers sync) and R[..] of step v done (helpers arrive, the
+    // resolver syncs at step v+2).  A step of the serial chain is then resolve + bookkeeping (~400 cycles)
+    // instead of resolve, barrier, OR phase, barrier (~1 500).
     if (use_ring) {
-        // stage of step u: [t][32 words] for t in [u, nw); 16-byte chunk c -> column word u + c/8, part c%8
-        auto issue = [&](int u) {
-            if (u < nw) {
-                uint32_t* dst = ring + (u % NMS_RING_STAGES) * (NMS_RING_WORDS * 32);
-                const int chunks = (nw - u) * 8;
-                for (int c = t; c < chunks; c += NMS_MAX_WORDS) {
-                    const int tw = u + (c >> 3), part = c & 7;
-                    cp_async_16(dst + tw * 32 + part * 4, mask + (size_t)tw * a.S + 32 * u + part * 4);
-                }
-            }
-            cp_async_commit();  // one group per step, empty past the end: the wait count stays uniform
-        };
-#pragma unroll
-        for (int u = 0; u < NMS_RING_DEPTH; ++u) issue(u);
-#ifdef FRCNN_NMS_TIMING
-        long long tq0 = clock64(), tq_wait = 0, tq_res = 0, tq_s2 = 0, tq_or = 0, tq_iss = 0, tq_fix = 0, tq;
-        int tq_steps = 0;
-#define TQ(acc) do { asm volatile("" ::: "memory"); long long n_ = clock64(); asm volatile("" ::: "memory"); acc += n_ - tq; tq = n_; } while (0)
-#else
-#define TQ(acc)
-#endif
-        for (int u = 0; u < nw; ++u) {
-#ifdef FRCNN_NMS_TIMING
-            tq = clock64();
-            ++tq_steps;
-#endif
-            cp_async_wait<NMS_RING_DEPTH - 1>();
-            __syncthreads();  // stage u landed for every thread; R[] of step u-1 complete
-            TQ(tq_wait);
-            const uint32_t* stage = ring + (u % NMS_RING_STAGES) * (NMS_RING_WORDS * 32);
-            if (warp == 0) {
+        __shared__ uint32_t s_kbs[4], s_dns[4];  // per step (mod 4): kept bits, "keep_cap reached"
+        constexpr int NH = NMS_MAX_WORDS - 32;  // helper threads
+        __syncthreads();                        // R[], s_nkept, s_done written
+        if (warp == 0) {
+            auto ld_diag = [&](int u) -> uint32_t {  // rows 32u + lane of column word u, strictly upper triangle
                 const int rowi = 32 * u + lane;
-                const uint32_t D = (rowi < ncol ? stage[u * 32 + lane] : 0u) & ~((2u << lane) - 1u);
-                uint32_t kb = nms_resolve_word(~R[u], D, lane);
-                TQ(tq_fix);
-                int nk = s_nkept;
-                int room = a.keep_cap - nk;
-                int cnt = __popc(kb);
-                int done = 0;
-                if (cnt >= room) {
-                    while (__popc(kb) > room) kb &= ~(0x80000000u >> __clz(kb));
-                    cnt = __popc(kb);
-                    done = 1;
-                }
-                if ((kb >> lane) & 1u) {
-                    int pos = nk + __popc(kb & ((1u << lane) - 1u));
-                    int row = c0 + 32 * u + lane;
-                    a.keep[(size_t)b * a.keep_cap + pos] = row;  // its box is copied after the loop
-                }
-                if (lane == 0) {
-                    s_kb = kb;
-                    s_nkept = nk + cnt;
-                    if (done) s_done = 1;
+                const uint32_t d = (u < nw && rowi < ncol) ? __ldcg(mask + (size_t)u * a.S + rowi) : 0u;
+                return d & ~((2u << lane) - 1u);
+            };
+            auto ld_next = [&](int u) -> uint32_t {  // the same rows in column word u + 1
+                const int rowi = 32 * u + lane;
+                return (u + 1 < nw && rowi < ncol) ? __ldcg(mask + (size_t)(u + 1) * a.S + rowi) : 0u;
+            };
+            uint32_t Dp[4], Np[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                Dp[i] = ld_diag(i);
+                Np[i] = ld_next(i);
+            }
+            int nk = st.n_kept;
+            uint32_t carry = 0u;  // rows of word u-1's kept candidates in column word u
+            bool stop = false;
+            for (int u0 = 0; u0 < nw && !stop; u0 += 4) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int u = u0 + i;
+                    if (u < nw && !stop) {
+                        if (u >= 2) nms_bar_sync(3 + (u & 1), NMS_MAX_WORDS);  // helpers finished word u-2
+                        const uint32_t D = Dp[i], Nw = Np[i];
+                        Dp[i] = ld_diag(u + 4);
+                        Np[i] = ld_next(u + 4);
+                        uint32_t kb = nms_resolve_word(~(R[u] | carry), D, lane);
+                        const int room = a.keep_cap - nk;
+                        int cnt = __popc(kb);
+                        int done = 0;
+                        if (cnt >= room) {
+                            while (__popc(kb) > room) kb &= ~(0x80000000u >> __clz(kb));
+                            cnt = __popc(kb);
+                            done = 1;
+                        }
+                        if (lane == 0) {
+                            s_kbs[u & 3] = kb;
+                            s_dns[u & 3] = (uint32_t)done;  // read by the helpers for THIS step: all of them leave together
+                            if (done) s_done = 1;
+                        }
+                        __threadfence_block();
+                        nms_bar_arrive(1 + (u & 1), NMS_MAX_WORDS);  // kb of word u published
+                        if ((kb >> lane) & 1u) {
+                            const int pos = nk + __popc(kb & ((1u << lane) - 1u));
+                            a.keep[(size_t)b * a.keep_cap + pos] = c0 + 32 * u + lane;  // its box is copied after the loop
+                        }
+                        carry = __reduce_or_sync(0xFFFFFFFFu, ((kb >> lane) & 1u) ? Nw : 0u);
+                        nk += cnt;
+                        stop = done != 0;
+                    }
                 }
             }
-            TQ(tq_res);
-            __syncthreads();
-            TQ(tq_s2);
-            if (s_done) break;
-            // next stage first: it overwrites the stage step u-1 used (its readers passed this step's barriers),
-            // and its issue latency then overlaps the OR phase instead of following it
-            issue(u + NMS_RING_DEPTH);
-            TQ(tq_iss);
-            {
-                // rows of the kept candidates ORed into the removed words of the later column words: four
-                // threads per column word (two 16-byte quarters of its 32 rows each, selected without
-                // predicates), combined by two xor shuffles; 64 column words per pass = one pass
-                const uint32_t kb = s_kb;
-                const int part = t & 3;
+            if (lane == 0) s_nkept = nk;
+        } else {
+            const int ht = t - 32;
+            // stage of step u: [tw][32 words] for tw in [u, nw); 16-byte chunk c -> column word u + c/8, part c%8
+            auto issue = [&](int u) {
+                if (u < nw) {
+                    uint32_t* dst = ring + (u % NMS_RING_STAGES) * (NMS_RING_WORDS * 32);
+                    const int chunks = (nw - u) * 8;
+                    for (int c = ht; c < chunks; c += NH) {
+                        const int tw = u + (c >> 3), part = c & 7;
+                        cp_async_16(dst + tw * 32 + part * 4, mask + (size_t)tw * a.S + 32 * u + part * 4);
+                    }
+                }
+                cp_async_commit();  // one group per step, empty past the end: the wait count stays uniform
+            };
+#pragma unroll
+            for (int u = 0; u < NMS_RING_DEPTH; ++u) issue(u);
+            for (int v = 0; v < nw; ++v) {
+                cp_async_wait<NMS_RING_DEPTH - 1>();
+                nms_bar_sync(5, NH);                             // stage v landed for every helper; R[] of step v-1 written
+                nms_bar_sync(1 + (v & 1), NMS_MAX_WORDS);        // kb of word v
+                const uint32_t kb = s_kbs[v & 3];
+                if (s_dns[v & 3]) break;
+                // next stage first: it overwrites the stage step v-1 used (every helper is past this step's barrier)
+                issue(v + NMS_RING_DEPTH);
+                const uint32_t* stage = ring + (v % NMS_RING_STAGES) * (NMS_RING_WORDS * 32);
+                // rows of the kept candidates ORed into the removed words of column words >= v + 2 (v + 1 is the
+                // resolver's own carry): four threads per column word (two 16-byte quarters of its 32 rows each,
+                // selected without predicates), combined by two xor shuffles
+                const int part = ht & 3;
                 const uint32_t ka = kb >> (8 * part), kc = ka >> 4;
                 const uint32_t a0 = 0u - (ka & 1u), a1 = 0u - ((ka >> 1) & 1u), a2 = 0u - ((ka >> 2) & 1u),
                                a3 = 0u - ((ka >> 3) & 1u);
                 const uint32_t c0_ = 0u - (kc & 1u), c1_ = 0u - ((kc >> 1) & 1u), c2_ = 0u - ((kc >> 2) & 1u),
                                c3_ = 0u - ((kc >> 3) & 1u);
-                for (int tw = u + 1 + (t >> 2); tw - (t >> 2) < nw; tw += NMS_MAX_WORDS / 4) {  // warp-uniform trip count
+                for (int tw = v + 2 + (ht >> 2); tw - (ht >> 2) < nw; tw += NH / 4) {  // warp-uniform trip count
                     uint32_t acc = 0u;
                     if (tw < nw) {
                         const uint4* m = reinterpret_cast<const uint4*>(stage + tw * 32 + part * 8);
-                        const uint4 v = m[0], w = m[1];
-                        acc = (v.x & a0) | (v.y & a1) | (v.z & a2) | (v.w & a3) | (w.x & c0_) | (w.y & c1_) | (w.z & c2_) |
+                        const uint4 x = m[0], w = m[1];
+                        acc = (x.x & a0) | (x.y & a1) | (x.z & a2) | (x.w & a3) | (w.x & c0_) | (w.y & c1_) | (w.z & c2_) |
                               (w.w & c3_);
                     }
                     acc |= __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
                     acc |= __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
                     if (part == 0 && tw < nw) R[tw] |= acc;
                 }
+                if (v + 2 < nw) {
+                    __threadfence_block();
+                    nms_bar_arrive(3 + (v & 1), NMS_MAX_WORDS);  // R[v+2..] has word v's rows
+                }
             }
-            TQ(tq_or);
+            cp_async_wait<0>();
         }
-#ifdef FRCNN_NMS_TIMING
-        if (t == 0 && b == 0)
-            printf("nms scan c0=%d nw=%d steps=%d total=%lld wait=%lld resolve=%lld sync2=%lld or=%lld issue=%lld fix=%lld kept=%d\n", c0,
-                   nw, tq_steps, clock64() - tq0, tq_wait, tq_res, tq_s2, tq_or, tq_iss, tq_fix, s_nkept);
-#endif
-        cp_async_wait<0>();
         nms_copy_kept_boxes(a, b, boxes, st.n_kept, &s_nkept);
         if (t == 0) {
             int done = s_done || (c1 >= n);
