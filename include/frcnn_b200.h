@@ -201,7 +201,10 @@ int frcnn_roi_head_coords(const float* rois, const int32_t* roi_indices, int32_t
  * out [K,C,PH,PW]; argmax [K,C,PH,PW] int32 (nullable; needed only for backward).
  * rois_per_image: 0 = RoIs in any order (bucketed by their batch index on the device); R > 0 = the
  * caller guarantees K == B*R and rows [b*R,(b+1)*R) belong to image b, as the head builds them
- * (nets/classify.py:38), which skips the bucketing pass.                                         */
+ * (nets/classify.py:38), which skips the bucketing pass.
+ * The workspace (frcnn_roi_workspace_bytes) is needed either way: besides the bucketing arrays it holds
+ * the per-RoI bin / sample geometry that the 7x7 / 14x14 kernels compute once per RoI instead of once
+ * per channel slab.                                                                              */
 size_t frcnn_roi_workspace_bytes(int32_t batch, int32_t num_rois);
 int frcnn_roi_pool_forward(const float* feat, int32_t batch, int32_t channels, int32_t height,
                            int32_t width, const float* rois5, int32_t num_rois, int32_t rois_per_image,
