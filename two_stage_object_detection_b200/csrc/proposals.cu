@@ -753,12 +753,22 @@ __device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const Nm
             int nk = st.n_kept;
             uint32_t carry = 0u;  // rows of word u-1's kept candidates in column word u
             bool stop = false;
+#ifdef FRCNN_NMS_TIMING
+            long long q0 = clock64(), q_wait = 0, q_res = 0, qa;
+#endif
             for (int u0 = 0; u0 < nw && !stop; u0 += 4) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int u = u0 + i;
                     if (u < nw && !stop) {
+#ifdef FRCNN_NMS_TIMING
+                        qa = clock64();
+#endif
                         if (u >= 2) nms_bar_sync(3 + (u & 1), NMS_MAX_WORDS);  // helpers finished word u-2
+#ifdef FRCNN_NMS_TIMING
+                        q_wait += clock64() - qa;
+                        qa = clock64();
+#endif
                         const uint32_t D = Dp[i], Nw = Np[i];
                         Dp[i] = ld_diag(u + 4);
                         Np[i] = ld_next(u + 4);
@@ -785,10 +795,17 @@ __device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const Nm
                         carry = __reduce_or_sync(0xFFFFFFFFu, ((kb >> lane) & 1u) ? Nw : 0u);
                         nk += cnt;
                         stop = done != 0;
+#ifdef FRCNN_NMS_TIMING
+                        q_res += clock64() - qa;
+#endif
                     }
                 }
             }
             if (lane == 0) s_nkept = nk;
+#ifdef FRCNN_NMS_TIMING
+            if (lane == 0 && b == 0 && c0 == 0)
+                printf("nms resolver nw=%d total=%lld wait_helpers=%lld resolve=%lld kept=%d\n", nw, clock64() - q0, q_wait, q_res, nk);
+#endif
         } else {
             const int ht = t - 32;
             // stage of step u: [tw][32 words] for tw in [u, nw); 16-byte chunk c -> column word u + c/8, part c%8
@@ -805,14 +822,29 @@ __device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const Nm
             };
 #pragma unroll
             for (int u = 0; u < NMS_RING_DEPTH; ++u) issue(u);
+#ifdef FRCNN_NMS_TIMING
+            long long h_stage = 0, h_kb = 0, h_iss = 0, h_or = 0, ha;
+#endif
             for (int v = 0; v < nw; ++v) {
+#ifdef FRCNN_NMS_TIMING
+                ha = clock64();
+#endif
                 cp_async_wait<NMS_RING_DEPTH - 1>();
                 nms_bar_sync(5, NH);                             // stage v landed for every helper; R[] of step v-1 written
+#ifdef FRCNN_NMS_TIMING
+                h_stage += clock64() - ha; ha = clock64();
+#endif
                 nms_bar_sync(1 + (v & 1), NMS_MAX_WORDS);        // kb of word v
+#ifdef FRCNN_NMS_TIMING
+                h_kb += clock64() - ha; ha = clock64();
+#endif
                 const uint32_t kb = s_kbs[v & 3];
                 if (s_dns[v & 3]) break;
                 // next stage first: it overwrites the stage step v-1 used (every helper is past this step's barrier)
                 issue(v + NMS_RING_DEPTH);
+#ifdef FRCNN_NMS_TIMING
+                h_iss += clock64() - ha; ha = clock64();
+#endif
                 const uint32_t* stage = ring + (v % NMS_RING_STAGES) * (NMS_RING_WORDS * 32);
                 // rows of the kept candidates ORed into the removed words of column words >= v + 2 (v + 1 is the
                 // resolver's own carry): four threads per column word (two 16-byte quarters of its 32 rows each,
@@ -839,7 +871,14 @@ __device__ __forceinline__ void nms_scan_image(const NmsArgs& a, int b, const Nm
                     __threadfence_block();
                     nms_bar_arrive(3 + (v & 1), NMS_MAX_WORDS);  // R[v+2..] has word v's rows
                 }
+#ifdef FRCNN_NMS_TIMING
+                h_or += clock64() - ha;
+#endif
             }
+#ifdef FRCNN_NMS_TIMING
+            if (t == 32 && b == 0 && c0 == 0)
+                printf("nms helpers stage_wait=%lld kb_wait=%lld issue=%lld or=%lld\n", h_stage, h_kb, h_iss, h_or);
+#endif
             cp_async_wait<0>();
         }
         nms_copy_kept_boxes(a, b, boxes, st.n_kept, &s_nkept);
@@ -1289,7 +1328,9 @@ int frcnn_proposals(const frcnn_proposal_params* p, const frcnn_anchor_spec* anc
     rc = run_nms_sorted(w.sorted, w.n_sel, B, rows, p->nms_thresh, p->n_post_nms, p->nms_superblock, w.keep,
                         w.n_keep, w.nms_ws, w.nms_bytes, stream);
     if (rc) return rc;
-    finalize_kernel<<<B, 256, 0, stream>>>((const float4*)w.sorted, w.order, w.n_sel, w.keep, w.n_keep, rows,
+    // one CTA per image (the status flag is a CTA-wide OR); two dependent L2 round trips per row, so as many rows
+    // in flight as the CTA can hold
+    finalize_kernel<<<B, p->n_post_nms > 512 ? 1024 : (p->n_post_nms > 256 ? 512 : 256), 0, stream>>>((const float4*)w.sorted, w.order, w.n_sel, w.keep, w.n_keep, rows,
                                            p->n_post_nms, (float4*)rois, roi_src, n_keep, status);
     FRCNN_LAUNCH_CHECK();
     return FRCNN_OK;
