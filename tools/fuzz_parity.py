@@ -139,6 +139,31 @@ def check_proposals(rng, it):
         assert np.array_equal(N(rois[b]), ref[b]) and np.array_equal(N(src[b]).astype(np.int64), ref_src[b]), tag + f" b={b}"
 
 
+def check_long_nms(rng, it):
+    """Long score-ordered candidate lists (several super-blocks; the adaptive schedule when 2 * cap > 2048) with
+    random density, i.e. keep rates from a few percent to nearly all, images of different lengths in one batch."""
+    if it % 8:
+        return
+    B = int(rng.integers(1, 4))
+    R = int(rng.integers(2500, 14000))
+    cap = int(rng.choice([300, 1100, 2000, 3000]))
+    thr = float(rng.choice([0.5, 0.7]))
+    n_sel = rng.integers(R // 3, R + 1, B).astype(np.int32)
+    batch = np.zeros((B, R, 4), np.float32)
+    refs = []
+    for b in range(B):
+        extent = float(rng.choice([200, 600, 2000, 6000]))
+        bx = rand_boxes(rng, int(n_sel[b]), extent, 10, 120)
+        batch[b, :n_sel[b]] = bx
+        refs.append(O.nms(bx, np.arange(len(bx), 0, -1, dtype=np.float32), thr))
+    keep, n_keep = F.nms_sorted(T(batch), T(n_sel), thr, cap)
+    for b in range(B):
+        k = int(n_keep[b])
+        tag = f"long nms it={it} B={B} R={R} cap={cap} thr={thr} b={b}"
+        assert k == min(cap, len(refs[b])), tag + f" count {k} vs {len(refs[b])}"
+        assert np.array_equal(N(keep[b, :k]).astype(np.int64), refs[b][:k]), tag
+
+
 def check_detections(rng, it):
     B, R, C = int(rng.integers(1, 4)), int(rng.integers(1, 700)), int(rng.integers(1, 30))
     boxes = np.stack([rand_boxes(rng, R, 300, 5, 150) for _ in range(B)])
@@ -171,7 +196,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
-    checks = [check_roi, check_targets, check_proposals, check_detections]
+    checks = [check_roi, check_targets, check_proposals, check_detections, check_long_nms]
     counts = {c.__name__: 0 for c in checks}
     for it in range(args.iters):
         for c in checks:
