@@ -943,6 +943,23 @@ def test_ddp_training_step_two_gpus():
     assert "ddp ok" in out.stdout
 
 
+def test_sharded_inference_equals_single_gpu():
+    """images sharded over two ranks + one NCCL all-gather of the detections == the single-GPU run,
+    bit for bit (skipped on a single-GPU box; tools/sharded_inference_check.py)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29534",
+                          os.path.join(root, "tools", "sharded_inference_check.py")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "sharded ok" in out.stdout
+
+
 # ------------------------------------------------------------------------------------------------
 # after the head (SURVEY 8f-3)
 # ------------------------------------------------------------------------------------------------
