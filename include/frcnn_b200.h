@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FRCNN_ABI_VERSION 1
+#define FRCNN_ABI_VERSION 2
 
 typedef void* frcnn_stream_t; /* cudaStream_t */
 
@@ -53,6 +53,10 @@ int frcnn_abi_version(void);
 const char* frcnn_last_error(void);
 /* sm count / compute capability of the current device (host-side query) */
 int frcnn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Measurement hooks (bench.py): kernels launched by this library in this process so far, and the template
+ * instance the last RoI forward call of the calling thread picked (e.g. "roi_pool_tab_kernel<14,392,4,2,...>"). */
+uint64_t frcnn_launch_count(void);
+const char* frcnn_last_roi_kernel(void);
 
 /* How anchors reach a kernel: either an explicit [N,4] tensor, or generated in registers from the
  * base anchors (utils/basic_anchors.py:27-57: anchor[(y*W+x)*A+a] = base[a] + (x*s, y*s, x*s, y*s)). */
@@ -230,9 +234,11 @@ int frcnn_roi_align_mean_forward(const float* feat, int32_t batch, int32_t chann
                                  int32_t pooled_h, int32_t pooled_w, float spatial_scale,
                                  int32_t sampling_ratio, int32_t aligned, float* out, void* workspace,
                                  size_t workspace_bytes, frcnn_stream_t stream);
-/* grad_in [B,C,H,W] must be zero-initialised by the caller.                                     */
+/* Backward of torchvision RoIPool w.r.t. the features (the gradient the head's loss sends into the
+ * extractor through nets/classify.py:43).  grad_in [B,C,H,W] must be zero-initialised by the caller; RoIs
+ * whose batch index is outside [0,batch) contribute nothing.                                       */
 int frcnn_roi_pool_backward(const float* grad_out, const int32_t* argmax, const float* rois5,
-                            int32_t num_rois, int32_t channels, int32_t height, int32_t width,
+                            int32_t num_rois, int32_t batch, int32_t channels, int32_t height, int32_t width,
                             int32_t pooled_h, int32_t pooled_w, float* grad_in, frcnn_stream_t stream);
 /* torchvision roi_align forward (BASELINE.json RoIAlign 7x7 configuration).                      */
 int frcnn_roi_align_forward(const float* feat, int32_t batch, int32_t channels, int32_t height,
@@ -240,7 +246,8 @@ int frcnn_roi_align_forward(const float* feat, int32_t batch, int32_t channels, 
                             int32_t pooled_h, int32_t pooled_w, float spatial_scale, int32_t sampling_ratio,
                             int32_t aligned, float* out, void* workspace, size_t workspace_bytes,
                             frcnn_stream_t stream);
-int frcnn_roi_align_backward(const float* grad_out, const float* rois5, int32_t num_rois,
+/* Backward of torchvision roi_align w.r.t. the features; grad_in [B,C,H,W] zero-initialised by the caller. */
+int frcnn_roi_align_backward(const float* grad_out, const float* rois5, int32_t num_rois, int32_t batch,
                              int32_t channels, int32_t height, int32_t width, int32_t pooled_h,
                              int32_t pooled_w, float spatial_scale, int32_t sampling_ratio,
                              int32_t aligned, float* grad_in, frcnn_stream_t stream);

@@ -13,7 +13,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FRCNN_B200_LIB") or os.path.join(_PKG, "libfrcnn_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 ERR_UNSUPPORTED = -4  # FRCNN_ERR_UNSUPPORTED
 MAX_BASE_ANCHORS = 64
 
@@ -58,6 +58,8 @@ SIGNATURES = {
     "frcnn_abi_version": (_I, []),
     "frcnn_last_error": (C.c_char_p, []),
     "frcnn_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "frcnn_launch_count": (C.c_uint64, []),
+    "frcnn_last_roi_kernel": (C.c_char_p, []),
     "frcnn_base_anchors": (_I, [C.POINTER(_F), C.POINTER(_F), _I, C.POINTER(_F), _I, _P, _P]),
     "frcnn_shifted_anchors": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "frcnn_loc2bbox": (_I, [_P, _P, _L, _I, _P, _P]),
@@ -86,9 +88,9 @@ SIGNATURES = {
     "frcnn_roi_align_mean_workspace_bytes": (_Z, [_I, _I]),
     "frcnn_roi_align_mean_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _F, _I, _I, _P, _P, _Z, _P]),
     "frcnn_roi_pool_mean_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _F, _P, _P, _Z, _P]),
-    "frcnn_roi_pool_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "frcnn_roi_pool_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "frcnn_roi_align_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _F, _I, _I, _P, _P, _Z, _P]),
-    "frcnn_roi_align_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P]),
+    "frcnn_roi_align_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P]),
 }
 
 _lib = None
@@ -168,6 +170,16 @@ def f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
+
+
+def launch_count() -> int:
+    """Kernels this library has launched in this process (bench.py's gpu_launches)."""
+    return int(load().frcnn_launch_count())
+
+
+def last_roi_kernel() -> str:
+    """Template instance the last RoI forward call picked (bench.py's roofline.kernel)."""
+    return load().frcnn_last_roi_kernel().decode("utf-8", "replace")
 
 
 def device_info():

@@ -4,6 +4,11 @@
 #include <algorithm>
 #include <string.h>
 
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace frcnn {
@@ -14,6 +19,31 @@ void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static std::mutex g_smem_mu;
+static std::map<std::pair<int, const void*>, size_t> g_smem_set;
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(g_smem_mu);
+    size_t& have = g_smem_set[std::make_pair(dev, func)];
+    if (bytes <= have) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
+
+static thread_local char g_roi_kernel[160] = "";
+void note_roi_kernel(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_roi_kernel, sizeof(g_roi_kernel), fmt, ap);
     va_end(ap);
 }
 
@@ -211,6 +241,8 @@ extern "C" {
 
 int frcnn_abi_version(void) { return FRCNN_ABI_VERSION; }
 const char* frcnn_last_error(void) { return g_err; }
+uint64_t frcnn_launch_count(void) { return (uint64_t)g_launches.load(std::memory_order_relaxed); }
+const char* frcnn_last_roi_kernel(void) { return g_roi_kernel; }
 
 int frcnn_device_info(int* sm, int* major, int* minor) {
     int dev = 0;

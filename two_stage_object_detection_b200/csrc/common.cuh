@@ -31,7 +31,22 @@ void set_error(const char* fmt, ...);
         }                                                                                     \
     } while (0)
 
-#define FRCNN_LAUNCH_CHECK() FRCNN_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this: the counter is what bench.py reports as
+// `gpu_launches` (frcnn_launch_count), counted, not computed
+void count_launch();
+#define FRCNN_LAUNCH_CHECK()            \
+    do {                                \
+        ::frcnn::count_launch();        \
+        FRCNN_CUDA(cudaGetLastError()); \
+    } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize, set once per (device, kernel) -- and again only when a
+// launch needs more than any earlier one did -- instead of a driver call in front of every launch
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes);
+#define FRCNN_SMEM(kernel, bytes) FRCNN_CUDA(::frcnn::ensure_dynamic_smem((const void*)(kernel), (size_t)(bytes)))
+
+// name of the gather kernel variant the last RoI forward call picked (frcnn_last_roi_kernel)
+void note_roi_kernel(const char* fmt, ...);
 
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -191,7 +191,7 @@ int frcnn_nms_by_class(const float* boxes, const float* scores, const int64_t* c
     a.keep = keep;
     a.n_keep = n_keep;
     const size_t smem = det_nms_smem(rows > 0 ? rows : 1);
-    FRCNN_CUDA(cudaFuncSetAttribute(nms_by_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FRCNN_SMEM(nms_by_class_kernel, smem);
     nms_by_class_kernel<<<batch, DN_THREADS, smem, (cudaStream_t)stream>>>(a);
     FRCNN_LAUNCH_CHECK();
     return FRCNN_OK;

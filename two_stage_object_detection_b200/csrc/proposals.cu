@@ -1141,12 +1141,11 @@ static int run_topk(const uint32_t* keys, const float* boxes, int batch, int n, 
     const int seg = (n + TK_CL - 1) / TK_CL;
     const size_t dsmem = TK_SMEM + (size_t)2 * seg * sizeof(uint2);
     if (dsmem <= 200 * 1024 && k_cap <= n) {  // keys stay in distributed shared memory
-        FRCNN_CUDA(cudaFuncSetAttribute(topk_sort_dsmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)dsmem));
+        FRCNN_SMEM(topk_sort_dsmem_kernel, dsmem);
         topk_sort_dsmem_kernel<<<batch * TK_CL, TK_THREADS, dsmem, stream>>>(
             keys, (const float4*)boxes, n, k_cap, seg, order, n_sel, (float4*)sorted_boxes);
     } else {  // global-memory ping-pong buffers
-        FRCNN_CUDA(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TK_SMEM));
+        FRCNN_SMEM(topk_sort_kernel, TK_SMEM);
         topk_sort_kernel<<<batch * TK_CL, TK_THREADS, TK_SMEM, stream>>>(keys, (const float4*)boxes, n, k_cap, wk, wi,
                                                                          order, n_sel, (float4*)sorted_boxes);
     }

@@ -38,14 +38,19 @@ __global__ void roi_head_coords_kernel(const float4* __restrict__ rois, const in
 // ---------------------------------------------------------------------------------------------
 constexpr int BUCKET_THREADS = 1024;
 
+// RoIs whose batch index is outside [0,B) belong to no image: they are listed after the valid ones,
+// perm[offs[B] .. offs[B] + offs[B+1]), and roi_fill_dropped_kernel gives their output rows the value the
+// direct kernels give them (0, argmax -1) instead of leaving them unwritten.
 __global__ void __launch_bounds__(BUCKET_THREADS)
 roi_bucket_kernel(const float* __restrict__ rois5, int K, int B, int* __restrict__ perm, int* __restrict__ offs) {
     extern __shared__ int sb[];  // cnt[B], cur[B]
     int* cnt = sb;
     int* cur = sb + B;
     __shared__ int chunk_tot[BUCKET_THREADS];
+    __shared__ int s_total, s_bad;
     const int tid = threadIdx.x;
     for (int i = tid; i < B; i += BUCKET_THREADS) cnt[i] = 0;
+    if (tid == 0) s_bad = 0;
     __syncthreads();
     for (int k = tid; k < K; k += BUCKET_THREADS) {
         int b = (int)__ldg(rois5 + (size_t)k * 5);
@@ -67,6 +72,7 @@ roi_bucket_kernel(const float* __restrict__ rois5, int K, int B, int* __restrict
             run += t;
         }
         offs[B] = run;
+        s_total = run;
     }
     __syncthreads();
     int run = chunk_tot[tid];
@@ -79,6 +85,22 @@ roi_bucket_kernel(const float* __restrict__ rois5, int K, int B, int* __restrict
     for (int k = tid; k < K; k += BUCKET_THREADS) {
         int b = (int)__ldg(rois5 + (size_t)k * 5);
         if (b >= 0 && b < B) perm[atomicAdd(&cur[b], 1)] = k;
+        else perm[s_total + atomicAdd(&s_bad, 1)] = k;
+    }
+    __syncthreads();
+    if (tid == 0) offs[B + 1] = s_bad;
+}
+
+__global__ void __launch_bounds__(256)
+roi_fill_dropped_kernel(const int* __restrict__ perm, const int* __restrict__ offs, int B, size_t per_roi,
+                        float* __restrict__ out, int* __restrict__ argmax) {
+    const int base = offs[B], n_bad = offs[B + 1];
+    for (int i = blockIdx.x; i < n_bad; i += gridDim.x) {
+        const size_t o = (size_t)perm[base + i] * per_roi;
+        for (size_t j = threadIdx.x; j < per_roi; j += 256) {
+            out[o + j] = 0.f;
+            if (argmax) argmax[o + j] = -1;
+        }
     }
 }
 
@@ -1087,8 +1109,8 @@ __global__ void roi_pool_direct_kernel(RoiArgs a) {
 }
 
 __global__ void roi_pool_backward_kernel(const float* __restrict__ go, const int* __restrict__ argmax,
-                                         const float* __restrict__ rois5, size_t total, int C, int HW, int PP,
-                                         float* __restrict__ gi) {
+                                         const float* __restrict__ rois5, size_t total, int B, int C, int HW,
+                                         int PP, float* __restrict__ gi) {
     size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= total) return;
     int am = __ldg(argmax + o);
@@ -1097,6 +1119,7 @@ __global__ void roi_pool_backward_kernel(const float* __restrict__ go, const int
     int c = kc % C;
     size_t k = kc / C;
     int b = (int)__ldg(rois5 + k * 5);
+    if (b < 0 || b >= B || am >= HW) return;  // a RoI of no image contributes nothing (its forward row is 0 / -1)
     atomicAdd(gi + ((size_t)b * C + c) * HW + am, __ldg(go + o));
 }
 
@@ -1713,7 +1736,7 @@ struct RoiWs {
 static size_t roi_layout(Workspace& ws, int batch, int num_rois, RoiWs* out) {
     RoiWs w;
     w.perm = ws.take<int>(num_rois > 0 ? num_rois : 1);
-    w.offs = ws.take<int>(batch + 1);
+    w.offs = ws.take<int>(batch + 2);
     w.ent = ws.take<int2>((size_t)(num_rois > 0 ? num_rois : 1) * 56);
     if (out) *out = w;
     return ws.off;
@@ -1751,7 +1774,7 @@ static int check_roi_common(const float* feat, int B, int C, int H, int W, const
 
 template <typename KernelT>
 static int launch_staged(KernelT kernel, const RoiArgs& a, size_t smem, cudaStream_t stream) {
-    FRCNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FRCNN_SMEM(kernel, smem);
     int slabs = cdiv(a.C, a.CS);
     FRCNN_CHECK_ARG(slabs <= 65535 && a.B <= 65535, "roi op: too many channel slabs / images");
     dim3 grid(a.groups, slabs, a.B);
@@ -1762,7 +1785,7 @@ static int launch_staged(KernelT kernel, const RoiArgs& a, size_t smem, cudaStre
 
 template <typename KernelT>
 static int launch_align(KernelT kernel, const RoiArgs& a, size_t smem, cudaStream_t stream) {
-    FRCNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FRCNN_SMEM(kernel, smem);
     int slabs = cdiv(a.C, 4);
     FRCNN_CHECK_ARG(slabs <= 65535 && a.B <= 65535, "roi op: too many channel slabs / images");
     dim3 grid(a.groups, slabs, a.B);
@@ -1773,7 +1796,7 @@ static int launch_align(KernelT kernel, const RoiArgs& a, size_t smem, cudaStrea
 
 template <typename KernelT>
 static int launch_tab(KernelT kernel, const RoiArgs& a, size_t smem, int threads, cudaStream_t stream) {
-    FRCNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FRCNN_SMEM(kernel, smem);
     int slabs = cdiv(a.C, a.CS);
     FRCNN_CHECK_ARG(slabs <= 65535 && a.B <= 65535, "roi op: too many channel slabs / images");
     dim3 grid(a.groups, slabs, a.B);
@@ -1878,6 +1901,9 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             return FRCNN_ERR_WORKSPACE;
         }
         roi_bucket_kernel<<<1, BUCKET_THREADS, 2 * B * sizeof(int), stream>>>(rois5, K, B, w.perm, w.offs);
+        FRCNN_LAUNCH_CHECK();
+        roi_fill_dropped_kernel<<<sm_count(), 256, 0, stream>>>(w.perm, w.offs, B, mean ? (size_t)C : (size_t)C * PH * PW,
+                                                               out, argmax);
         FRCNN_LAUNCH_CHECK();
         a.perm = w.perm;
         a.offs = w.offs;
@@ -2125,6 +2151,8 @@ int frcnn_roi_align_mean_forward(const float* feat, int32_t B, int32_t C, int32_
     } else {
         roi_bucket_kernel<<<1, BUCKET_THREADS, 2 * B * sizeof(int), stream>>>(rois5, K, B, w.perm, w.offs);
         FRCNN_LAUNCH_CHECK();
+        roi_fill_dropped_kernel<<<sm_count(), 256, 0, stream>>>(w.perm, w.offs, B, (size_t)C, out, nullptr);
+        FRCNN_LAUNCH_CHECK();
         a.perm = w.perm;
         a.offs = w.offs;
     }
@@ -2134,35 +2162,37 @@ int frcnn_roi_align_mean_forward(const float* feat, int32_t B, int32_t C, int32_
     FRCNN_CHECK_ARG(slabs <= 65535, "%s: too many channel slabs", who);
     const int nw = AM_THREADS / 32;
     a.groups = std::max(1, std::min(cdiv(cdiv(K, B), 8 * nw), cdiv(8 * sm_count(), B * slabs)));
-    FRCNN_CUDA(cudaFuncSetAttribute(roi_align_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FRCNN_SMEM(roi_align_mean_kernel, smem);
     roi_align_mean_kernel<<<dim3(a.groups, slabs, B), AM_THREADS, smem, stream>>>(a, rec);
     FRCNN_LAUNCH_CHECK();
     return FRCNN_OK;
 }
 
 int frcnn_roi_pool_backward(const float* grad_out, const int32_t* argmax, const float* rois5, int32_t K,
-                            int32_t C, int32_t H, int32_t W, int32_t PH, int32_t PW, float* grad_in,
+                            int32_t B, int32_t C, int32_t H, int32_t W, int32_t PH, int32_t PW, float* grad_in,
                             frcnn_stream_t stream) {
-    FRCNN_CHECK_ARG(K >= 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0, "frcnn_roi_pool_backward: bad shape");
+    FRCNN_CHECK_ARG(K >= 0 && B > 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0,
+                    "frcnn_roi_pool_backward: bad shape");
     if (K == 0) return FRCNN_OK;
     FRCNN_CHECK_ARG(grad_out && argmax && rois5 && grad_in, "frcnn_roi_pool_backward: null pointer");
     size_t total = (size_t)K * C * PH * PW;
     roi_pool_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        grad_out, argmax, rois5, total, C, H * W, PH * PW, grad_in);
+        grad_out, argmax, rois5, total, B, C, H * W, PH * PW, grad_in);
     FRCNN_LAUNCH_CHECK();
     return FRCNN_OK;
 }
 
-int frcnn_roi_align_backward(const float* grad_out, const float* rois5, int32_t K, int32_t C, int32_t H,
+int frcnn_roi_align_backward(const float* grad_out, const float* rois5, int32_t K, int32_t B, int32_t C, int32_t H,
                              int32_t W, int32_t PH, int32_t PW, float scale, int32_t sampling_ratio,
                              int32_t aligned, float* grad_in, frcnn_stream_t stream) {
-    FRCNN_CHECK_ARG(K >= 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0, "frcnn_roi_align_backward: bad shape");
+    FRCNN_CHECK_ARG(K >= 0 && B > 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0,
+                    "frcnn_roi_align_backward: bad shape");
     if (K == 0) return FRCNN_OK;
     FRCNN_CHECK_ARG(grad_out && rois5 && grad_in, "frcnn_roi_align_backward: null pointer");
     RoiArgs a;
     memset(&a, 0, sizeof(a));
     a.rois5 = rois5;
-    a.B = 1 << 30;
+    a.B = B;
     a.C = C;
     a.H = H;
     a.W = W;

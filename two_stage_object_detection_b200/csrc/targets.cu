@@ -471,7 +471,7 @@ int frcnn_anchor_targets(const frcnn_anchor_target_params* p, const frcnn_anchor
     FRCNN_CUDA(cudaMemsetAsync(w.colbest, 0, w.zero_bytes, stream));
     size_t smem = at_smem(p->max_gt);
     if (smem > 48 * 1024)
-        FRCNN_CUDA(cudaFuncSetAttribute(anchor_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FRCNN_SMEM(anchor_iou_kernel, smem);
     dim3 grid(a.tiles, p->batch);
     anchor_iou_kernel<<<grid, AT_THREADS, smem, stream>>>(a);
     FRCNN_LAUNCH_CHECK();
@@ -512,8 +512,7 @@ int frcnn_proposal_targets(const frcnn_proposal_target_params* p, const float* r
     a.status = status;
     size_t smem = (size_t)p->max_gt * (sizeof(float4) + sizeof(float));
     if (smem > 32 * 1024)
-        FRCNN_CUDA(cudaFuncSetAttribute(proposal_target_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
+        FRCNN_SMEM(proposal_target_kernel, smem);
     proposal_target_kernel<<<p->batch, PT_THREADS, smem, stream>>>(a);
     FRCNN_LAUNCH_CHECK();
     return FRCNN_OK;

@@ -5,12 +5,25 @@ host.  The reference-named per-image wrappers live in ``utils/`` and ``nets/``.
 from __future__ import annotations
 
 import ctypes as C
+import logging
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 
 from . import _lib
+_log = logging.getLogger("two_stage_object_detection_b200")
+_warned = set()
+
+
+def _note_unfused(what: str, why: str) -> None:
+    """A fused kernel did not cover this shape and the (still CUDA, still ours) two-step form ran instead:
+    say so once per call site and shape class, never silently."""
+    if what not in _warned:
+        _warned.add(what)
+        _log.warning("%s: fused kernel not used (%s); running the two-kernel form", what, why)
+
+
 from ._lib import AnchorSpec, AnchorTargetParams, ProposalParams, ProposalTargetParams, check, f32c, ptr
 
 
@@ -389,6 +402,7 @@ def roi_pool_mean(feat, rois5, output_size, spatial_scale=1.0, rois_per_image=0)
                                              float(spatial_scale), out.data_ptr(), ws.data_ptr(), ws.numel(),
                                              _lib.stream_ptr(dev))
     if rc == _lib.ERR_UNSUPPORTED:
+        _note_unfused("roi_pool_mean", lib.frcnn_last_error().decode("utf-8", "replace"))
         return roi_pool_forward(f, r, output_size, spatial_scale, rois_per_image=rois_per_image).mean((2, 3))
     check(rc, "frcnn_roi_pool_mean_forward")
     return out
@@ -412,6 +426,7 @@ def roi_align_mean(feat, rois5, output_size, spatial_scale=1.0, sampling_ratio=-
                                               float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
                                               out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
     if rc == _lib.ERR_UNSUPPORTED:
+        _note_unfused("roi_align_mean", lib.frcnn_last_error().decode("utf-8", "replace"))
         return roi_align_forward(f, r, output_size, spatial_scale, sampling_ratio, aligned,
                                  rois_per_image=rois_per_image).mean((2, 3))
     check(rc, "frcnn_roi_align_mean_forward")
@@ -461,7 +476,7 @@ class _RoIPoolFn(torch.autograd.Function):
         go = f32c(grad_out)
         gi = torch.zeros((B, Cc, H, W), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            check(lib.frcnn_roi_pool_backward(go.data_ptr(), am.data_ptr(), r.data_ptr(), r.shape[0], Cc, H, W,
+            check(lib.frcnn_roi_pool_backward(go.data_ptr(), am.data_ptr(), r.data_ptr(), r.shape[0], B, Cc, H, W,
                                               ctx.ps[0], ctx.ps[1], gi.data_ptr(), _lib.stream_ptr(dev)),
                   "frcnn_roi_pool_backward")
         return gi, None, None, None, None
@@ -487,7 +502,7 @@ class _RoIAlignFn(torch.autograd.Function):
         go = f32c(grad_out)
         gi = torch.zeros((B, Cc, H, W), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            check(lib.frcnn_roi_align_backward(go.data_ptr(), r.data_ptr(), r.shape[0], Cc, H, W, ph, pw, scale,
+            check(lib.frcnn_roi_align_backward(go.data_ptr(), r.data_ptr(), r.shape[0], B, Cc, H, W, ph, pw, scale,
                                                sr, al, gi.data_ptr(), _lib.stream_ptr(dev)),
                   "frcnn_roi_align_backward")
         return gi, None, None, None, None, None, None
@@ -562,6 +577,7 @@ def nms_by_class(boxes: torch.Tensor, scores: torch.Tensor, classes: Optional[to
         check(rc, "frcnn_nms_by_class")
         return keep, n_keep
     # more than 1024 rows per image: the evaluator's own loop (one frcnn_nms per image and class; synchronises)
+    _note_unfused("nms_by_class", f"{R} rows per image > 1024")
     keep.fill_(-1)
     for i in range(B):
         n = R if nv is None else int(nv[i])

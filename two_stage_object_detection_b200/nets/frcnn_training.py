@@ -113,7 +113,9 @@ class FasterRCNNTrainer(torch.nn.Module):
         s2 = sigma ** 2
         diff = torch.abs(gt_loc - pred_loc).float()
         loss = torch.where(diff < (1. / s2), 0.5 * s2 * diff ** 2, diff - 0.5 / s2)
-        return (loss * pos).sum((1, 2)) / (pos.sum((1, 2)) * 4)
+        # select-then-sum like the reference (:222-223): a non-finite target on a row that is NOT selected
+        # (bbox2loc against a zero-width GT gives -inf for every anchor assigned to it) must not reach the sum
+        return torch.where(pos, loss, torch.zeros_like(loss)).sum((1, 2)) / (pos.sum((1, 2)) * 4)
 
     def forward(self, imgs, bboxes, labels, scale=1):
         from torch.nn import functional as TF
@@ -159,4 +161,9 @@ class FasterRCNNTrainer(torch.nn.Module):
         roi_cls_loss = ce2.sum(1) / valid.sum(1)
         losses = [rpn_loc_loss.sum() / n, rpn_cls_loss.sum() / n, roi_loc_loss.sum() / n, roi_cls_loss.sum() / n]
         losses = losses + [sum(losses)]
-        return losses, anchors_pred, classes_pred, classes_score_pred, bb, ll + 1
+        # ground truth as the reference returns it (boxes, labels + 1) in the padded batch layout [n,Gmax,...]:
+        # rows past an image's n_gt are padding, box (0,0,0,0) with class id 0 = background, never a real class
+        # (a calculate_metrics-style consumer must not count them); self.last_n_gt holds the true counts
+        self.last_n_gt = n_gt
+        real = torch.arange(ll.shape[1], device=dev).unsqueeze(0) < n_gt.unsqueeze(1)
+        return losses, anchors_pred, classes_pred, classes_score_pred, bb, torch.where(real, ll + 1, torch.zeros_like(ll))
