@@ -76,6 +76,11 @@ def lib():
             L.oracle_roi_align.restype = None
             L.oracle_roi_align.argtypes = [f32p, i64, i64, i64, i64, f32p, i64, i64, i64,
                                            ctypes.c_float, ctypes.c_int, ctypes.c_int, f32p]
+            L.oracle_roi_pool_backward.restype = None
+            L.oracle_roi_pool_backward.argtypes = [f32p, i32p, f32p, i64, i64, i64, i64, i64, i64, i64, f32p]
+            L.oracle_roi_align_backward.restype = None
+            L.oracle_roi_align_backward.argtypes = [f32p, f32p, i64, i64, i64, i64, i64, i64, i64,
+                                                    ctypes.c_float, ctypes.c_int, ctypes.c_int, f32p]
             L.oracle_max_threads.restype = ctypes.c_int
             L.oracle_set_threads.restype = None
             L.oracle_set_threads.argtypes = [ctypes.c_int]
@@ -451,6 +456,32 @@ def roi_align(feat, rois5, output_size, spatial_scale=1.0, sampling_ratio=-1, al
                            ph, pw, float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
                            _p(out, ctypes.c_float))
     return out
+
+
+def roi_pool_backward(grad_out, argmax, rois5, feat_shape):
+    """torchvision RoIPool backward w.r.t. the features: grad_in[b,c,argmax] += grad_out, in the CPU
+    kernel's sequential order.  feat_shape = (B,C,H,W)."""
+    go = _f32(grad_out)
+    am = np.ascontiguousarray(argmax, dtype=np.int32)
+    r = _f32(rois5).reshape(-1, 5)
+    B, C, H, W = (int(v) for v in feat_shape)
+    gi = np.empty((B, C, H, W), dtype=F32)
+    lib().oracle_roi_pool_backward(_p(go, ctypes.c_float), _p(am, ctypes.c_int32), _p(r, ctypes.c_float),
+                                   r.shape[0], B, C, H, W, go.shape[2], go.shape[3], _p(gi, ctypes.c_float))
+    return gi
+
+
+def roi_align_backward(grad_out, rois5, feat_shape, spatial_scale=1.0, sampling_ratio=-1, aligned=False):
+    """torchvision roi_align backward w.r.t. the features (what autograd computes through
+    torchvision.ops.roi_align): grad * w_i / count onto the four taps of every sample."""
+    go = _f32(grad_out)
+    r = _f32(rois5).reshape(-1, 5)
+    B, C, H, W = (int(v) for v in feat_shape)
+    gi = np.empty((B, C, H, W), dtype=F32)
+    lib().oracle_roi_align_backward(_p(go, ctypes.c_float), _p(r, ctypes.c_float), r.shape[0], B, C, H, W,
+                                    go.shape[2], go.shape[3], float(spatial_scale), int(sampling_ratio),
+                                    int(bool(aligned)), _p(gi, ctypes.c_float))
+    return gi
 
 
 def roi_head_gather(feat, rois, roi_indices, img_size, roi_size=7, spatial_scale=1.0,

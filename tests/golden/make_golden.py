@@ -168,6 +168,16 @@ def gen_proposals():
     proposal_case("proposal_600_train", 38, 38, "train", 0.2, 8)
 
 
+def gen_proposals_large():
+    """The BASELINE configs 4 and 5 at their full sizes through the reference's ProposalCreator:
+    800x800 (N = 22 500, 3 000 -> 300) and the proposal-stress size 1024x1024 (N = 36 864, 30 000 -> 2 000,
+    ~4 s of torchvision CPU nms).  loc std 0.1 keeps enough overlap that NMS needs several thousand candidates
+    to find its 2 000 boxes."""
+    proposal_case("proposal_800_test", 50, 50, "test", 0.2, 21, img=(3, 800, 800))
+    proposal_case("proposal_1024_stress", 64, 64, "test", 0.1, 22, img=(3, 1024, 1024),
+                  limits=dict(n_test_pre_nms=30000, n_test_post_nms=2000))
+
+
 def gen_nms():
     g = torch.Generator().manual_seed(202)
     arrs = {}
@@ -341,6 +351,59 @@ def gen_roi():
          w_score=npy(head.score.weight), b_score=npy(head.score.bias), **outs)
 
 
+def gen_roi_large():
+    """torchvision roi_pool 7x7 / 14x14 and roi_align 7x7 (sampling_ratio 2) on the feature-map sizes of the
+    BASELINE configs (38x38, 50x50, 64x64; C = 8 keeps the fixture small), RoIs in feature coordinates sized
+    like proposals (1 px .. most of the map, some hanging over the border)."""
+    arrs = {}
+    for H in (38, 50, 64):
+        g = torch.Generator().manual_seed(700 + H)
+        feat = torch.randn(2, 8, H, H, generator=g)
+        feat[1] = torch.relu(feat[1])
+        K = 48
+        r = rand_boxes(g, K, H, 1.0, H * 0.9)
+        r[::9] += 3.0    # some hang over the right / bottom border
+        r[4::9] -= 3.0   # ... or the left / top one
+        bi = torch.randint(0, 2, (K, 1), generator=g).float()
+        rois = torch.cat([bi, r], 1)
+        arrs[f"feat{H}"], arrs[f"rois{H}"] = npy(feat), npy(rois)
+        for P in (7, 14):
+            out, am = torch.ops.torchvision.roi_pool(feat, rois, 1.0, P, P)
+            assert torch.equal(out, tv_roi_pool(feat, rois, (P, P), 1.0))
+            arrs[f"pool{H}_P{P}"] = npy(out)
+            arrs[f"argmax{H}_P{P}"] = npy(am).astype(np.int32)
+        arrs[f"align{H}_P7_sr2"] = npy(tv_roi_align(feat, rois, (7, 7), 1.0, 2, False))
+        arrs[f"align{H}_P7_sr2_al"] = npy(tv_roi_align(feat, rois, (7, 7), 1.0, 2, True))
+        print(f"  roi_large {H}x{H}: K={K}")
+    save("roi_large", **arrs)
+
+
+def gen_roi_backward():
+    """Gradients w.r.t. the features through torchvision.ops.roi_pool / roi_align (CPU autograd): the oracle
+    of frcnn_roi_pool_backward / frcnn_roi_align_backward.  Same feature map and RoIs as roi_ops.npz (border,
+    inverted, outside, degenerate RoIs included)."""
+    src = np.load(os.path.join(OUT, "roi_ops.npz"))
+    feat0, rois = torch.from_numpy(src["feat"]), torch.from_numpy(src["rois"])
+    g = torch.Generator().manual_seed(800)
+    arrs = {}
+    for P in (7, 14):
+        feat = feat0.clone().requires_grad_(True)
+        out = tv_roi_pool(feat, rois, (P, P), 1.0)
+        go = torch.randn(out.shape, generator=g)
+        (gi,) = torch.autograd.grad(out, feat, go)
+        arrs[f"pool_P{P}_go"], arrs[f"pool_P{P}_gi"] = npy(go), npy(gi)
+    for sr in (2, -1):
+        for al in (False, True):
+            for sc in (1.0, 0.5):
+                feat = feat0.clone().requires_grad_(True)
+                out = tv_roi_align(feat, rois, (7, 7), sc, sr, al)
+                go = torch.randn(out.shape, generator=g)
+                (gi,) = torch.autograd.grad(out, feat, go)
+                tag = f"align_sr{sr}_al{int(al)}_s{sc}"
+                arrs[f"{tag}_go"], arrs[f"{tag}_gi"] = npy(go), npy(gi)
+    save("roi_backward", **arrs)
+
+
 def gen_rpn_forward():
     """RegionProposalNetwork.forward post-conv glue (nets/rpn.py:107-143) on a tiny feature map."""
     torch.manual_seed(600)
@@ -443,8 +506,9 @@ def gen_detections():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (gen_anchors, gen_boxmath, gen_proposals, gen_nms, gen_anchor_targets,
-               gen_proposal_targets, gen_roi, gen_rpn_forward, gen_trainer, gen_detections):
+    for fn in (gen_anchors, gen_boxmath, gen_proposals, gen_proposals_large, gen_nms, gen_anchor_targets,
+               gen_proposal_targets, gen_roi, gen_roi_large, gen_roi_backward, gen_rpn_forward, gen_trainer,
+               gen_detections):
         if only and fn.__name__ not in only:
             continue
         print(fn.__name__)

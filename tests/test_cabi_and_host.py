@@ -183,3 +183,34 @@ def test_all_gather_detections_gloo_world2(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"ok {r}" in o
+
+
+def test_divergence_proof_accepts_threshold_flips_only():
+    """tests/divergence.py (the 'why may rows differ' proof used by the drop-in tests): a decision that flips
+    because it sat on its threshold is reported, a flip with a real margin is an assertion failure."""
+    from divergence import first_divergence
+    a = np.array([[0, 0, 100, 100]], np.float32)
+    # IoU of [0,0,100,100] with [0,0,100,h]: h/100 for h < 100 -> 0.7 at h = 70
+    ref = np.concatenate([a, [[0, 0, 100, 70.0001]], [[200, 200, 300, 300]]]).astype(np.float32)
+    oth = np.concatenate([a, [[0, 0, 100, 69.9999]], [[200, 200, 300, 300]]]).astype(np.float32)
+    score = np.array([0.9, 0.8, 0.7], np.float32)
+    kw = dict(img_size=(3, 400, 400), min_size=16.0, nms_iou=0.7, n_pre=10, n_post=3)
+    same = first_divergence(ref, ref, score, **kw)
+    assert same["kind"] is None and same["rows_equal"] == 3
+    flip = first_divergence(ref, oth, score, **kw)
+    assert flip["kind"] == "nms" and flip["rows_equal"] == 1
+    far = oth.copy()
+    far[1, 3] = 60.0  # IoU 0.6 against the reference's 0.700001: this side is nowhere near the threshold
+    with pytest.raises(AssertionError):
+        first_divergence(ref, far, score, **kw)
+    ref_clear = ref.copy()
+    ref_clear[1, 3] = 90.0  # IoU 0.9 in the reference, 0.6 in the other: not a threshold effect
+    with pytest.raises(AssertionError):
+        first_divergence(ref_clear, far, score, **kw)
+    small_r = np.array([[0, 0, 16.00001, 50]], np.float32)
+    small_o = np.array([[0, 0, 15.99999, 50]], np.float32)
+    ms = first_divergence(np.concatenate([small_r, a]), np.concatenate([small_o, a]), np.array([0.9, 0.8], np.float32), **kw)
+    assert ms["kind"] == "min_size" and ms["rows_equal"] == 0
+    with pytest.raises(AssertionError):
+        first_divergence(np.concatenate([small_r, a]), np.concatenate([[[0, 0, 12, 50]], a]).astype(np.float32),
+                         np.array([0.9, 0.8], np.float32), **kw)
