@@ -240,11 +240,15 @@ int frcnn_roi_align_mean_forward(const float* feat, int32_t batch, int32_t chann
 int frcnn_roi_pool_backward(const float* grad_out, const int32_t* argmax, const float* rois5,
                             int32_t num_rois, int32_t batch, int32_t channels, int32_t height, int32_t width,
                             int32_t pooled_h, int32_t pooled_w, float* grad_in, frcnn_stream_t stream);
-/* torchvision roi_align forward (BASELINE.json RoIAlign 7x7 configuration).                      */
+/* torchvision roi_align forward (BASELINE.json RoIAlign 7x7 configuration; the reference itself only calls
+ * RoIPool, nets/classify.py:17,43).  exact = 1: the reference's operation order without FMA, bit-identical to
+ * torchvision's CPU kernel.  exact = 0: the fast variant where one exists (sampling_ratio 2, 7x7 / 14x14) --
+ * merged separable weights and FMA, within 1e-5 of the largest tap magnitude of the reference's value (the
+ * tolerance north_star states for RoIAlign) -- and the exact kernels everywhere else.                   */
 int frcnn_roi_align_forward(const float* feat, int32_t batch, int32_t channels, int32_t height,
                             int32_t width, const float* rois5, int32_t num_rois, int32_t rois_per_image,
                             int32_t pooled_h, int32_t pooled_w, float spatial_scale, int32_t sampling_ratio,
-                            int32_t aligned, float* out, void* workspace, size_t workspace_bytes,
+                            int32_t aligned, int32_t exact, float* out, void* workspace, size_t workspace_bytes,
                             frcnn_stream_t stream);
 /* Backward of torchvision roi_align w.r.t. the features; grad_in [B,C,H,W] zero-initialised by the caller. */
 int frcnn_roi_align_backward(const float* grad_out, const float* rois5, int32_t num_rois, int32_t batch,

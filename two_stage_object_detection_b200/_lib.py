@@ -89,7 +89,7 @@ SIGNATURES = {
     "frcnn_roi_align_mean_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _F, _I, _I, _P, _P, _Z, _P]),
     "frcnn_roi_pool_mean_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _F, _P, _P, _Z, _P]),
     "frcnn_roi_pool_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
-    "frcnn_roi_align_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _F, _I, _I, _P, _P, _Z, _P]),
+    "frcnn_roi_align_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _F, _I, _I, _I, _P, _P, _Z, _P]),
     "frcnn_roi_align_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P]),
 }
 

@@ -1490,6 +1490,230 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_tab_kernel(RoiArgs
 }
 
 // ---------------------------------------------------------------------------------------------
+// RoIAlign forward, FAST variant (the default; north_star asks 1e-5 relative for RoIAlign, not bit-exactness).
+//
+// Same skeleton and thread mapping as roi_align_tab_kernel -- TMA-staged slab, channel-interleaved float4 table,
+// one thread per output bin for good, geometry records handed over through three mbarrier-guarded buffers -- but
+// the arithmetic is reorganised, which the bit-exact variant cannot do:
+//   * a bin's 2 x 2 samples x 4 bilinear taps are SEPARABLE: out = sum_y Wy[y] * (sum_x Wx[x] * f[y][x]) / 4 with
+//     per-axis weights.  The two samples of an axis are bin/2 apart, so their tap pairs coincide (RoI narrower
+//     than ~7 px), overlap in one pixel, or are disjoint: the per-axis footprint is 2, 3 or 4 pixels with MERGED
+//     weights, computed once per RoI by roi_align_fast_entries_kernel.  A bin reads ny x nx in {4..16} pixels
+//     (one LDS.128 = 4 channels) instead of 16 taps, and needs no per-sample weight products;
+//   * FMA, two channels per instruction (fma.rn.f32x2, SASS FFMA2): ny*nx*2 + ny*2 FFMA2 per bin and 4 channels
+//     instead of ~150 unfused multiplies / adds;
+//   * dead slots (weight 0: merged away, out of range, map border) are skipped per lane (no shared-memory
+//     wavefronts) and warp-uniformly when no lane needs them (no issue slots);
+//   * odd row pitch, so vertically adjacent taps do not alias banks.
+// Result: within 1e-5 of the largest tap magnitude of the reference's value (fp32 rounding of a different
+// association); not bit-identical.  frcnn_roi_align_forward(exact = 1) selects the reference-order kernel.
+// ---------------------------------------------------------------------------------------------
+struct FastAxis {     // one bin of one axis: up to four pixels = two pairs (o0, o0 + unit), (o1, o1 + unit)
+    float w[4];       // merged weights of the four slots (rows: already divided by the sample count); 0 = dead slot
+    uint32_t o0, o1;  // BYTE offsets into the float4 table along this axis (rows: y * pitch * 16, columns: x * 16)
+};
+
+// record of RoI row r: float4 w[2P] (rows, then columns), then uint2 o[2P]
+__global__ void __launch_bounds__(256) roi_align_fast_entries_kernel(RoiArgs a, unsigned char* __restrict__ rec, int P) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= a.K * 2 * P) return;
+    const int r = idx / (2 * P), e = idx - r * 2 * P;
+    const float* rp = a.rois5 + (size_t)roi_at(a, r) * 5;
+    const bool is_row = e < P;
+    const int p = is_row ? e : e - P;
+    const int limit = is_row ? a.H : a.W;
+    const float c1 = __ldg(rp + (is_row ? 2 : 1)), c2 = __ldg(rp + (is_row ? 4 : 3));
+    const AlignEntry s0 = align_entry(p, 0, P, 2, c1, c2, a.scale, a.aligned, limit, 1);
+    const AlignEntry s1 = align_entry(p, 1, P, 2, c1, c2, a.scale, a.aligned, limit, 1);
+    const bool v0 = s0.lohi >= 0, v1 = s1.lohi >= 0;
+    int x0 = s0.lohi & 0xFFFF, x1 = s1.lohi & 0xFFFF;
+    float h0 = v0 ? 1.f - s0.l : 0.f, l0 = v0 ? s0.l : 0.f;
+    float h1 = v1 ? 1.f - s1.l : 0.f, l1 = v1 ? s1.l : 0.f;
+    bool second = v1;
+    if (!v0) {  // only the second sample is in range: it takes the first pair
+        x0 = x1;
+        h0 = h1;
+        l0 = l1;
+        second = false;
+    }
+    float w0 = h0, w1 = l0, w2 = 0.f, w3 = 0.f;
+    int xb = 0;
+    if (second) {
+        if (x1 == x0) {          // same pixel pair
+            w0 = w0 + h1;
+            w1 = w1 + l1;
+        } else if (x1 == x0 + 1) {  // pairs overlap in one pixel
+            w1 = w1 + h1;
+            w2 = l1;
+            xb = min(x1 + 1, limit - 1);
+        } else {                 // disjoint pairs
+            w2 = h1;
+            w3 = l1;
+            xb = x1;
+        }
+    }
+    if (!(v0 || v1)) x0 = 0;
+    const float norm = is_row ? 0.25f : 1.f;  // 1 / (2 x 2 samples), exact
+    const uint32_t unit = is_row ? (uint32_t)a.pitch * 16u : 16u;
+    unsigned char* base = rec + (size_t)r * (2 * P * 24);
+    reinterpret_cast<float4*>(base)[e] = make_float4(w0 * norm, w1 * norm, w2 * norm, w3 * norm);
+    reinterpret_cast<uint2*>(base + 2 * P * 16)[e] = make_uint2((uint32_t)x0 * unit, (uint32_t)xb * unit);
+}
+
+// d += a * b for two channels at once (SASS FFMA2; b is one weight for both)
+__device__ __forceinline__ void fma2(float2& d, const float2& a, float b) {
+    const float2 bb = make_float2(b, b);
+    uint64_t& dd = reinterpret_cast<uint64_t&>(d);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(dd)
+        : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(bb)));
+}
+
+template <int P, int AL_THREADS, int MINB>
+__global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_fast_kernel(RoiArgs a) {
+    constexpr int BINS = P * P;
+    constexpr int RPI = AL_THREADS / BINS;   // RoIs per iteration
+    constexpr int NB = P <= 7 ? 16 : 8;      // RoIs per batch
+    constexpr int ITERS = NB / RPI;
+    constexpr int REC = 2 * P * 24;          // bytes per RoI record
+    constexpr int WORDS = NB * REC / 16;     // 16-byte words per batch: one per thread
+    static_assert(RPI * BINS == AL_THREADS && ITERS * RPI == NB && REC % 16 == 0 && WORDS <= AL_THREADS, "thread mapping");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    constexpr int NWARPS = (AL_THREADS + 31) / 32;
+    __shared__ __align__(16) uint4 s_rec[3][WORDS];
+    __shared__ size_t s_ob[3][NB];
+    __shared__ __align__(8) uint64_t s_full[3];
+    float4* tab = reinterpret_cast<float4*>(smem_raw);
+    const int H = a.H, W = a.W, HW = H * W, WP = a.pitch, HWp = (H * WP + 3) & ~3;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * 4;
+    const int cs = min(4, a.C - c0);
+    int r_begin, r_end;
+    roi_range(a, b, r_begin, r_end);
+    const int stride = a.groups * NB;
+    int r0 = r_begin + blockIdx.x * NB;
+    if (r0 >= r_end) return;
+    const int tid = threadIdx.x;
+    const uint4* grec = reinterpret_cast<const uint4*>(a.ent);
+    uint4 pre;
+    int prek;
+    auto load_entries = [&](int rr) {  // records of the batch starting at RoI row rr are contiguous
+        const int lim = rr < r_end ? min(NB, r_end - rr) * (REC / 16) : 0;
+        pre = tid < lim ? __ldg(grec + (size_t)rr * (REC / 16) + tid) : make_uint4(0u, 0u, 0u, 0u);
+        prek = (tid < NB && rr + tid < r_end) ? roi_at(a, rr + tid) : 0;
+    };
+    load_entries(r0);
+    float* raw = reinterpret_cast<float*>(tab + HWp);
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) mbar_init(&s_full[i], NWARPS);
+    }
+    stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, cs * HW, &bar);
+    {
+        const int step_y = AL_THREADS / W, step_x = AL_THREADS - step_y * W;
+        int y = tid / W, x = tid - y * W;
+        for (int p = tid; p < HW; p += AL_THREADS) {
+            float4 v;
+            v.x = raw[p];
+            v.y = cs > 1 ? raw[HW + p] : 0.f;
+            v.z = cs > 2 ? raw[2 * HW + p] : 0.f;
+            v.w = cs > 3 ? raw[3 * HW + p] : 0.f;
+            tab[y * WP + x] = v;
+            x += step_x;
+            y += step_y;
+            if (x >= W) {
+                x -= W;
+                ++y;
+            }
+        }
+    }
+    __syncthreads();
+    const int e = tid % BINS, ej = tid / BINS;
+    const int ph = e / P, pw = e % P;
+    const uint32_t row_step = (uint32_t)WP * 16u;
+    auto fill = [&](int buf) {
+        if (tid < WORDS) s_rec[buf][tid] = pre;
+        if (tid < NB) s_ob[buf][tid] = (((size_t)prek * a.C + c0) * BINS) * sizeof(float);
+    };
+    fill(0);
+    load_entries(r0 + stride);
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&s_full[0]);
+    uint32_t batch = 0;
+    for (; r0 < r_end; r0 += stride, ++batch) {
+        const int cur = (int)(batch % 3u), nbuf = (int)((batch + 1u) % 3u);
+        mbar_wait(&s_full[cur], (batch / 3u) & 1u);
+        fill(nbuf);
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&s_full[nbuf]);
+        load_entries(r0 + 2 * stride);
+        const int nb = min(NB, r_end - r0);
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int j = it * RPI + ej;
+            if (it * RPI >= nb) break;
+            const bool valid = j < nb;
+            const unsigned char* rec = reinterpret_cast<const unsigned char*>(&s_rec[cur][0]) + (valid ? j : 0) * REC;
+            const float4 rw = reinterpret_cast<const float4*>(rec)[ph];
+            const float4 cw = reinterpret_cast<const float4*>(rec)[P + pw];
+            const uint2 ro = reinterpret_cast<const uint2*>(rec + 2 * P * 16)[ph];
+            const uint2 co = reinterpret_cast<const uint2*>(rec + 2 * P * 16)[P + pw];
+            float2 acc01 = make_float2(0.f, 0.f), acc23 = make_float2(0.f, 0.f);
+            const bool c1 = cw.y != 0.f, c2 = cw.z != 0.f, c3 = cw.w != 0.f;
+            const bool any_c2 = __any_sync(0xFFFFFFFFu, c2), any_c3 = __any_sync(0xFFFFFFFFu, c3);
+            auto row = [&](uint32_t rbase, float wy) {
+                const unsigned char* pa = smem_raw + rbase + co.x;
+                const unsigned char* pb = smem_raw + rbase + co.y;
+                float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
+                if (cw.x != 0.f) {
+                    const float4 v = *reinterpret_cast<const float4*>(pa);
+                    fma2(s01, make_float2(v.x, v.y), cw.x);
+                    fma2(s23, make_float2(v.z, v.w), cw.x);
+                }
+                if (c1) {
+                    const float4 v = *reinterpret_cast<const float4*>(pa + 16);
+                    fma2(s01, make_float2(v.x, v.y), cw.y);
+                    fma2(s23, make_float2(v.z, v.w), cw.y);
+                }
+                if (any_c2) {
+                    if (c2) {
+                        const float4 v = *reinterpret_cast<const float4*>(pb);
+                        fma2(s01, make_float2(v.x, v.y), cw.z);
+                        fma2(s23, make_float2(v.z, v.w), cw.z);
+                    }
+                    if (any_c3) {
+                        if (c3) {
+                            const float4 v = *reinterpret_cast<const float4*>(pb + 16);
+                            fma2(s01, make_float2(v.x, v.y), cw.w);
+                            fma2(s23, make_float2(v.z, v.w), cw.w);
+                        }
+                    }
+                }
+                fma2(acc01, s01, wy);
+                fma2(acc23, s23, wy);
+            };
+            if (rw.x != 0.f) row(ro.x, rw.x);
+            if (__any_sync(0xFFFFFFFFu, rw.y != 0.f)) {
+                if (rw.y != 0.f) row(ro.x + row_step, rw.y);
+            }
+            if (__any_sync(0xFFFFFFFFu, rw.z != 0.f)) {
+                if (rw.z != 0.f) row(ro.y, rw.z);
+                if (__any_sync(0xFFFFFFFFu, rw.w != 0.f)) {
+                    if (rw.w != 0.f) row(ro.y + row_step, rw.w);
+                }
+            }
+            if (valid) {
+                float* o = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.out) + s_ob[cur][j]) + e;
+                o[0] = acc01.x;
+                if (cs > 1) o[BINS] = acc01.y;
+                if (cs > 2) o[2 * BINS] = acc23.x;
+                if (cs > 3) o[3 * BINS] = acc23.y;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // RoIAlign + global average pool (HarDNet head with the RoIAlign configuration).
 //
 // mean over bins of RoIAlign is LINEAR in the features and, with a fixed sampling grid, SEPARABLE:
@@ -1729,15 +1953,15 @@ __global__ void roi_align_backward_kernel(const float* __restrict__ go, RoiArgs 
 struct RoiWs {
     int* perm;
     int* offs;
-    int2* ent;  // [num_rois][<= 56] bin / sample geometry of the inference table kernels (roi_pool_entries_kernel: 2*P
-                // words per RoI, roi_align_entries_kernel: 2*P*SR)
+    int2* ent;  // [num_rois][<= 84] bin / sample geometry of the inference table kernels (roi_pool_entries_kernel: 2*P
+                // words per RoI, roi_align_entries_kernel: 2*P*SR, roi_align_fast_entries_kernel: 2*P*3)
 };
 
 static size_t roi_layout(Workspace& ws, int batch, int num_rois, RoiWs* out) {
     RoiWs w;
     w.perm = ws.take<int>(num_rois > 0 ? num_rois : 1);
     w.offs = ws.take<int>(batch + 2);
-    w.ent = ws.take<int2>((size_t)(num_rois > 0 ? num_rois : 1) * 56);
+    w.ent = ws.take<int2>((size_t)(num_rois > 0 ? num_rois : 1) * 84);  // up to 672 bytes per RoI (fast RoIAlign, P = 14)
     if (out) *out = w;
     return ws.off;
 }
@@ -1780,28 +2004,34 @@ static int launch_staged(KernelT kernel, const RoiArgs& a, size_t smem, cudaStre
     dim3 grid(a.groups, slabs, a.B);
     kernel<<<grid, ROI_THREADS, smem, stream>>>(a);
     FRCNN_LAUNCH_CHECK();
+    note_roi_kernel("staged kernel, %d channels per CTA, %d threads", a.CS, ROI_THREADS);
     return FRCNN_OK;
 }
 
 template <typename KernelT>
-static int launch_align(KernelT kernel, const RoiArgs& a, size_t smem, cudaStream_t stream) {
+static int launch_align(const char* name, KernelT kernel, const RoiArgs& a, size_t smem, cudaStream_t stream) {
     FRCNN_SMEM(kernel, smem);
     int slabs = cdiv(a.C, 4);
     FRCNN_CHECK_ARG(slabs <= 65535 && a.B <= 65535, "roi op: too many channel slabs / images");
     dim3 grid(a.groups, slabs, a.B);
     kernel<<<grid, 392, smem, stream>>>(a);
     FRCNN_LAUNCH_CHECK();
+    note_roi_kernel("%s", name);
     return FRCNN_OK;
 }
 
+#define FRCNN_STR2(...) #__VA_ARGS__
+#define FRCNN_STR(...) FRCNN_STR2(__VA_ARGS__)
+
 template <typename KernelT>
-static int launch_tab(KernelT kernel, const RoiArgs& a, size_t smem, int threads, cudaStream_t stream) {
+static int launch_tab(const char* name, KernelT kernel, const RoiArgs& a, size_t smem, int threads, cudaStream_t stream) {
     FRCNN_SMEM(kernel, smem);
     int slabs = cdiv(a.C, a.CS);
     FRCNN_CHECK_ARG(slabs <= 65535 && a.B <= 65535, "roi op: too many channel slabs / images");
     dim3 grid(a.groups, slabs, a.B);
     kernel<<<grid, threads, smem, stream>>>(a);
     FRCNN_LAUNCH_CHECK();
+    note_roi_kernel("%s", name);
     return FRCNN_OK;
 }
 
@@ -1851,10 +2081,15 @@ size_t frcnn_roi_workspace_bytes(int32_t batch, int32_t num_rois) {
     return roi_layout(ws, batch > 0 ? batch : 1, num_rois, nullptr);
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 static int roi_forward_common(bool align, const float* feat, int B, int C, int H, int W, const float* rois5,
                               int K, int per_image, int PH, int PW, float scale, int sampling_ratio, int aligned, float* out,
                               int32_t* argmax, void* workspace, size_t workspace_bytes, cudaStream_t stream,
-                              const char* who, bool mean = false) {
+                              const char* who, bool mean = false, bool exact = true) {
     int rc = check_roi_common(feat, B, C, H, W, rois5, K, PH, PW, out, who);
     if (rc) return rc;
     if (K == 0) return FRCNN_OK;
@@ -1911,6 +2146,45 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
     a.CS = cs;
     a.groups = pick_groups(K, B, cdiv(C, cs));
     size_t smem = (size_t)cs * H * W * 4;
+    if (align && !exact && sampling_ratio == 2 && PH == PW && (PH == 7 || PH == 14)) {
+        // fast variant (FMA, merged separable weights): table with an odd pitch + the staging area must fit
+        static const int pitch_override = env_int("FRCNN_ALIGN_PITCH", 0);  // experiments only
+        a.pitch = pitch_override >= W ? pitch_override : (W | 1);
+        const size_t fsmem = (size_t)((H * a.pitch + 3) & ~3) * sizeof(float4) + (size_t)4 * H * W * sizeof(float);
+        if (fsmem <= 200 * 1024) {
+            a.CS = 4;
+            const bool two = fsmem <= 97 * 1024;  // two CTAs per SM (static part: ~17 KB)
+            const int slabs = cdiv(C, 4);
+            a.groups = std::max(1, std::min(cdiv(cdiv(K, B), 4 * (PH == 7 ? 16 : 8)), cdiv(8 * sm_count(), B * slabs)));
+            Workspace ews(workspace, workspace_bytes);
+            RoiWs w;
+            roi_layout(ews, B, K, &w);
+            if (!ews.ok()) {
+                set_error("%s: workspace too small or misaligned (%zu needed, %zu given)", who, ews.off, workspace_bytes);
+                return FRCNN_ERR_WORKSPACE;
+            }
+            roi_align_fast_entries_kernel<<<cdiv(K * 2 * PH, 256), 256, 0, stream>>>(a, (unsigned char*)w.ent, PH);
+            FRCNN_LAUNCH_CHECK();
+            a.ent = w.ent;
+            FRCNN_CHECK_ARG(slabs <= 65535 && B <= 65535, "roi op: too many channel slabs / images");
+            const dim3 grid(a.groups, slabs, B);
+#define FRCNN_FAST(PP_, TH_, MB_)                                                              \
+    do {                                                                                      \
+        FRCNN_SMEM((roi_align_fast_kernel<PP_, TH_, MB_>), fsmem);                            \
+        roi_align_fast_kernel<PP_, TH_, MB_><<<grid, TH_, fsmem, stream>>>(a);               \
+        FRCNN_LAUNCH_CHECK();                                                                 \
+        note_roi_kernel("roi_align_fast_kernel<%d,%d,%d> pitch %d", PP_, TH_, MB_, a.pitch); \
+        return FRCNN_OK;                                                                      \
+    } while (0)
+            if (PH == 7) {
+                if (two) FRCNN_FAST(7, 392, 2);
+                FRCNN_FAST(7, 784, 1);
+            }
+            if (two) FRCNN_FAST(14, 392, 2);
+            FRCNN_FAST(14, 784, 1);
+#undef FRCNN_FAST
+        }
+    }
     if (align) {
         // interleaved kernel for the common fixed 2x2 sampling grid; plane + staging area must fit
         const size_t al_smem = (size_t)2 * ((H * W + 3) & ~3) * sizeof(float4);
@@ -1935,10 +2209,10 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
                 a.ent = w.ent;
             }
             if (PH == 7)
-                return minb == 2 ? launch_align(roi_align_tab_kernel<7, 2, 392, 2>, a, al_smem, stream)
-                                 : launch_align(roi_align_tab_kernel<7, 2, 392, 1>, a, al_smem, stream);
-            return minb == 2 ? launch_align(roi_align_tab_kernel<14, 2, 392, 2>, a, al_smem, stream)
-                             : launch_align(roi_align_tab_kernel<14, 2, 392, 1>, a, al_smem, stream);
+                return minb == 2 ? launch_align(FRCNN_STR(roi_align_tab_kernel<7, 2, 392, 2>), roi_align_tab_kernel<7, 2, 392, 2>, a, al_smem, stream)
+                                 : launch_align(FRCNN_STR(roi_align_tab_kernel<7, 2, 392, 1>), roi_align_tab_kernel<7, 2, 392, 1>, a, al_smem, stream);
+            return minb == 2 ? launch_align(FRCNN_STR(roi_align_tab_kernel<14, 2, 392, 2>), roi_align_tab_kernel<14, 2, 392, 2>, a, al_smem, stream)
+                             : launch_align(FRCNN_STR(roi_align_tab_kernel<14, 2, 392, 1>), roi_align_tab_kernel<14, 2, 392, 1>, a, al_smem, stream);
         }
         return launch_staged(roi_align_staged_kernel, a, smem, stream);
     }
@@ -1969,7 +2243,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             const int rc_ = launch_entries(a, PP_, false, CS_, workspace, workspace_bytes, stream, who);   \
             if (rc_) return rc_;                                                                            \
         }                                                                                                   \
-        return launch_tab(roi_pool_tab_kernel<PP_, TH_, CS_, MB_, AM_, LV_, 1, !(AM_)>, a, table_bytes(LV_, CS_, a.pitch), \
+        return launch_tab(FRCNN_STR(roi_pool_tab_kernel<PP_, TH_, CS_, MB_, AM_, LV_, 1, !(AM_)>), roi_pool_tab_kernel<PP_, TH_, CS_, MB_, AM_, LV_, 1, !(AM_)>, a, table_bytes(LV_, CS_, a.pitch), \
                           TH_, stream);                                                                     \
     } while (0)
         // rows whose byte length is a multiple of 64 would put vertically adjacent bins on the same banks
@@ -1994,7 +2268,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
                 const int rc_ = launch_entries(a, PH, diag, 4, workspace, workspace_bytes, stream, who);
                 if (rc_) return rc_;
             }
-#define FRCNN_MEAN(PP_, DG_, TH_) return launch_tab(roi_pool_mean_kernel<PP_, 4, 2, DG_, TH_>, a, smem, TH_, stream)
+#define FRCNN_MEAN(PP_, DG_, TH_) return launch_tab(FRCNN_STR(roi_pool_mean_kernel<PP_, 4, 2, DG_, TH_>), roi_pool_mean_kernel<PP_, 4, 2, DG_, TH_>, a, smem, TH_, stream)
             if (PH == 7) {
                 if (diag) { if (threads == 1024) FRCNN_MEAN(7, true, 1024); FRCNN_MEAN(7, true, PM_THREADS); }
                 if (threads == 1024) FRCNN_MEAN(7, false, 1024);
@@ -2035,7 +2309,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
         set_groups(4, TH_);                                                                                 \
         const int rc_ = launch_entries(a, PP_, true, 4, workspace, workspace_bytes, stream, who);          \
         if (rc_) return rc_;                                                                                \
-        return launch_tab(roi_pool_tab_kernel<PP_, TH_, 4, MB_, false, 2, 1, true, true>, a, smemd, TH_, stream); \
+        return launch_tab(FRCNN_STR(roi_pool_tab_kernel<PP_, TH_, 4, MB_, false, 2, 1, true, true>), roi_pool_tab_kernel<PP_, TH_, 4, MB_, false, 2, 1, true, true>, a, smemd, TH_, stream); \
     } while (0)
                 if (PH == 7) {
                     if (two) FRCNN_TABD(7, 392, 2);
@@ -2048,7 +2322,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             if (tcs == 4 && minb == 2) {
                 if (PH == 7) FRCNN_TAB(7, 392, 4, 2, false, 2);
                 set_groups(4, 392);  // 14x14: two adjacent bins per thread
-                return launch_tab(roi_pool_tab_kernel<14, 392, 4, 2, false, 2, 2, true>, a, table_bytes(2, 4, a.pitch), 392,
+                return launch_tab(FRCNN_STR(roi_pool_tab_kernel<14, 392, 4, 2, false, 2, 2, true>), roi_pool_tab_kernel<14, 392, 4, 2, false, 2, 2, true>, a, table_bytes(2, 4, a.pitch), 392,
                                   stream);
             } else if (tcs == 2 && minb == 2) {
                 if (PH == 7) FRCNN_TAB(7, 392, 2, 2, false, 2);
@@ -2091,10 +2365,11 @@ int frcnn_roi_pool_mean_forward(const float* feat, int32_t B, int32_t C, int32_t
 
 int frcnn_roi_align_forward(const float* feat, int32_t B, int32_t C, int32_t H, int32_t W, const float* rois5,
                             int32_t K, int32_t per_image, int32_t PH, int32_t PW, float scale,
-                            int32_t sampling_ratio, int32_t aligned, float* out, void* workspace,
+                            int32_t sampling_ratio, int32_t aligned, int32_t exact, float* out, void* workspace,
                             size_t workspace_bytes, frcnn_stream_t stream) {
     return roi_forward_common(true, feat, B, C, H, W, rois5, K, per_image, PH, PW, scale, sampling_ratio, aligned, out,
-                              nullptr, workspace, workspace_bytes, (cudaStream_t)stream, "frcnn_roi_align_forward");
+                              nullptr, workspace, workspace_bytes, (cudaStream_t)stream, "frcnn_roi_align_forward", false,
+                              exact != 0);
 }
 
 size_t frcnn_roi_align_mean_workspace_bytes(int32_t batch, int32_t num_rois) {

@@ -428,13 +428,16 @@ def roi_align_mean(feat, rois5, output_size, spatial_scale=1.0, sampling_ratio=-
     if rc == _lib.ERR_UNSUPPORTED:
         _note_unfused("roi_align_mean", lib.frcnn_last_error().decode("utf-8", "replace"))
         return roi_align_forward(f, r, output_size, spatial_scale, sampling_ratio, aligned,
-                                 rois_per_image=rois_per_image).mean((2, 3))
+                                 rois_per_image=rois_per_image, exact=True).mean((2, 3))
     check(rc, "frcnn_roi_align_mean_forward")
     return out
 
 
 def roi_align_forward(feat, rois5, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=False, out=None,
-                      rois_per_image=0):
+                      rois_per_image=0, exact=False):
+    """torchvision.ops.roi_align forward.  ``exact=True``: the reference's operation order, bit-identical to
+    torchvision's CPU kernel.  Default: the fast kernel where one exists (sampling_ratio 2, 7x7 / 14x14 bins;
+    FMA + merged separable weights, within 1e-5 of the largest tap magnitude), the exact ones elsewhere."""
     lib = _lib.load()
     dev = _lib.require_cuda(feat, rois5)
     f, r = f32c(feat), f32c(rois5).view(-1, 5)
@@ -448,7 +451,8 @@ def roi_align_forward(feat, rois5, output_size, spatial_scale=1.0, sampling_rati
         ws = _lib.workspace(dev, nbytes)
         check(lib.frcnn_roi_align_forward(f.data_ptr(), B, Cc, H, W, r.data_ptr(), K, int(rois_per_image), ph, pw,
                                           float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
-                                          out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)),
+                                          int(bool(exact)), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          _lib.stream_ptr(dev)),
               "frcnn_roi_align_forward")
     return out
 
@@ -484,9 +488,9 @@ class _RoIPoolFn(torch.autograd.Function):
 
 class _RoIAlignFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feat, rois5, output_size, spatial_scale, sampling_ratio, aligned, rois_per_image):
+    def forward(ctx, feat, rois5, output_size, spatial_scale, sampling_ratio, aligned, rois_per_image, exact):
         out = roi_align_forward(feat, rois5, output_size, spatial_scale, sampling_ratio, aligned,
-                                rois_per_image=rois_per_image)
+                                rois_per_image=rois_per_image, exact=exact)
         if feat.requires_grad:
             ctx.save_for_backward(f32c(rois5).view(-1, 5))
             ctx.cfg = (tuple(feat.shape), _pair(output_size), float(spatial_scale), int(sampling_ratio),
@@ -505,7 +509,7 @@ class _RoIAlignFn(torch.autograd.Function):
             check(lib.frcnn_roi_align_backward(go.data_ptr(), r.data_ptr(), r.shape[0], B, Cc, H, W, ph, pw, scale,
                                                sr, al, gi.data_ptr(), _lib.stream_ptr(dev)),
                   "frcnn_roi_align_backward")
-        return gi, None, None, None, None, None, None
+        return gi, None, None, None, None, None, None, None
 
 
 def roi_pool(feat, rois5, output_size, spatial_scale=1.0, rois_per_image=0):
@@ -516,12 +520,14 @@ def roi_pool(feat, rois5, output_size, spatial_scale=1.0, rois_per_image=0):
     return roi_pool_forward(feat, rois5, output_size, spatial_scale, rois_per_image=rois_per_image)
 
 
-def roi_align(feat, rois5, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=False, rois_per_image=0):
-    """torchvision.ops.roi_align equivalent with autograd w.r.t. ``feat``."""
+def roi_align(feat, rois5, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=False, rois_per_image=0,
+              exact=False):
+    """torchvision.ops.roi_align equivalent with autograd w.r.t. ``feat`` (``exact``: see roi_align_forward)."""
     if feat.requires_grad and torch.is_grad_enabled():
-        return _RoIAlignFn.apply(feat, rois5, output_size, spatial_scale, sampling_ratio, aligned, rois_per_image)
+        return _RoIAlignFn.apply(feat, rois5, output_size, spatial_scale, sampling_ratio, aligned, rois_per_image,
+                                 exact)
     return roi_align_forward(feat, rois5, output_size, spatial_scale, sampling_ratio, aligned,
-                             rois_per_image=rois_per_image)
+                             rois_per_image=rois_per_image, exact=exact)
 
 
 # ------------------------------------------------------------------------------------------------
