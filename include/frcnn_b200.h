@@ -102,7 +102,12 @@ typedef struct frcnn_proposal_params {
     float min_size;     /* fp32(min_size * scale)                                              */
     double nms_thresh;  /* compared as torchvision does: (double)iou > thresh                  */
     int32_t score_mode; /* 0: score is fg probability [B,N]; 1: score is logits [B,N,2] and the
-                           kernel computes softmax(...)[1] (nets/rpn.py:115-118)               */
+                           kernel computes softmax(...)[1] (nets/rpn.py:115-118); 2: loc and score
+                           are the RPN's conv outputs as cuDNN wrote them, loc [B,4A,H,W] and logits
+                           [B,2A,H,W] (NCHW), read in place: the permute(0,2,3,1).contiguous() passes
+                           of nets/rpn.py:107-113 never run (needs num_base / height / width in the
+                           anchor spec; boxes and keys are bit-identical to mode 1 on the permuted
+                           tensors)                                                            */
     int32_t boxes_are_decoded; /* 1: `loc` already holds decoded boxes (skip loc2bbox)          */
     int32_t nms_superblock;    /* 0 = library default                                           */
 } frcnn_proposal_params;

@@ -247,6 +247,39 @@ def test_proposal_creator_dropin(F, name):
     assert max_ulp_error(N(roi)[:rows], g["roi"][:rows], float(max(img))) <= ULP_BOUND
 
 
+@pytest.mark.parametrize("shape", [(3, 9, 38, 38), (2, 9, 5, 7), (1, 8, 9, 4), (2, 9, 64, 64), (1, 1, 3, 70)])
+def test_proposals_read_conv_outputs_in_place(F, shape):
+    """layout='nchw' reads loc [B,4A,H,W] / logits [B,2A,H,W] as the 1x1 convs wrote them; boxes,
+    keys, fg scores and the final RoIs are bit-identical to the NHWC path on permute(0,2,3,1).contiguous() copies
+    (nets/rpn.py:107-118).  Tile tails (H*W not a multiple of 64), A != 9, explicit anchors."""
+    B, A, H, W = shape
+    g = torch.Generator().manual_seed(B * 1000 + A * 100 + H)
+    loc_map = (torch.randn(B, 4 * A, H, W, generator=g) * 0.2).to(DEV)
+    score_map = torch.randn(B, 2 * A, H, W, generator=g).to(DEV)
+    score_map[0, 1, 0, 0] = float("inf")  # special values go through the same softmax form
+    score_map[0, 0, 0, 1 % W] = float("nan")
+    nhwc_loc = loc_map.permute(0, 2, 3, 1).contiguous().view(B, -1, 4)
+    nhwc_sc = score_map.permute(0, 2, 3, 1).contiguous().view(B, -1, 2)
+    base = F.base_anchors(device=DEV) if A == 9 else F.base_anchors(base_size=16, ratios=[0.5, 1, 2, 3][:max(A // 2, 1)],
+                                                                    anchor_scales=[4, 8][:A // max(A // 2, 1)], device=DEV)
+    assert base.shape[0] == A
+    S = 16 * max(H, W)
+    kw = dict(clip_x_max=S, clip_y_max=S, min_size=16.0, base=base, feat_stride=16)
+    b1, k1, f1 = F.decode_clip_score(nhwc_loc, nhwc_sc, feat_hw=(H, W), score_is_logits=True, **kw)
+    b2, k2, f2 = F.decode_clip_score(loc_map, score_map, layout="nchw", **kw)
+    assert torch.equal(k1, k2)
+    assert np.array_equal(N(b1), N(b2), equal_nan=True) and np.array_equal(N(f1), N(f2), equal_nan=True)
+    n_pre, n_post = min(3000, A * H * W), min(300, max(1, A * H * W // 8))
+    r1 = F.proposals(nhwc_loc, nhwc_sc, feat_hw=(H, W), score_is_logits=True, n_pre_nms=n_pre, n_post_nms=n_post, **kw)
+    r2 = F.proposals(loc_map, score_map, layout="nchw", n_pre_nms=n_pre, n_post_nms=n_post, **kw)
+    for x1, x2 in zip(r1, r2):
+        assert np.array_equal(N(x1), N(x2), equal_nan=True)
+    anchor = F.shifted_anchors(base, 16, H, W)  # explicit [N,4] anchors with the conv layout
+    kw2 = dict(kw, base=None, anchor=anchor)
+    b3, k3, _ = F.decode_clip_score(loc_map, score_map, layout="nchw", **kw2)
+    assert torch.equal(k3, k1) and np.array_equal(N(b3), N(b1), equal_nan=True)
+
+
 def test_proposal_creator_raises_like_reference(F):
     from two_stage_object_detection_b200.nets import ProposalCreator
     from two_stage_object_detection_b200.utils import enumerate_shifted_anchor, generate_basic_anchor

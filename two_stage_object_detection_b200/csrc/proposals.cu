@@ -74,6 +74,56 @@ __global__ void __launch_bounds__(256) decode_clip_key_kernel(DecodeArgs a) {
     if (a.fg_out) a.fg_out[t] = s;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same, reading the RPN's 1x1-conv outputs IN PLACE (score_mode 2): loc [B,4A,H,W], logits [B,2A,H,W],
+// NCHW as cuDNN writes them.  nets/rpn.py:107-118 permutes both to NHWC and makes them contiguous before the
+// proposal layer -- two full passes over [B,54,H,W] that exist only to change the layout.  Here a CTA takes a
+// tile of DEC_TILE consecutive pixels: every one of the 6A planes contributes one contiguous run (coalesced along
+// W), the tile is transposed through shared memory, and each thread then owns anchors in OUTPUT order
+// (i = pixel*A + a), so boxes (16 B per anchor) and keys are written fully coalesced.  Anchor a of a pixel reads
+// loc channels 4a..4a+3 and logit channels 2a, 2a+1 -- exactly the elements view(n,-1,4) / view(n,-1,2) of the
+// permuted tensors would hand to the NHWC kernel, in the same arithmetic: boxes and keys are bit-identical.
+// ---------------------------------------------------------------------------------------------
+constexpr int DEC_TILE = 64;
+constexpr int DEC_PITCH = DEC_TILE + 1;
+
+__global__ void __launch_bounds__(256) decode_clip_key_nchw_kernel(DecodeArgs a) {
+    extern __shared__ float dsm[];  // [6A][DEC_PITCH]: planes 0..4A-1 = loc, 4A..6A-1 = logits
+    const int A = a.gen.num_base, HW = a.gen.height * a.gen.width;
+    const int p0 = blockIdx.x * DEC_TILE, b = blockIdx.y;
+    const int np = min(DEC_TILE, HW - p0);
+    const float* loc = reinterpret_cast<const float*>(a.loc) + (size_t)b * 4 * A * HW + p0;
+    const float* sc = a.score + (size_t)b * 2 * A * HW + p0;
+    for (int e = threadIdx.x; e < 6 * A * DEC_TILE; e += blockDim.x) {
+        const int pl = e / DEC_TILE, q = e - pl * DEC_TILE;
+        if (q < np) dsm[pl * DEC_PITCH + q] = pl < 4 * A ? __ldg(loc + (size_t)pl * HW + q) : __ldg(sc + (size_t)(pl - 4 * A) * HW + q);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < np * A; j += blockDim.x) {
+        const int q = j / A, an = j - q * A;
+        const int i = p0 * A + j;  // anchor index within the image
+        const int64_t t = (int64_t)b * a.n + i;
+        const float* lp = dsm + (an * 4) * DEC_PITCH + q;
+        const float4 l = make_float4(lp[0], lp[DEC_PITCH], lp[2 * DEC_PITCH], lp[3 * DEC_PITCH]);
+        float4 r = decode_box(load_anchor(a.gen, i), l);
+        const float* sp = dsm + (4 * A + an * 2) * DEC_PITCH + q;
+        const float2 lg = make_float2(sp[0], sp[DEC_PITCH]);
+        const bool fg_larger = lg.y >= lg.x;  // same softmax form as decode_clip_key_kernel
+        const float big = fg_larger ? lg.y : lg.x, small = fg_larger ? lg.x : lg.y;
+        const float eb = 1.f + (big - big), es = expf(small - big);
+        const float e0 = fg_larger ? es : eb, e1 = fg_larger ? eb : es;
+        const float s = e1 / (e0 + e1);
+        r.x = clamp_torch(r.x, a.xmax);
+        r.z = clamp_torch(r.z, a.xmax);
+        r.y = clamp_torch(r.y, a.ymax);
+        r.w = clamp_torch(r.w, a.ymax);
+        const bool ok = ((r.z - r.x) >= a.min_size) && ((r.w - r.y) >= a.min_size);
+        a.boxes[t] = r;
+        a.keys[t] = ok ? score_key(s) : 0u;
+        if (a.fg_out) a.fg_out[t] = s;
+    }
+}
+
 __global__ void scores_to_keys_kernel(const float* __restrict__ s, int n, uint32_t* __restrict__ keys) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) keys[i] = score_key(__ldg(s + i));
@@ -1189,6 +1239,13 @@ static int run_decode(const frcnn_proposal_params* p, const frcnn_anchor_spec* a
     a.keys = keys;
     a.fg_out = fg_out;
     FRCNN_CHECK_ARG(p->batch <= 65535, "frcnn_decode_clip_score: batch %d > 65535", p->batch);
+    if (p->score_mode == 2) {
+        const size_t smem = (size_t)6 * a.gen.num_base * DEC_PITCH * sizeof(float);
+        FRCNN_SMEM(decode_clip_key_nchw_kernel, smem);
+        decode_clip_key_nchw_kernel<<<dim3(cdiv(a.gen.height * a.gen.width, DEC_TILE), p->batch), 256, smem, stream>>>(a);
+        FRCNN_LAUNCH_CHECK();
+        return FRCNN_OK;
+    }
     decode_clip_key_kernel<<<dim3(cdiv(p->num_anchors, 256), p->batch), 256, 0, stream>>>(a);
     FRCNN_LAUNCH_CHECK();
     return FRCNN_OK;
@@ -1199,10 +1256,16 @@ static int check_params(const frcnn_proposal_params* p, const frcnn_anchor_spec*
     FRCNN_CHECK_ARG(p->batch > 0 && p->num_anchors > 0, "%s: batch and num_anchors must be positive", who);
     FRCNN_CHECK_ARG(p->n_post_nms >= 0, "%s: n_post_nms must be >= 0", who);
     FRCNN_CHECK_ARG((int64_t)p->batch * p->num_anchors < (1ll << 31), "%s: batch*num_anchors too large", who);
-    FRCNN_CHECK_ARG(p->score_mode == 0 || p->score_mode == 1, "%s: bad score_mode", who);
+    FRCNN_CHECK_ARG(p->score_mode >= 0 && p->score_mode <= 2, "%s: bad score_mode", who);
     if (!p->boxes_are_decoded) {
         int rc = check_anchor_spec(anchors, p->num_anchors, who);
         if (rc) return rc;
+    }
+    if (p->score_mode == 2) {  // NCHW conv outputs: the (A, H, W) factorisation of N must be known
+        FRCNN_CHECK_ARG(!p->boxes_are_decoded && anchors && anchors->num_base > 0 &&
+                            anchors->num_base <= FRCNN_MAX_BASE_ANCHORS && anchors->height > 0 && anchors->width > 0 &&
+                            (int64_t)anchors->num_base * anchors->height * anchors->width == p->num_anchors,
+                        "%s: score_mode 2 needs num_base, height, width in the anchor spec with A*H*W == N", who);
     }
     return FRCNN_OK;
 }

@@ -1714,6 +1714,285 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_fast_kernel(RoiArg
 }
 
 // ---------------------------------------------------------------------------------------------
+// RoIAlign forward, STREAMING variant (7x7 bins, sampling_ratio 2; the default for that shape).
+//
+// roi_align_fast_kernel is bound by the shared-memory data pipe (ncu: l1tex data-pipe wavefronts 93 % of peak):
+// a thread per bin re-reads every pixel row for each of the ~2.6 bin rows it feeds, and every bin fetches its
+// own geometry.  Here the bilinear sums are reorganised so that a pixel row is read ONCE per bin column:
+//   out[ph][pw] = sum_y Wy[y][ph] * T[y][pw],   T[y][pw] = sum_x Wx[pw][x] * f[y][x]
+// A thread owns one bin COLUMN pw of one RoI (8 lanes = one RoI: 7 columns + 1 helper lane; a warp = 4 RoIs),
+// walks the RoI's pixel rows top to bottom, computes T once per row (<= 4 LDS.128 + FFMA2) and adds it to its
+// seven row accumulators with that row's dense weight vector Wy[y][0..6] (zeros where the row does not reach a
+// bin): straight-line FFMA2, no per-bin geometry, no data-dependent register index.  The per-RoI "row program"
+// {row offset, 7 weights} comes from roi_align_stream_entries_kernel (once per RoI for all channel slabs) and is
+// read from L2 two rows ahead.
+// Stores: the 7 lanes drop their 7 x 4 results into a per-RoI staging block in shared memory (the region the
+// TMA-staged input planes occupied), and the helper lane hands the finished [4][7][7] block (784 contiguous,
+// 16-byte aligned bytes of the output tensor) to the TMA engine: cp.async.bulk.global.shared (SASS UBLKCP).
+// The LSU data pipe sees 28 conflict-free STS.32 per RoI instead of 196 scattered STG.32.
+// Loops are warp-uniform (trip counts are maxima over the four RoIs of a warp, dead iterations predicated), so
+// the four RoIs of a warp never serialise.  Same numerical contract as roi_align_fast_kernel (1e-5 of the
+// largest tap magnitude; fixed evaluation order, run-to-run identical).
+// ---------------------------------------------------------------------------------------------
+constexpr int AS_P = 7;
+constexpr int AS_REC = 1152;     // bytes per RoI record
+constexpr int AS_ROWS_OFF = 192; // row program starts here: 32 bytes per row {u32 row byte offset, float w[7]}
+constexpr int AS_MAX_ROWS = 30;
+constexpr int AS_STAGE = 800;    // bytes between staging blocks (784 used; 800: the four RoIs of a warp on distinct banks)
+
+__global__ void __launch_bounds__(128) roi_align_stream_entries_kernel(RoiArgs a, unsigned char* __restrict__ rec) {
+    constexpr int P = AS_P;
+    const int r = blockIdx.x * 128 + threadIdx.x;
+    if (r >= a.K) return;
+    const float* rp = a.rois5 + (size_t)roi_at(a, r) * 5;
+    unsigned char* base = rec + (size_t)r * AS_REC;
+    int py[P][4];
+    float pwt[P][4];
+    int y_min = 0x7FFFFFFF, y_max = -1;
+#pragma unroll
+    for (int ax = 0; ax < 2; ++ax) {
+        const bool is_row = ax == 0;
+        const int limit = is_row ? a.H : a.W;
+        const float c1 = __ldg(rp + (is_row ? 2 : 1)), c2 = __ldg(rp + (is_row ? 4 : 3));
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const AlignEntry s0 = align_entry(p, 0, P, 2, c1, c2, a.scale, a.aligned, limit, 1);
+            const AlignEntry s1 = align_entry(p, 1, P, 2, c1, c2, a.scale, a.aligned, limit, 1);
+            const bool v0 = s0.lohi >= 0, v1 = s1.lohi >= 0;
+            int x0 = s0.lohi & 0xFFFF, x1 = s1.lohi & 0xFFFF;
+            float h0 = v0 ? 1.f - s0.l : 0.f, l0 = v0 ? s0.l : 0.f;
+            float h1 = v1 ? 1.f - s1.l : 0.f, l1 = v1 ? s1.l : 0.f;
+            bool second = v1;
+            if (!v0) {
+                x0 = x1;
+                h0 = h1;
+                l0 = l1;
+                second = false;
+            }
+            float w0 = h0, w1 = l0, w2 = 0.f, w3 = 0.f;
+            int xb = 0;
+            if (second) {
+                if (x1 == x0) {
+                    w0 = w0 + h1;
+                    w1 = w1 + l1;
+                } else if (x1 == x0 + 1) {
+                    w1 = w1 + h1;
+                    w2 = l1;
+                    xb = min(x1 + 1, limit - 1);
+                } else {
+                    w2 = h1;
+                    w3 = l1;
+                    xb = x1;
+                }
+            }
+            if (!(v0 || v1)) x0 = 0;
+            if (is_row) {  // kept for the transposition below: pixel rows x0, x0+1, xb, xb+1 with weights / 4
+                py[p][0] = x0;
+                py[p][1] = x0 + 1;
+                py[p][2] = xb;
+                py[p][3] = xb + 1;
+                pwt[p][0] = w0 * 0.25f;
+                pwt[p][1] = w1 * 0.25f;
+                pwt[p][2] = w2 * 0.25f;
+                pwt[p][3] = w3 * 0.25f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (pwt[p][q] != 0.f) {
+                        y_min = min(y_min, py[p][q]);
+                        y_max = max(y_max, py[p][q]);
+                    }
+            } else {
+                reinterpret_cast<float4*>(base)[p] = make_float4(w0, w1, w2, w3);
+                reinterpret_cast<uint2*>(base + P * 16)[p] = make_uint2((uint32_t)x0 * 16u, (uint32_t)xb * 16u);
+            }
+        }
+    }
+    // row program: the pixel rows that reach at least one bin, top to bottom, each with its weight per bin row
+    int n = 0;
+    for (int y = y_min; y <= y_max && n < AS_MAX_ROWS; ++y) {
+        float w[P];
+        bool any = false;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (py[p][q] == y) t = t + pwt[p][q];  // a row appears at most twice in a bin (inverted RoIs)
+            w[p] = t;
+            any = any || t != 0.f;
+        }
+        if (!any) continue;
+        uint4* dst = reinterpret_cast<uint4*>(base + AS_ROWS_OFF + n * 32);
+        dst[0] = make_uint4((uint32_t)y * (uint32_t)a.pitch * 16u, __float_as_uint(w[0]), __float_as_uint(w[1]),
+                            __float_as_uint(w[2]));
+        dst[1] = make_uint4(__float_as_uint(w[3]), __float_as_uint(w[4]), __float_as_uint(w[5]), __float_as_uint(w[6]));
+        ++n;
+    }
+    *reinterpret_cast<int*>(base + P * 24) = n;
+}
+
+__device__ __forceinline__ void fma2s(float2& d, const float2& a, float b) {  // d = a * b + d
+    fma2(d, a, b);
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) roi_align_stream_kernel(RoiArgs a) {
+    constexpr int P = AS_P, BINS = P * P;
+    constexpr int NQ = THREADS / 8;  // RoIs in flight per CTA (one per 8 lanes)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    float4* tab = reinterpret_cast<float4*>(smem_raw);
+    const int H = a.H, W = a.W, HW = H * W, WP = a.pitch, HWp = (H * WP + 3) & ~3;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * 4;
+    int r_begin, r_end;
+    roi_range(a, b, r_begin, r_end);
+    const int first = r_begin + blockIdx.x * NQ;
+    if (first >= r_end) return;
+    const int tid = threadIdx.x;
+    unsigned char* region = reinterpret_cast<unsigned char*>(tab + HWp);  // input planes now, output staging later
+    float* raw = reinterpret_cast<float*>(region);
+    stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, 4 * HW, &bar);
+    {
+        const int step_y = THREADS / W, step_x = THREADS - step_y * W;
+        int y = tid / W, x = tid - y * W;
+        for (int p = tid; p < HW; p += THREADS) {
+            tab[y * WP + x] = make_float4(raw[p], raw[HW + p], raw[2 * HW + p], raw[3 * HW + p]);
+            x += step_x;
+            y += step_y;
+            if (x >= W) {
+                x -= W;
+                ++y;
+            }
+        }
+    }
+    __syncthreads();  // table complete; the planes are dead: their region becomes the output staging area
+
+    const int qid = tid >> 3, ql = tid & 7;
+    const bool col_lane = ql < P;          // lanes 0..6: bin column pw = ql; lane 7: issues the bulk stores
+    float* stg = reinterpret_cast<float*>(region + (size_t)qid * AS_STAGE);
+    const int stride = a.groups * NQ;
+    const int iters = (r_end - first + stride - 1) / stride;  // same for every thread of the CTA
+    const unsigned char* recs = reinterpret_cast<const unsigned char*>(a.ent);
+
+    struct Geo {
+        float4 cw;
+        uint2 co;
+        int n;
+    };
+    auto load_geo = [&](int r) {
+        Geo g;
+        g.cw = make_float4(0.f, 0.f, 0.f, 0.f);
+        g.co = make_uint2(0u, 0u);
+        g.n = 0;
+        if (r < r_end) {
+            const unsigned char* rb = recs + (size_t)r * AS_REC;
+            g.n = __ldg(reinterpret_cast<const int*>(rb + P * 24));
+            if (col_lane) {
+                g.cw = __ldg(reinterpret_cast<const float4*>(rb) + ql);
+                g.co = __ldg(reinterpret_cast<const uint2*>(rb + P * 16) + ql);
+            }
+        }
+        return g;
+    };
+    Geo nxt = load_geo(first + qid);
+    bool store_pending = false;
+    for (int it = 0; it < iters; ++it) {
+        const int r = first + qid + it * stride;
+        const bool valid = r < r_end;
+        const Geo g = nxt;
+        nxt = load_geo(r + stride);
+        const uint4* rows = reinterpret_cast<const uint4*>(recs + (size_t)(valid ? r : r_begin) * AS_REC + AS_ROWS_OFF);
+        const int n = g.n;
+        const int nmax = __reduce_max_sync(0xFFFFFFFFu, n);
+        const float4 cw = g.cw;
+        const bool c1 = cw.y != 0.f, c2 = cw.z != 0.f, c3 = cw.w != 0.f;
+        const bool any_c2 = __any_sync(0xFFFFFFFFu, c2), any_c3 = __any_sync(0xFFFFFFFFu, c3);
+        float2 acc[P][2];
+#pragma unroll
+        for (int k = 0; k < P; ++k) acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
+        // row records two ahead in registers (L2 latency); rows past n read as zero weights
+        auto load_row = [&](int i, uint4& lo, uint4& hi) {
+            lo = hi = make_uint4(0u, 0u, 0u, 0u);
+            if (i < n) {
+                lo = __ldg(rows + 2 * i);
+                hi = __ldg(rows + 2 * i + 1);
+            }
+        };
+        uint4 r0l, r0h, r1l, r1h;
+        load_row(0, r0l, r0h);
+        load_row(1, r1l, r1h);
+        for (int i = 0; i < nmax; ++i) {
+            uint4 r2l, r2h;
+            load_row(i + 2, r2l, r2h);
+            const unsigned char* pa = smem_raw + r0l.x + g.co.x;
+            const unsigned char* pb = smem_raw + r0l.x + g.co.y;
+            float2 t01 = make_float2(0.f, 0.f), t23 = make_float2(0.f, 0.f);
+            const bool live = i < n;
+            if (live && cw.x != 0.f) {
+                const float4 v = *reinterpret_cast<const float4*>(pa);
+                fma2(t01, make_float2(v.x, v.y), cw.x);
+                fma2(t23, make_float2(v.z, v.w), cw.x);
+            }
+            if (live && c1) {
+                const float4 v = *reinterpret_cast<const float4*>(pa + 16);
+                fma2(t01, make_float2(v.x, v.y), cw.y);
+                fma2(t23, make_float2(v.z, v.w), cw.y);
+            }
+            if (any_c2) {
+                if (live && c2) {
+                    const float4 v = *reinterpret_cast<const float4*>(pb);
+                    fma2(t01, make_float2(v.x, v.y), cw.z);
+                    fma2(t23, make_float2(v.z, v.w), cw.z);
+                }
+                if (any_c3) {
+                    if (live && c3) {
+                        const float4 v = *reinterpret_cast<const float4*>(pb + 16);
+                        fma2(t01, make_float2(v.x, v.y), cw.w);
+                        fma2(t23, make_float2(v.z, v.w), cw.w);
+                    }
+                }
+            }
+            const float wk[P] = {__uint_as_float(r0l.y), __uint_as_float(r0l.z), __uint_as_float(r0l.w),
+                                 __uint_as_float(r0h.x), __uint_as_float(r0h.y), __uint_as_float(r0h.z),
+                                 __uint_as_float(r0h.w)};
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                fma2(acc[k][0], t01, wk[k]);
+                fma2(acc[k][1], t23, wk[k]);
+            }
+            r0l = r1l;
+            r0h = r1h;
+            r1l = r2l;
+            r1h = r2h;
+        }
+        // the staging block is free once the previous bulk store has READ it
+        if (store_pending && ql == P) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        if (col_lane && valid) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                stg[0 * BINS + k * P + ql] = acc[k][0].x;
+                stg[1 * BINS + k * P + ql] = acc[k][0].y;
+                stg[2 * BINS + k * P + ql] = acc[k][1].x;
+                stg[3 * BINS + k * P + ql] = acc[k][1].y;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (ql == P && valid) {
+            float* dst = a.out + ((size_t)roi_at(a, r) * a.C + c0) * BINS;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(stg)),
+                         "n"(4 * BINS * 4)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            store_pending = true;
+        }
+    }
+    if (store_pending && ql == P) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // before the CTA's smem goes away
+}
+
+// ---------------------------------------------------------------------------------------------
 // RoIAlign + global average pool (HarDNet head with the RoIAlign configuration).
 //
 // mean over bins of RoIAlign is LINEAR in the features and, with a fixed sampling grid, SEPARABLE:
@@ -1953,15 +2232,16 @@ __global__ void roi_align_backward_kernel(const float* __restrict__ go, RoiArgs 
 struct RoiWs {
     int* perm;
     int* offs;
-    int2* ent;  // [num_rois][<= 84] bin / sample geometry of the inference table kernels (roi_pool_entries_kernel: 2*P
-                // words per RoI, roi_align_entries_kernel: 2*P*SR, roi_align_fast_entries_kernel: 2*P*3)
+    int2* ent;  // [num_rois][<= 144] bin / sample geometry of the inference table kernels (roi_pool_entries_kernel: 2*P
+                // words per RoI, roi_align_entries_kernel: 2*P*SR, roi_align_fast_entries_kernel: 2*P*3,
+                // roi_align_stream_entries_kernel: AS_REC bytes)
 };
 
 static size_t roi_layout(Workspace& ws, int batch, int num_rois, RoiWs* out) {
     RoiWs w;
     w.perm = ws.take<int>(num_rois > 0 ? num_rois : 1);
     w.offs = ws.take<int>(batch + 2);
-    w.ent = ws.take<int2>((size_t)(num_rois > 0 ? num_rois : 1) * 84);  // up to 672 bytes per RoI (fast RoIAlign, P = 14)
+    w.ent = ws.take<int2>((size_t)(num_rois > 0 ? num_rois : 1) * 144);  // up to 1152 bytes per RoI (streaming RoIAlign)
     if (out) *out = w;
     return ws.off;
 }
@@ -2146,6 +2426,38 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
     a.CS = cs;
     a.groups = pick_groups(K, B, cdiv(C, cs));
     size_t smem = (size_t)cs * H * W * 4;
+    static const int align_impl = env_int("FRCNN_ALIGN_IMPL", 0);  // experiments only: 1 = thread-per-bin fast kernel
+    if (align && !exact && sampling_ratio == 2 && PH == 7 && PW == 7 && C % 4 == 0 && align_impl != 1 &&
+        (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        // streaming variant: column threads, every pixel row read once per bin column, TMA bulk stores
+        static const int pitch_override = env_int("FRCNN_ALIGN_PITCH", 0);
+        a.pitch = pitch_override >= W ? pitch_override : (W | 1);
+        constexpr int TH = 256;
+        const size_t tab_bytes = (size_t)((H * a.pitch + 3) & ~3) * sizeof(float4);
+        const size_t region = std::max((size_t)4 * H * W * sizeof(float), (size_t)(TH / 8) * AS_STAGE);
+        const size_t ssmem = tab_bytes + region;
+        if (ssmem <= 110 * 1024) {  // two CTAs per SM
+            a.CS = 4;
+            const int slabs = C / 4;
+            a.groups = std::max(1, std::min(cdiv(cdiv(K, B), 4 * (TH / 8)), cdiv(8 * sm_count(), B * slabs)));
+            Workspace ews(workspace, workspace_bytes);
+            RoiWs w;
+            roi_layout(ews, B, K, &w);
+            if (!ews.ok()) {
+                set_error("%s: workspace too small or misaligned (%zu needed, %zu given)", who, ews.off, workspace_bytes);
+                return FRCNN_ERR_WORKSPACE;
+            }
+            roi_align_stream_entries_kernel<<<cdiv(K, 128), 128, 0, stream>>>(a, (unsigned char*)w.ent);
+            FRCNN_LAUNCH_CHECK();
+            a.ent = w.ent;
+            FRCNN_CHECK_ARG(slabs <= 65535 && B <= 65535, "roi op: too many channel slabs / images");
+            FRCNN_SMEM((roi_align_stream_kernel<TH>), ssmem);
+            roi_align_stream_kernel<TH><<<dim3(a.groups, slabs, B), TH, ssmem, stream>>>(a);
+            FRCNN_LAUNCH_CHECK();
+            note_roi_kernel("roi_align_stream_kernel<%d> pitch %d", TH, a.pitch);
+            return FRCNN_OK;
+        }
+    }
     if (align && !exact && sampling_ratio == 2 && PH == PW && (PH == 7 || PH == 14)) {
         // fast variant (FMA, merged separable weights): table with an odd pitch + the staging area must fit
         static const int pitch_override = env_int("FRCNN_ALIGN_PITCH", 0);  // experiments only

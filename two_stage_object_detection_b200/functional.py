@@ -144,30 +144,54 @@ def _proposal_params(B, N, n_pre_nms, n_post_nms, clip_x_max, clip_y_max, min_si
     return p
 
 
+def _conv_layout(dev, loc, score, anchor, base, feat_stride):
+    """score_mode 2: loc [B,4A,H,W] / logits [B,2A,H,W] straight from the RPN's 1x1 convs (NCHW)."""
+    l, s = f32c(loc), f32c(score)
+    if l.dim() != 4 or s.dim() != 4 or l.shape[1] % 4 or s.shape[1] * 2 != l.shape[1] or \
+            l.shape[0] != s.shape[0] or l.shape[2:] != s.shape[2:]:
+        raise ValueError(f"proposals(layout='nchw'): loc [B,4A,H,W] and logits [B,2A,H,W] expected, got "
+                         f"{tuple(loc.shape)} / {tuple(score.shape)}")
+    B, A, H, W = l.shape[0], l.shape[1] // 4, l.shape[2], l.shape[3]
+    spec, keep = _spec(dev, anchor, base, feat_stride, (H, W))
+    spec.num_base, spec.height, spec.width = A, H, W  # the (A, H, W) factorisation of N, explicit anchors or not
+    if base is not None and base.shape[0] != A:
+        raise ValueError(f"proposals(layout='nchw'): {A} anchors per location in loc, {base.shape[0]} base anchors")
+    return l, s, B, A * H * W, spec, keep
+
+
 def proposals(loc: torch.Tensor, score: torch.Tensor, *, clip_x_max: float, clip_y_max: float,
               n_pre_nms: int, n_post_nms: int, nms_iou: float = 0.7, min_size: float = 16.0,
               anchor: Optional[torch.Tensor] = None, base: Optional[torch.Tensor] = None,
               feat_stride: Optional[int] = None, feat_hw: Optional[Sequence[int]] = None,
               score_is_logits: bool = False, boxes_are_decoded: bool = False, nms_superblock: int = 0,
-              ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+              layout: str = "nhwc") -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """Batched ProposalCreator (nets/rpn.py:36-70 for every image of the batch in one pass).
 
     loc [B,N,4]; score [B,N] fg probabilities (or [B,N,2] logits with ``score_is_logits``).
+    ``layout="nchw"``: loc [B,4A,H,W] and logits [B,2A,H,W] are the RPN conv outputs themselves, read in
+    place (no permute / contiguous pass, nets/rpn.py:107-113); results are bit-identical.
     Returns (rois [B,n_post,4], roi_src [B,n_post] int32, n_keep [B] int32, status [B] int32); all on
     the device, nothing synchronises.  ``min_size`` is the already scaled value (min_size*scale).
     """
     lib = _lib.load()
     dev = _lib.require_cuda(loc, score)
-    l, s = f32c(loc), f32c(score)
-    if l.dim() != 3 or l.shape[2] != 4:
-        raise ValueError(f"proposals: loc must be [B,N,4], got {tuple(loc.shape)}")
-    B, N = l.shape[0], l.shape[1]
-    want = (B, N, 2) if score_is_logits else (B, N)
-    if tuple(s.shape) != want:
-        raise ValueError(f"proposals: score must be {want}, got {tuple(score.shape)}")
-    spec, keep = (AnchorSpec(), []) if boxes_are_decoded else _spec(dev, anchor, base, feat_stride, feat_hw)
+    if layout == "nchw":
+        if boxes_are_decoded:
+            raise ValueError("proposals: layout='nchw' reads conv outputs, not decoded boxes")
+        l, s, B, N, spec, keep = _conv_layout(dev, loc, score, anchor, base, feat_stride)
+        mode = 2
+    else:
+        l, s = f32c(loc), f32c(score)
+        if l.dim() != 3 or l.shape[2] != 4:
+            raise ValueError(f"proposals: loc must be [B,N,4], got {tuple(loc.shape)}")
+        B, N = l.shape[0], l.shape[1]
+        want = (B, N, 2) if score_is_logits else (B, N)
+        if tuple(s.shape) != want:
+            raise ValueError(f"proposals: score must be {want}, got {tuple(score.shape)}")
+        spec, keep = (AnchorSpec(), []) if boxes_are_decoded else _spec(dev, anchor, base, feat_stride, feat_hw)
+        mode = 1 if score_is_logits else 0
     p = _proposal_params(B, N, n_pre_nms, n_post_nms, clip_x_max, clip_y_max, min_size, nms_iou,
-                         1 if score_is_logits else 0, boxes_are_decoded, nms_superblock)
+                         mode, boxes_are_decoded, nms_superblock)
     rois = torch.empty((B, n_post_nms, 4), dtype=torch.float32, device=dev)
     src = torch.empty((B, n_post_nms), dtype=torch.int32, device=dev)
     n_keep = torch.empty((B,), dtype=torch.int32, device=dev)
@@ -183,15 +207,20 @@ def proposals(loc: torch.Tensor, score: torch.Tensor, *, clip_x_max: float, clip
 
 
 def decode_clip_score(loc, score, *, clip_x_max, clip_y_max, min_size=16.0, anchor=None, base=None,
-                      feat_stride=None, feat_hw=None, score_is_logits=False, boxes_are_decoded=False):
+                      feat_stride=None, feat_hw=None, score_is_logits=False, boxes_are_decoded=False,
+                      layout="nhwc"):
     """Stage 1 only: (boxes [B,N,4] clipped, keys [B,N] uint32-as-int32, fg [B,N])."""
     lib = _lib.load()
     dev = _lib.require_cuda(loc, score)
-    l, s = f32c(loc), f32c(score)
-    B, N = l.shape[0], l.shape[1]
-    spec, keep = (AnchorSpec(), []) if boxes_are_decoded else _spec(dev, anchor, base, feat_stride, feat_hw)
-    p = _proposal_params(B, N, 0, 0, clip_x_max, clip_y_max, min_size, 0.7, 1 if score_is_logits else 0,
-                         boxes_are_decoded, 0)
+    if layout == "nchw":
+        l, s, B, N, spec, keep = _conv_layout(dev, loc, score, anchor, base, feat_stride)
+        mode = 2
+    else:
+        l, s = f32c(loc), f32c(score)
+        B, N = l.shape[0], l.shape[1]
+        spec, keep = (AnchorSpec(), []) if boxes_are_decoded else _spec(dev, anchor, base, feat_stride, feat_hw)
+        mode = 1 if score_is_logits else 0
+    p = _proposal_params(B, N, 0, 0, clip_x_max, clip_y_max, min_size, 0.7, mode, boxes_are_decoded, 0)
     boxes = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
     keys = torch.empty((B, N), dtype=torch.int32, device=dev)
     fg = torch.empty((B, N), dtype=torch.float32, device=dev)

@@ -41,14 +41,15 @@ class ProposalCreator():
         return self.n_test_pre_nms, self.n_test_post_nms
 
     def batched(self, loc, score, img_size, scale=1., anchor=None, base=None, feat_stride=None, feat_hw=None,
-                score_is_logits=False):
-        """All images at once: loc [B,N,4], score [B,N] (or logits [B,N,2]).
+                score_is_logits=False, layout="nhwc"):
+        """All images at once: loc [B,N,4], score [B,N] (or logits [B,N,2]); with ``layout="nchw"`` the RPN conv
+        outputs themselves, loc [B,4A,H,W] and logits [B,2A,H,W].
         Returns (rois [B,n_post,4], roi_src, n_keep, status) without host synchronisation."""
         n_pre, n_post = self.limits()
         return F.proposals(loc, score, clip_x_max=img_size[1], clip_y_max=img_size[2], n_pre_nms=n_pre,
                            n_post_nms=n_post, nms_iou=self.nms_iou, min_size=self.min_size * scale,
                            anchor=anchor, base=base, feat_stride=feat_stride, feat_hw=feat_hw,
-                           score_is_logits=score_is_logits)
+                           score_is_logits=score_is_logits, layout=layout)
 
     def __call__(self, loc, score, anchor, img_size, scale=1.):
         rois, _, _, status = self.batched(loc.unsqueeze(0), score.reshape(1, -1), img_size, scale, anchor=anchor)
@@ -78,9 +79,14 @@ class RegionProposalNetwork(nn.Module):
         self.loc = nn.Conv2d(in_channels, n_anchor * 4, 1, 1, 0)
         self.feat_stride = feat_stride
         self.proposal_layer = ProposalCreator(mode)
-        # fused_softmax: the decode kernel reads the logits and computes softmax(...)[1] itself
-        # (nets/rpn.py:115-118) instead of a separate softmax + slice + copy.
+        # fused_softmax: the decode kernel reads the conv outputs in place (NCHW) and computes softmax(...)[1]
+        # itself: neither the permute(0,2,3,1).contiguous() passes (nets/rpn.py:107-113) nor the softmax + slice +
+        # copy (:115-118) stand between the convolutions and the proposal layer.
         self.fused_softmax = True
+        # The NHWC tensors rpn_locs / rpn_scores are RETURN VALUES (the trainer's losses read them).  They are
+        # produced after the proposal kernels have been enqueued, and not at all when this is False
+        # (inference callers that only want the RoIs get None in their place).
+        self.return_rpn_outputs = True
         # nets/frcnn.py:37,48 unpacks five values (with roi_indices); nets/rpn.py:143 returns four.
         self.return_roi_indices = False
         self._anchor_cache = {}
@@ -97,16 +103,19 @@ class RegionProposalNetwork(nn.Module):
 
     def forward(self, x, img_size, scale=1.):
         n, _, h, w = x.shape
-        rpn_locs = self.loc(x).permute(0, 2, 3, 1).contiguous().view(n, -1, 4)
-        rpn_scores = self.score(x).permute(0, 2, 3, 1).contiguous().view(n, -1, 2)
+        loc_map, score_map = self.loc(x), self.score(x)  # [n,4A,h,w], [n,2A,h,w] as cuDNN writes them
         base = self.anchor_base.to(x.device)
+        rpn_locs = rpn_scores = None
         if self.fused_softmax:
-            score_in, logits = rpn_scores, True
-        else:
-            score_in, logits = torch.softmax(rpn_scores, dim=-1)[:, :, 1].contiguous(), False
-        rois, _, _, status = self.proposal_layer.batched(
-            rpn_locs, score_in, img_size, scale, base=base, feat_stride=self.feat_stride, feat_hw=(h, w),
-            score_is_logits=logits)
+            rois, _, _, status = self.proposal_layer.batched(
+                loc_map, score_map, img_size, scale, base=base, feat_stride=self.feat_stride, layout="nchw")
+        if self.return_rpn_outputs or not self.fused_softmax:
+            rpn_locs = loc_map.permute(0, 2, 3, 1).contiguous().view(n, -1, 4)
+            rpn_scores = score_map.permute(0, 2, 3, 1).contiguous().view(n, -1, 2)
+        if not self.fused_softmax:  # the reference's own sequence of ops, kept for comparison
+            score_in = torch.softmax(rpn_scores, dim=-1)[:, :, 1].contiguous()
+            rois, _, _, status = self.proposal_layer.batched(
+                rpn_locs, score_in, img_size, scale, base=base, feat_stride=self.feat_stride, feat_hw=(h, w))
         self.last_status = status  # per-image FRCNN_IMG_* flags, left on the device
         rois = rois.type_as(x)
         anchor = self._anchors(h, w, x.device).unsqueeze(0)
