@@ -182,6 +182,7 @@ struct RoiArgs {
     int per_image;   // > 0: RoIs are grouped, rows [b*per_image, (b+1)*per_image) belong to image b
     int pitch;       // table kernels: row pitch of the shared-memory tables (>= W)
     const int2* ent; // inference table kernels: per-RoI bin geometry [K][2P] from roi_pool_entries_kernel
+    const int* perm2; // streaming RoIAlign: RoI rows of every image ordered by row-program length
 };
 
 __device__ __forceinline__ int round_half_away(float v) { return (int)roundf(v); }
@@ -1831,8 +1832,32 @@ __global__ void __launch_bounds__(128) roi_align_stream_entries_kernel(RoiArgs a
     *reinterpret_cast<int*>(base + P * 24) = n;
 }
 
-__device__ __forceinline__ void fma2s(float2& d, const float2& a, float b) {  // d = a * b + d
-    fma2(d, a, b);
+// RoI rows of every image ordered by the length of their row program, longest first (counting sort, one CTA per
+// image): the four RoIs that share a warp of roi_align_stream_kernel then have (almost) the same trip count, so the
+// warp-uniform row loop wastes no iterations on the shortest of them (unsorted: 16.3 iterations per warp for a mean of
+// 10.2 rows per RoI on the 800x800 configuration).  Order inside a bucket is arbitrary; results do not depend on it.
+__global__ void __launch_bounds__(256) roi_align_stream_sort_kernel(RoiArgs a, const unsigned char* __restrict__ rec,
+                                                                    int* __restrict__ sorted) {
+    __shared__ int cnt[AS_MAX_ROWS + 2];
+    const int b = blockIdx.x;
+    int r_begin, r_end;
+    roi_range(a, b, r_begin, r_end);
+    if (threadIdx.x < AS_MAX_ROWS + 2) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int r = r_begin + threadIdx.x; r < r_end; r += 256)
+        atomicAdd(&cnt[AS_MAX_ROWS - *reinterpret_cast<const int*>(rec + (size_t)r * AS_REC + AS_P * 24)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = r_begin;
+        for (int i = 0; i <= AS_MAX_ROWS; ++i) {
+            const int c = cnt[i];
+            cnt[i] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (int r = r_begin + threadIdx.x; r < r_end; r += 256)
+        sorted[atomicAdd(&cnt[AS_MAX_ROWS - *reinterpret_cast<const int*>(rec + (size_t)r * AS_REC + AS_P * 24)], 1)] = r;
 }
 
 template <int THREADS>
@@ -1895,77 +1920,109 @@ __global__ void __launch_bounds__(THREADS, 2) roi_align_stream_kernel(RoiArgs a)
         }
         return g;
     };
-    Geo nxt = load_geo(first + qid);
+    const int* sorted = a.perm2;  // RoI rows of this image, longest row program first
+    auto row_of = [&](int i) { return i < r_end ? __ldg(sorted + i) : r_end; };
+    auto rows_of = [&](int r) {
+        return reinterpret_cast<const uint4*>(recs + (size_t)(r < r_end ? r : r_begin) * AS_REC + AS_ROWS_OFF);
+    };
+    struct RowRec {
+        uint4 lo, hi;  // {row byte offset, w0, w1, w2}, {w3..w6}
+    };
+    // Row records travel through three registers sets, three rows ahead of their use (L2 latency): a set is reloaded
+    // right after its row has been consumed and read again three rows later -- no rotation, a move would wait for
+    // the load.  Rows past a RoI's own count are not loaded and never applied.
+    auto load_row = [&](const uint4* rows, int n, int i, RowRec& q) {
+        if (i < n) {
+            q.lo = __ldg(rows + 2 * i);
+            q.hi = __ldg(rows + 2 * i + 1);
+        }
+    };
+    int r_next = row_of(first + qid);
+    Geo nxt = load_geo(r_next);
+    RowRec ra, rb, rc;
+    ra.lo = ra.hi = rb.lo = rb.hi = rc.lo = rc.hi = make_uint4(0u, 0u, 0u, 0u);
+    load_row(rows_of(r_next), nxt.n, 0, ra);
+    load_row(rows_of(r_next), nxt.n, 1, rb);
+    load_row(rows_of(r_next), nxt.n, 2, rc);
     bool store_pending = false;
     for (int it = 0; it < iters; ++it) {
-        const int r = first + qid + it * stride;
+        const int r = r_next;
         const bool valid = r < r_end;
         const Geo g = nxt;
-        nxt = load_geo(r + stride);
-        const uint4* rows = reinterpret_cast<const uint4*>(recs + (size_t)(valid ? r : r_begin) * AS_REC + AS_ROWS_OFF);
+        r_next = row_of(first + qid + (it + 1) * stride);
+        nxt = load_geo(r_next);
+        const uint4* rows = rows_of(r);
         const int n = g.n;
         const int nmax = __reduce_max_sync(0xFFFFFFFFu, n);
+        const int nmin = __reduce_min_sync(0xFFFFFFFFu, n);
         const float4 cw = g.cw;
-        const bool c1 = cw.y != 0.f, c2 = cw.z != 0.f, c3 = cw.w != 0.f;
-        const bool any_c2 = __any_sync(0xFFFFFFFFu, c2), any_c3 = __any_sync(0xFFFFFFFFu, c3);
+        const bool cl0 = cw.x != 0.f, c1 = cw.y != 0.f, c2 = cw.z != 0.f, c3 = cw.w != 0.f;
+        const unsigned char* ca = smem_raw + g.co.x;
+        const unsigned char* cb = smem_raw + g.co.y;
         float2 acc[P][2];
 #pragma unroll
         for (int k = 0; k < P; ++k) acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
-        // row records two ahead in registers (L2 latency); rows past n read as zero weights
-        auto load_row = [&](int i, uint4& lo, uint4& hi) {
-            lo = hi = make_uint4(0u, 0u, 0u, 0u);
-            if (i < n) {
-                lo = __ldg(rows + 2 * i);
-                hi = __ldg(rows + 2 * i + 1);
-            }
-        };
-        uint4 r0l, r0h, r1l, r1h;
-        load_row(0, r0l, r0h);
-        load_row(1, r1l, r1h);
-        for (int i = 0; i < nmax; ++i) {
-            uint4 r2l, r2h;
-            load_row(i + 2, r2l, r2h);
-            const unsigned char* pa = smem_raw + r0l.x + g.co.x;
-            const unsigned char* pb = smem_raw + r0l.x + g.co.y;
+        // one pixel row: T = sum over this column's (<= 4) pixels, then into the seven bin-row accumulators
+        auto process = [&](const RowRec& q) {
+            const unsigned char* pa = ca + q.lo.x;
+            const unsigned char* pb = cb + q.lo.x;
             float2 t01 = make_float2(0.f, 0.f), t23 = make_float2(0.f, 0.f);
-            const bool live = i < n;
-            if (live && cw.x != 0.f) {
+            if (cl0) {
                 const float4 v = *reinterpret_cast<const float4*>(pa);
                 fma2(t01, make_float2(v.x, v.y), cw.x);
                 fma2(t23, make_float2(v.z, v.w), cw.x);
             }
-            if (live && c1) {
+            if (c1) {
                 const float4 v = *reinterpret_cast<const float4*>(pa + 16);
                 fma2(t01, make_float2(v.x, v.y), cw.y);
                 fma2(t23, make_float2(v.z, v.w), cw.y);
             }
-            if (any_c2) {
-                if (live && c2) {
-                    const float4 v = *reinterpret_cast<const float4*>(pb);
-                    fma2(t01, make_float2(v.x, v.y), cw.z);
-                    fma2(t23, make_float2(v.z, v.w), cw.z);
-                }
-                if (any_c3) {
-                    if (live && c3) {
-                        const float4 v = *reinterpret_cast<const float4*>(pb + 16);
-                        fma2(t01, make_float2(v.x, v.y), cw.w);
-                        fma2(t23, make_float2(v.z, v.w), cw.w);
-                    }
-                }
+            // (no warp-uniform skip of the second pair: straight-line code lets the scheduler hoist the loads of all
+            //  three rows of an unrolled group above their FMAs; a dead slot costs two predicated-off issue slots)
+            if (c2) {
+                const float4 v = *reinterpret_cast<const float4*>(pb);
+                fma2(t01, make_float2(v.x, v.y), cw.z);
+                fma2(t23, make_float2(v.z, v.w), cw.z);
             }
-            const float wk[P] = {__uint_as_float(r0l.y), __uint_as_float(r0l.z), __uint_as_float(r0l.w),
-                                 __uint_as_float(r0h.x), __uint_as_float(r0h.y), __uint_as_float(r0h.z),
-                                 __uint_as_float(r0h.w)};
+            if (c3) {
+                const float4 v = *reinterpret_cast<const float4*>(pb + 16);
+                fma2(t01, make_float2(v.x, v.y), cw.w);
+                fma2(t23, make_float2(v.z, v.w), cw.w);
+            }
+            const float wk[P] = {__uint_as_float(q.lo.y), __uint_as_float(q.lo.z), __uint_as_float(q.lo.w),
+                                 __uint_as_float(q.hi.x), __uint_as_float(q.hi.y), __uint_as_float(q.hi.z),
+                                 __uint_as_float(q.hi.w)};
 #pragma unroll
             for (int k = 0; k < P; ++k) {
                 fma2(acc[k][0], t01, wk[k]);
                 fma2(acc[k][1], t23, wk[k]);
             }
-            r0l = r1l;
-            r0h = r1h;
-            r1l = r2l;
-            r1h = r2h;
+        };
+        int i = 0;
+        for (; i + 3 <= nmin; i += 3) {  // every RoI of the warp has these rows: no per-RoI predicate
+            process(ra);
+            load_row(rows, n, i + 3, ra);
+            process(rb);
+            load_row(rows, n, i + 4, rb);
+            process(rc);
+            load_row(rows, n, i + 5, rc);
         }
+        for (; i < nmax; i += 3) {       // ragged end: rows some RoIs of the warp do not have
+            if (i < n) process(ra);
+            load_row(rows, n, i + 3, ra);
+            if (i + 1 < nmax) {
+                if (i + 1 < n) process(rb);
+                load_row(rows, n, i + 4, rb);
+            }
+            if (i + 2 < nmax) {
+                if (i + 2 < n) process(rc);
+                load_row(rows, n, i + 5, rc);
+            }
+        }
+        // first rows of the NEXT RoI: their L2 round trip hides behind this RoI's stores
+        load_row(rows_of(r_next), nxt.n, 0, ra);
+        load_row(rows_of(r_next), nxt.n, 1, rb);
+        load_row(rows_of(r_next), nxt.n, 2, rc);
         // the staging block is free once the previous bulk store has READ it
         if (store_pending && ql == P) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
@@ -2232,6 +2289,7 @@ __global__ void roi_align_backward_kernel(const float* __restrict__ go, RoiArgs 
 struct RoiWs {
     int* perm;
     int* offs;
+    int* sorted;  // streaming RoIAlign: rows of every image, longest row program first
     int2* ent;  // [num_rois][<= 144] bin / sample geometry of the inference table kernels (roi_pool_entries_kernel: 2*P
                 // words per RoI, roi_align_entries_kernel: 2*P*SR, roi_align_fast_entries_kernel: 2*P*3,
                 // roi_align_stream_entries_kernel: AS_REC bytes)
@@ -2241,6 +2299,7 @@ static size_t roi_layout(Workspace& ws, int batch, int num_rois, RoiWs* out) {
     RoiWs w;
     w.perm = ws.take<int>(num_rois > 0 ? num_rois : 1);
     w.offs = ws.take<int>(batch + 2);
+    w.sorted = ws.take<int>(num_rois > 0 ? num_rois : 1);
     w.ent = ws.take<int2>((size_t)(num_rois > 0 ? num_rois : 1) * 144);  // up to 1152 bytes per RoI (streaming RoIAlign)
     if (out) *out = w;
     return ws.off;
@@ -2432,7 +2491,8 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
         // streaming variant: column threads, every pixel row read once per bin column, TMA bulk stores
         static const int pitch_override = env_int("FRCNN_ALIGN_PITCH", 0);
         a.pitch = pitch_override >= W ? pitch_override : (W | 1);
-        constexpr int TH = 256;
+        static const int th_override = env_int("FRCNN_ALIGN_THREADS", 0);  // experiments only
+        const int TH = th_override == 384 ? 384 : 256;  // 384: 80 registers with spills, measured slower (0.56 vs 0.52 ms)
         const size_t tab_bytes = (size_t)((H * a.pitch + 3) & ~3) * sizeof(float4);
         const size_t region = std::max((size_t)4 * H * W * sizeof(float), (size_t)(TH / 8) * AS_STAGE);
         const size_t ssmem = tab_bytes + region;
@@ -2449,10 +2509,19 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             }
             roi_align_stream_entries_kernel<<<cdiv(K, 128), 128, 0, stream>>>(a, (unsigned char*)w.ent);
             FRCNN_LAUNCH_CHECK();
+            roi_align_stream_sort_kernel<<<B, 256, 0, stream>>>(a, (const unsigned char*)w.ent, w.sorted);
+            FRCNN_LAUNCH_CHECK();
             a.ent = w.ent;
+            a.perm2 = w.sorted;
             FRCNN_CHECK_ARG(slabs <= 65535 && B <= 65535, "roi op: too many channel slabs / images");
-            FRCNN_SMEM((roi_align_stream_kernel<TH>), ssmem);
-            roi_align_stream_kernel<TH><<<dim3(a.groups, slabs, B), TH, ssmem, stream>>>(a);
+            const dim3 grid(a.groups, slabs, B);
+            if (TH == 256) {
+                FRCNN_SMEM((roi_align_stream_kernel<256>), ssmem);
+                roi_align_stream_kernel<256><<<grid, 256, ssmem, stream>>>(a);
+            } else {
+                FRCNN_SMEM((roi_align_stream_kernel<384>), ssmem);
+                roi_align_stream_kernel<384><<<grid, 384, ssmem, stream>>>(a);
+            }
             FRCNN_LAUNCH_CHECK();
             note_roi_kernel("roi_align_stream_kernel<%d> pitch %d", TH, a.pitch);
             return FRCNN_OK;
