@@ -1725,10 +1725,10 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) roi_align_fast_kernel(RoiArg
 // walks the RoI's pixel rows top to bottom, computes T once per row (<= 4 LDS.128 + FFMA2) and adds it to its
 // seven row accumulators with that row's dense weight vector Wy[y][0..6] (zeros where the row does not reach a
 // bin): straight-line FFMA2, no per-bin geometry, no data-dependent register index.  The per-RoI "row program"
-// {row offset, 7 weights} comes from roi_align_stream_entries_kernel (once per RoI for all channel slabs) and is
-// read from L2 two rows ahead.
-// Stores: the 7 lanes drop their 7 x 4 results into a per-RoI staging block in shared memory (the region the
-// TMA-staged input planes occupied), and the helper lane hands the finished [4][7][7] block (784 contiguous,
+// {row offset, 7 weights} comes from roi_align_stream_entries_kernel (once per RoI for all channel slabs) and
+// reaches the warp through a shared-memory ring (roi_align_stream_pack_kernel / roi_align_stream2_kernel below).
+// Stores: the 7 lanes drop their 7 x 4 results into a per-RoI staging block in shared memory, and the helper
+// lane hands the finished [4][7][7] block (784 contiguous,
 // 16-byte aligned bytes of the output tensor) to the TMA engine: cp.async.bulk.global.shared (SASS UBLKCP).
 // The LSU data pipe sees 28 conflict-free STS.32 per RoI instead of 196 scattered STG.32.
 // Loops are warp-uniform (trip counts are maxima over the four RoIs of a warp, dead iterations predicated), so
@@ -1833,7 +1833,7 @@ __global__ void __launch_bounds__(128) roi_align_stream_entries_kernel(RoiArgs a
 }
 
 // RoI rows of every image ordered by the length of their row program, longest first (counting sort, one CTA per
-// image): the four RoIs that share a warp of roi_align_stream_kernel then have (almost) the same trip count, so the
+// image): the four RoIs that share a warp of roi_align_stream2_kernel then have (almost) the same trip count, so the
 // warp-uniform row loop wastes no iterations on the shortest of them (unsorted: 16.3 iterations per warp for a mean of
 // 10.2 rows per RoI on the 800x800 configuration).  Order inside a bucket is arbitrary; results do not depend on it.
 __global__ void __launch_bounds__(256) roi_align_stream_sort_kernel(RoiArgs a, const unsigned char* __restrict__ rec,
@@ -1860,112 +1860,167 @@ __global__ void __launch_bounds__(256) roi_align_stream_sort_kernel(RoiArgs a, c
         sorted[atomicAdd(&cnt[AS_MAX_ROWS - *reinterpret_cast<const int*>(rec + (size_t)r * AS_REC + AS_P * 24)], 1)] = r;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The streaming kernel proper: the row programs travel through shared memory.
+//
+// The first form of this kernel read the row records from L2 with __ldg, three rows ahead in 24 registers; ncu
+// (profiles/r2_cfg4_roialign_fast_and_stream.md) showed 44 % of a warp's time as "long scoreboard" -- with 16 warps
+// per SM three rows are not far enough.  Here roi_align_stream_pack_kernel lays the geometry of a whole PASS of a warp
+// (its 4 RoIs x up to 30 pixel rows) out as the warp will consume it -- 512-byte chunks: two header chunks
+// (column weights; column offsets, row count, output row) and one chunk per 4 pixel rows, each row
+// [4 RoIs][offset, w0..w6] -- and the warp copies chunk p + D into a private shared-memory ring with ONE cp.async
+// (32 lanes x 16 bytes, SASS LDGSTS) while it works on chunk p: no registers held for records in flight, no
+// L2 latency on the dependency chain, no mbarrier (cp.async.wait_group + __syncwarp; the ring is private to the
+// warp).  Rows a RoI does not have point at an all-zero pixel row appended to the table, so the row body needs
+// no per-RoI predicate.  The input planes are read straight from global memory into the channel-interleaved
+// table (coalesced 128-byte runs per plane) -- without the 40 KB TMA landing zone three CTAs fit on an SM.
+// ---------------------------------------------------------------------------------------------
+constexpr int AS2_CHUNK = 512;
+constexpr int AS2_HDR = 2;
+constexpr int AS2_MAXC = AS2_HDR + (AS_MAX_ROWS + 3) / 4;
+constexpr int AS2_SLOT = AS2_MAXC * AS2_CHUNK;  // bytes per (pass, warp)
+
+__device__ __forceinline__ int as2_pass_base(int r_begin, int b, int NQ) { return r_begin / NQ + b; }
+
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 2) roi_align_stream_kernel(RoiArgs a) {
+__global__ void __launch_bounds__(THREADS) roi_align_stream_pack_kernel(RoiArgs a, const unsigned char* __restrict__ rec,
+                                                                        const int* __restrict__ sorted,
+                                                                        unsigned char* __restrict__ prog) {
+    constexpr int P = AS_P, NQ = THREADS / 8, NW = THREADS / 32;
+    const int b = blockIdx.y;
+    int r_begin, r_end;
+    roi_range(a, b, r_begin, r_end);
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, ql = lane & 7;
+    for (int pi = blockIdx.x; r_begin + pi * NQ < r_end; pi += gridDim.x) {
+    const int pos0 = r_begin + pi * NQ;
+    const int pos = pos0 + (tid >> 3);
+    const bool valid = pos < r_end;
+    const int r = valid ? __ldg(sorted + pos) : r_begin;
+    const unsigned char* rb = rec + (size_t)r * AS_REC;
+    const int n = valid ? __ldg(reinterpret_cast<const int*>(rb + P * 24)) : 0;
+    float4 cw = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 co = make_uint2(0u, 0u);
+    if (valid && ql < P) {
+        cw = __ldg(reinterpret_cast<const float4*>(rb) + ql);
+        co = __ldg(reinterpret_cast<const uint2*>(rb + P * 16) + ql);
+    }
+    const int nmax = __reduce_max_sync(0xFFFFFFFFu, n);
+    const int k = max(1, (nmax + 3) >> 2);
+    unsigned char* slot = prog + ((size_t)(as2_pass_base(r_begin, b, NQ) + pi) * NW + w) * AS2_SLOT;
+    if (ql == 7) cw = make_float4(__int_as_float(k), __int_as_float(nmax), 0.f, 0.f);  // helper lanes carry the pass shape
+    reinterpret_cast<float4*>(slot)[lane] = cw;
+    reinterpret_cast<uint4*>(slot + AS2_CHUNK)[lane] =
+        make_uint4(co.x, co.y, (uint32_t)n, valid ? (uint32_t)roi_at(a, r) : 0xFFFFFFFFu);
+    const uint32_t zero_row = (uint32_t)a.H * (uint32_t)a.pitch * 16u;
+    for (int c = 0; c < k; ++c) {
+        const int i = 4 * c + (lane >> 3), gg = (lane & 7) >> 1, half = lane & 1;
+        const int r_g = __shfl_sync(0xFFFFFFFFu, r, gg * 8);
+        const int n_g = __shfl_sync(0xFFFFFFFFu, n, gg * 8);
+        uint4 v = half ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(zero_row, 0u, 0u, 0u);
+        if (i < n_g) v = __ldg(reinterpret_cast<const uint4*>(rec + (size_t)r_g * AS_REC + AS_ROWS_OFF) + 2 * i + half);
+        reinterpret_cast<uint4*>(slot + (AS2_HDR + c) * AS2_CHUNK)[lane] = v;
+    }
+    }
+}
+
+template <int THREADS, int MINB, int RING>
+__global__ void __launch_bounds__(THREADS, MINB) roi_align_stream2_kernel(RoiArgs a, const unsigned char* __restrict__ prog) {
     constexpr int P = AS_P, BINS = P * P;
-    constexpr int NQ = THREADS / 8;  // RoIs in flight per CTA (one per 8 lanes)
+    constexpr int NQ = THREADS / 8, NW = THREADS / 32, D = RING - 1;
+    static_assert(D >= 1 && D <= 3, "look-ahead must stay inside the next pass's header + first row chunk");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
     float4* tab = reinterpret_cast<float4*>(smem_raw);
-    const int H = a.H, W = a.W, HW = H * W, WP = a.pitch, HWp = (H * WP + 3) & ~3;
+    const int H = a.H, W = a.W, HW = H * W, WP = a.pitch;
+    const uint32_t tab_bytes = ((uint32_t)(H + 1) * WP * 16u + 127u) & ~127u;
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * 4;
     int r_begin, r_end;
     roi_range(a, b, r_begin, r_end);
-    const int first = r_begin + blockIdx.x * NQ;
-    if (first >= r_end) return;
-    const int tid = threadIdx.x;
-    unsigned char* region = reinterpret_cast<unsigned char*>(tab + HWp);  // input planes now, output staging later
-    float* raw = reinterpret_cast<float*>(region);
-    stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, 4 * HW, &bar);
-    {
-        const int step_y = THREADS / W, step_x = THREADS - step_y * W;
-        int y = tid / W, x = tid - y * W;
-        for (int p = tid; p < HW; p += THREADS) {
-            tab[y * WP + x] = make_float4(raw[p], raw[HW + p], raw[2 * HW + p], raw[3 * HW + p]);
-            x += step_x;
-            y += step_y;
-            if (x >= W) {
-                x -= W;
-                ++y;
-            }
-        }
+    const int n_pass_img = (r_end - r_begin + NQ - 1) / NQ;
+    const int pi0 = blockIdx.x;
+    if (pi0 >= n_pass_img) return;
+    const int n_pass = (n_pass_img - pi0 + a.groups - 1) / a.groups;  // passes of this CTA: pi0, pi0 + groups, ...
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 3, ql = lane & 7;
+    unsigned char* stg_b = smem_raw + tab_bytes + (size_t)(tid >> 3) * AS_STAGE;
+    float* stg = reinterpret_cast<float*>(stg_b);
+    const uint32_t ring = smem_u32(smem_raw + tab_bytes + (size_t)NQ * AS_STAGE + (size_t)w * (RING * AS2_CHUNK));
+    const unsigned char* slot = prog + ((size_t)(as2_pass_base(r_begin, b, NQ) + pi0) * NW + w) * AS2_SLOT + lane * 16;
+    const size_t slot_stride = (size_t)a.groups * NW * AS2_SLOT;
+
+    // chunk `pos` of the warp's stream lives in ring slot pos % RING
+    auto fetch = [&](const unsigned char* src, int pos) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (uint32_t)(pos % RING) * AS2_CHUNK + lane * 16),
+                     "l"(src)
+                     : "memory");
+    };
+    auto commit = [&]() { asm volatile("cp.async.commit_group;" ::: "memory"); };
+    auto wait_chunk = [&]() {
+        asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+        __syncwarp();
+    };
+#pragma unroll
+    for (int j = 0; j < D; ++j) {  // header (+ first row chunk): on their way while the table is built
+        fetch(slot + j * AS2_CHUNK, j);
+        commit();
     }
-    __syncthreads();  // table complete; the planes are dead: their region becomes the output staging area
-
-    const int qid = tid >> 3, ql = tid & 7;
-    const bool col_lane = ql < P;          // lanes 0..6: bin column pw = ql; lane 7: issues the bulk stores
-    float* stg = reinterpret_cast<float*>(region + (size_t)qid * AS_STAGE);
-    const int stride = a.groups * NQ;
-    const int iters = (r_end - first + stride - 1) / stride;  // same for every thread of the CTA
-    const unsigned char* recs = reinterpret_cast<const unsigned char*>(a.ent);
-
-    struct Geo {
-        float4 cw;
-        uint2 co;
-        int n;
-    };
-    auto load_geo = [&](int r) {
-        Geo g;
-        g.cw = make_float4(0.f, 0.f, 0.f, 0.f);
-        g.co = make_uint2(0u, 0u);
-        g.n = 0;
-        if (r < r_end) {
-            const unsigned char* rb = recs + (size_t)r * AS_REC;
-            g.n = __ldg(reinterpret_cast<const int*>(rb + P * 24));
-            if (col_lane) {
-                g.cw = __ldg(reinterpret_cast<const float4*>(rb) + ql);
-                g.co = __ldg(reinterpret_cast<const uint2*>(rb + P * 16) + ql);
-            }
+    {
+        const float* src = a.feat + ((size_t)b * a.C + c0) * HW;
+#pragma unroll 2
+        for (int p = tid; p < HW; p += THREADS) {
+            const int y = p / W, x = p - y * W;
+            tab[y * WP + x] = make_float4(__ldg(src + p), __ldg(src + HW + p), __ldg(src + 2 * HW + p), __ldg(src + 3 * HW + p));
         }
-        return g;
-    };
-    const int* sorted = a.perm2;  // RoI rows of this image, longest row program first
-    auto row_of = [&](int i) { return i < r_end ? __ldg(sorted + i) : r_end; };
-    auto rows_of = [&](int r) {
-        return reinterpret_cast<const uint4*>(recs + (size_t)(r < r_end ? r : r_begin) * AS_REC + AS_ROWS_OFF);
-    };
-    struct RowRec {
-        uint4 lo, hi;  // {row byte offset, w0, w1, w2}, {w3..w6}
-    };
-    // Row records travel through three registers sets, three rows ahead of their use (L2 latency): a set is reloaded
-    // right after its row has been consumed and read again three rows later -- no rotation, a move would wait for
-    // the load.  Rows past a RoI's own count are not loaded and never applied.
-    auto load_row = [&](const uint4* rows, int n, int i, RowRec& q) {
-        if (i < n) {
-            q.lo = __ldg(rows + 2 * i);
-            q.hi = __ldg(rows + 2 * i + 1);
-        }
-    };
-    int r_next = row_of(first + qid);
-    Geo nxt = load_geo(r_next);
-    RowRec ra, rb, rc;
-    ra.lo = ra.hi = rb.lo = rb.hi = rc.lo = rc.hi = make_uint4(0u, 0u, 0u, 0u);
-    load_row(rows_of(r_next), nxt.n, 0, ra);
-    load_row(rows_of(r_next), nxt.n, 1, rb);
-    load_row(rows_of(r_next), nxt.n, 2, rc);
+        for (int x = tid; x < WP; x += THREADS) tab[H * WP + x] = make_float4(0.f, 0.f, 0.f, 0.f);  // the row of no RoI
+    }
+    __syncthreads();
+
+    const bool col_lane = ql < P;
+    int pos = 0;  // chunks consumed so far
     bool store_pending = false;
-    for (int it = 0; it < iters; ++it) {
-        const int r = r_next;
-        const bool valid = r < r_end;
-        const Geo g = nxt;
-        r_next = row_of(first + qid + (it + 1) * stride);
-        nxt = load_geo(r_next);
-        const uint4* rows = rows_of(r);
-        const int n = g.n;
-        const int nmax = __reduce_max_sync(0xFFFFFFFFu, n);
-        const int nmin = __reduce_min_sync(0xFFFFFFFFu, n);
-        const float4 cw = g.cw;
+    // after consuming chunk j of a pass with kk row chunks: start the copy of the chunk D positions further on
+    auto prefetch = [&](int j, int kk, bool last_pass) {
+        int jj = j + D;
+        const unsigned char* base = slot;
+        bool ok = true;
+        if (jj >= AS2_HDR + kk) {
+            jj -= AS2_HDR + kk;
+            base += slot_stride;
+            ok = !last_pass;
+        }
+        if (ok) fetch(base + jj * AS2_CHUNK, pos + D);
+        commit();
+    };
+    for (int ip = 0; ip < n_pass; ++ip, slot += slot_stride) {
+        const bool last_pass = ip + 1 == n_pass;
+        wait_chunk();
+        float4 cw;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cw.x), "=f"(cw.y), "=f"(cw.z), "=f"(cw.w)
+                     : "r"(ring + (uint32_t)(pos % RING) * AS2_CHUNK + lane * 16));
+        const int kk = __shfl_sync(0xFFFFFFFFu, __float_as_int(cw.x), 7);
+        const int nmax = __shfl_sync(0xFFFFFFFFu, __float_as_int(cw.y), 7);
+        if (!col_lane) cw = make_float4(0.f, 0.f, 0.f, 0.f);
+        prefetch(0, kk, last_pass);
+        ++pos;
+        wait_chunk();
+        uint4 hd;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hd.x), "=r"(hd.y), "=r"(hd.z), "=r"(hd.w)
+                     : "r"(ring + (uint32_t)(pos % RING) * AS2_CHUNK + lane * 16));
+        prefetch(1, kk, last_pass);
+        ++pos;
         const bool cl0 = cw.x != 0.f, c1 = cw.y != 0.f, c2 = cw.z != 0.f, c3 = cw.w != 0.f;
-        const unsigned char* ca = smem_raw + g.co.x;
-        const unsigned char* cb = smem_raw + g.co.y;
+        const unsigned char* ca = smem_raw + hd.x;
+        const unsigned char* cb = smem_raw + hd.y;
+        const uint32_t orow = hd.w;
         float2 acc[P][2];
 #pragma unroll
         for (int k = 0; k < P; ++k) acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
-        // one pixel row: T = sum over this column's (<= 4) pixels, then into the seven bin-row accumulators
-        auto process = [&](const RowRec& q) {
-            const unsigned char* pa = ca + q.lo.x;
-            const unsigned char* pb = cb + q.lo.x;
+        auto process = [&](uint32_t raddr) {
+            uint4 lo, hi;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(raddr));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                         : "r"(raddr + 16));
+            const unsigned char* pa = ca + lo.x;
+            const unsigned char* pb = cb + lo.x;
             float2 t01 = make_float2(0.f, 0.f), t23 = make_float2(0.f, 0.f);
             if (cl0) {
                 const float4 v = *reinterpret_cast<const float4*>(pa);
@@ -1977,8 +2032,6 @@ __global__ void __launch_bounds__(THREADS, 2) roi_align_stream_kernel(RoiArgs a)
                 fma2(t01, make_float2(v.x, v.y), cw.y);
                 fma2(t23, make_float2(v.z, v.w), cw.y);
             }
-            // (no warp-uniform skip of the second pair: straight-line code lets the scheduler hoist the loads of all
-            //  three rows of an unrolled group above their FMAs; a dead slot costs two predicated-off issue slots)
             if (c2) {
                 const float4 v = *reinterpret_cast<const float4*>(pb);
                 fma2(t01, make_float2(v.x, v.y), cw.z);
@@ -1989,43 +2042,35 @@ __global__ void __launch_bounds__(THREADS, 2) roi_align_stream_kernel(RoiArgs a)
                 fma2(t01, make_float2(v.x, v.y), cw.w);
                 fma2(t23, make_float2(v.z, v.w), cw.w);
             }
-            const float wk[P] = {__uint_as_float(q.lo.y), __uint_as_float(q.lo.z), __uint_as_float(q.lo.w),
-                                 __uint_as_float(q.hi.x), __uint_as_float(q.hi.y), __uint_as_float(q.hi.z),
-                                 __uint_as_float(q.hi.w)};
+            const float wk[P] = {__uint_as_float(lo.y), __uint_as_float(lo.z), __uint_as_float(lo.w), __uint_as_float(hi.x),
+                                 __uint_as_float(hi.y), __uint_as_float(hi.z), __uint_as_float(hi.w)};
 #pragma unroll
             for (int k = 0; k < P; ++k) {
                 fma2(acc[k][0], t01, wk[k]);
                 fma2(acc[k][1], t23, wk[k]);
             }
         };
-        int i = 0;
-        for (; i + 3 <= nmin; i += 3) {  // every RoI of the warp has these rows: no per-RoI predicate
-            process(ra);
-            load_row(rows, n, i + 3, ra);
-            process(rb);
-            load_row(rows, n, i + 4, rb);
-            process(rc);
-            load_row(rows, n, i + 5, rc);
-        }
-        for (; i < nmax; i += 3) {       // ragged end: rows some RoIs of the warp do not have
-            if (i < n) process(ra);
-            load_row(rows, n, i + 3, ra);
-            if (i + 1 < nmax) {
-                if (i + 1 < n) process(rb);
-                load_row(rows, n, i + 4, rb);
+        for (int c = 0; c < kk; ++c) {
+            wait_chunk();
+            const uint32_t cbase = ring + (uint32_t)(pos % RING) * AS2_CHUNK + g * 32;
+            const int left = nmax - 4 * c;  // rows of this chunk some RoI of the warp really has (warp-uniform)
+            if (left >= 4) {
+                process(cbase);
+                process(cbase + 128);
+                process(cbase + 256);
+                process(cbase + 384);
+            } else {
+                if (left > 0) process(cbase);
+                if (left > 1) process(cbase + 128);
+                if (left > 2) process(cbase + 256);
             }
-            if (i + 2 < nmax) {
-                if (i + 2 < n) process(rc);
-                load_row(rows, n, i + 5, rc);
-            }
+            prefetch(AS2_HDR + c, kk, last_pass);
+            ++pos;
         }
-        // first rows of the NEXT RoI: their L2 round trip hides behind this RoI's stores
-        load_row(rows_of(r_next), nxt.n, 0, ra);
-        load_row(rows_of(r_next), nxt.n, 1, rb);
-        load_row(rows_of(r_next), nxt.n, 2, rc);
         // the staging block is free once the previous bulk store has READ it
         if (store_pending && ql == P) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
+        const bool valid = orow != 0xFFFFFFFFu;
         if (col_lane && valid) {
 #pragma unroll
             for (int k = 0; k < P; ++k) {
@@ -2038,7 +2083,7 @@ __global__ void __launch_bounds__(THREADS, 2) roi_align_stream_kernel(RoiArgs a)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
         __syncwarp();
         if (ql == P && valid) {
-            float* dst = a.out + ((size_t)roi_at(a, r) * a.C + c0) * BINS;
+            float* dst = a.out + ((size_t)orow * a.C + c0) * BINS;
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(stg)),
                          "n"(4 * BINS * 4)
                          : "memory");
@@ -2046,6 +2091,7 @@ __global__ void __launch_bounds__(THREADS, 2) roi_align_stream_kernel(RoiArgs a)
             store_pending = true;
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (store_pending && ql == P) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // before the CTA's smem goes away
 }
 
@@ -2290,6 +2336,7 @@ struct RoiWs {
     int* perm;
     int* offs;
     int* sorted;  // streaming RoIAlign: rows of every image, longest row program first
+    unsigned char* prog;  // streaming RoIAlign: the records re-laid per (pass, warp) by roi_align_stream_pack_kernel
     int2* ent;  // [num_rois][<= 144] bin / sample geometry of the inference table kernels (roi_pool_entries_kernel: 2*P
                 // words per RoI, roi_align_entries_kernel: 2*P*SR, roi_align_fast_entries_kernel: 2*P*3,
                 // roi_align_stream_entries_kernel: AS_REC bytes)
@@ -2301,6 +2348,8 @@ static size_t roi_layout(Workspace& ws, int batch, int num_rois, RoiWs* out) {
     w.offs = ws.take<int>(batch + 2);
     w.sorted = ws.take<int>(num_rois > 0 ? num_rois : 1);
     w.ent = ws.take<int2>((size_t)(num_rois > 0 ? num_rois : 1) * 144);  // up to 1152 bytes per RoI (streaming RoIAlign)
+    // streaming RoIAlign, packed per-warp programs: one AS2_SLOT per 4 RoIs, passes of >= 24 RoIs, one ragged pass per image
+    w.prog = ws.take<unsigned char>(((size_t)(num_rois > 0 ? num_rois : 1) / 24 + batch + 2) * 8 * AS2_SLOT);
     if (out) *out = w;
     return ws.off;
 }
@@ -2488,18 +2537,20 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
     static const int align_impl = env_int("FRCNN_ALIGN_IMPL", 0);  // experiments only: 1 = thread-per-bin fast kernel
     if (align && !exact && sampling_ratio == 2 && PH == 7 && PW == 7 && C % 4 == 0 && align_impl != 1 &&
         (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-        // streaming variant: column threads, every pixel row read once per bin column, TMA bulk stores
+        // streaming variant: column threads, every pixel row read once per bin column, row programs through a
+        // per-warp shared-memory ring, TMA bulk stores (see roi_align_stream2_kernel)
         static const int pitch_override = env_int("FRCNN_ALIGN_PITCH", 0);
         a.pitch = pitch_override >= W ? pitch_override : (W | 1);
         static const int th_override = env_int("FRCNN_ALIGN_THREADS", 0);  // experiments only
-        const int TH = th_override == 384 ? 384 : 256;  // 384: 80 registers with spills, measured slower (0.56 vs 0.52 ms)
-        const size_t tab_bytes = (size_t)((H * a.pitch + 3) & ~3) * sizeof(float4);
-        const size_t region = std::max((size_t)4 * H * W * sizeof(float), (size_t)(TH / 8) * AS_STAGE);
-        const size_t ssmem = tab_bytes + region;
-        if (ssmem <= 110 * 1024) {  // two CTAs per SM
+        const int T2 = th_override == 256 || th_override == 224 ? th_override : 192;  // cfg4: 0.432 / 0.444 / 0.464 ms
+        const int NQ2 = T2 / 8, RING2 = T2 == 224 ? 3 : 4;
+        const size_t tab2 = ((size_t)(H + 1) * a.pitch * 16 + 127) & ~(size_t)127;
+        const size_t smem2 = tab2 + (size_t)NQ2 * AS_STAGE + (size_t)(T2 / 32) * RING2 * AS2_CHUNK;
+        if (smem2 <= 110 * 1024) {  // at least two CTAs per SM (three on maps up to 50 x 50)
             a.CS = 4;
             const int slabs = C / 4;
-            a.groups = std::max(1, std::min(cdiv(cdiv(K, B), 4 * (TH / 8)), cdiv(8 * sm_count(), B * slabs)));
+            const int passes = cdiv(cdiv(K, B), NQ2);
+            a.groups = std::max(1, std::min(cdiv(passes, 4), cdiv(8 * sm_count(), B * slabs)));
             Workspace ews(workspace, workspace_bytes);
             RoiWs w;
             roi_layout(ews, B, K, &w);
@@ -2507,24 +2558,28 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
                 set_error("%s: workspace too small or misaligned (%zu needed, %zu given)", who, ews.off, workspace_bytes);
                 return FRCNN_ERR_WORKSPACE;
             }
+            FRCNN_CHECK_ARG(slabs <= 65535 && B <= 65535, "roi op: too many channel slabs / images");
             roi_align_stream_entries_kernel<<<cdiv(K, 128), 128, 0, stream>>>(a, (unsigned char*)w.ent);
             FRCNN_LAUNCH_CHECK();
             roi_align_stream_sort_kernel<<<B, 256, 0, stream>>>(a, (const unsigned char*)w.ent, w.sorted);
             FRCNN_LAUNCH_CHECK();
             a.ent = w.ent;
             a.perm2 = w.sorted;
-            FRCNN_CHECK_ARG(slabs <= 65535 && B <= 65535, "roi op: too many channel slabs / images");
-            const dim3 grid(a.groups, slabs, B);
-            if (TH == 256) {
-                FRCNN_SMEM((roi_align_stream_kernel<256>), ssmem);
-                roi_align_stream_kernel<256><<<grid, 256, ssmem, stream>>>(a);
-            } else {
-                FRCNN_SMEM((roi_align_stream_kernel<384>), ssmem);
-                roi_align_stream_kernel<384><<<grid, 384, ssmem, stream>>>(a);
-            }
-            FRCNN_LAUNCH_CHECK();
-            note_roi_kernel("roi_align_stream_kernel<%d> pitch %d", TH, a.pitch);
-            return FRCNN_OK;
+            const dim3 pgrid(passes, B), grid2(a.groups, slabs, B);
+#define FRCNN_STREAM2(TH_, MB_, RG_)                                                                              \
+    do {                                                                                                         \
+        roi_align_stream_pack_kernel<TH_><<<pgrid, TH_, 0, stream>>>(a, (const unsigned char*)w.ent, w.sorted, w.prog); \
+        FRCNN_LAUNCH_CHECK();                                                                                    \
+        FRCNN_SMEM((roi_align_stream2_kernel<TH_, MB_, RG_>), smem2);                                            \
+        roi_align_stream2_kernel<TH_, MB_, RG_><<<grid2, TH_, smem2, stream>>>(a, w.prog);                       \
+        FRCNN_LAUNCH_CHECK();                                                                                    \
+        note_roi_kernel("roi_align_stream2_kernel<%d,%d,%d> pitch %d", TH_, MB_, RG_, a.pitch);                  \
+        return FRCNN_OK;                                                                                         \
+    } while (0)
+            if (T2 == 256) FRCNN_STREAM2(256, 2, 4);
+            if (T2 == 224) FRCNN_STREAM2(224, 3, 3);
+            FRCNN_STREAM2(192, 3, 4);
+#undef FRCNN_STREAM2
         }
     }
     if (align && !exact && sampling_ratio == 2 && PH == PW && (PH == 7 || PH == 14)) {
