@@ -167,7 +167,9 @@ def test_nms_adaptive_superblocks_mixed_keep_rates(F, O):
     for i, b in enumerate(imgs):
         batch[i, :len(b)] = b
     refs = [O.nms(b, np.arange(len(b), 0, -1, dtype=np.float32), 0.7) if len(b) else np.zeros(0, np.int64) for b in imgs]
-    for cap in (2000, 1100, 100):  # 2 * cap > 2048: the adaptive schedule; 100: the fixed one
+    # default schedule = first block, one or two adaptive blocks, then nms_tail_kernel (a cluster per image looping
+    # over whatever is left): the dense and the collapsing images need many tail rounds, the sparse ones none
+    for cap in (2000, 1100, 100):
         keep, n_keep = F.nms_sorted(T(batch), T(n_sel), 0.7, cap)
         fixed, n_fixed = F.nms_sorted(T(batch), T(n_sel), 0.7, cap, superblock=1024)  # fixed schedule, same answer
         for i, ref in enumerate(refs):

@@ -603,14 +603,13 @@ __device__ __forceinline__ int nms_block_len(const NmsArgs& a, const NmsState& s
 
 // one mask tile (in-block triangle tile, or suppression of a column block by a chunk of the kept list)
 __device__ __forceinline__ void nms_mask_tile(const NmsArgs& a, int b, const NmsState& st, float4* srow,
-                                              float* sarea) {
+                                              float* sarea, int t, int tiles_total) {
     const int n = a.n_sel[b];
     const int c0 = st.c_next;
     if (c0 >= n) return;
     const int c1 = min(c0 + nms_block_len(a, st, n), n);
     const float4* boxes = a.boxes + (size_t)b * a.row_stride;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int t = blockIdx.x;
     if (t < a.tri_tiles) {
         // in-block tile: decode t -> (cb, rb), rb < 4*(cb+1)
         int cb = 0;
@@ -647,7 +646,7 @@ __device__ __forceinline__ void nms_mask_tile(const NmsArgs& a, int b, const Nms
         // more, shorter chunks, and a chunk is a serial loop of exact IoUs per column thread -- the latency of
         // the launch when only a few column blocks are live.
         t -= a.tri_tiles;
-        const int ntile = (int)gridDim.x - a.tri_tiles;
+        const int ntile = tiles_total - a.tri_tiles;
         const int ncb = (c1 - c0 + NMS_CB - 1) / NMS_CB;
         const int nchunk = ntile / ncb;  // >= ceil(keep_cap / NMS_KC), so a chunk has at most NMS_KC rows
         const int cb = t % ncb, kc = t / ncb;
@@ -658,7 +657,8 @@ __device__ __forceinline__ void nms_mask_tile(const NmsArgs& a, int b, const Nms
         const int col0 = c0 + cb * NMS_CB;
         const int kn = min(per, st.n_kept - k0);
         if (threadIdx.x < kn) {
-            float4 v = a.kept_box[(size_t)b * a.keep_cap + k0 + threadIdx.x];
+            // L2 read: inside nms_tail_kernel the list grows between two reads of the same line
+            float4 v = __ldcg(a.kept_box + (size_t)b * a.keep_cap + k0 + threadIdx.x);
             srow[threadIdx.x] = v;
             sarea[threadIdx.x] = box_area(v);
         }
@@ -1022,7 +1022,7 @@ __global__ void __launch_bounds__(NMS_MAX_WORDS) nms_block_kernel(NmsArgs a) {
     const int b = blockIdx.y;
     const NmsState st = a.state[b];
     if (st.done) return;  // set by an earlier launch: identical for all CTAs of this image
-    nms_mask_tile(a, b, st, srow, sarea);
+    nms_mask_tile(a, b, st, srow, sarea, (int)blockIdx.x, (int)gridDim.x);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1034,6 +1034,50 @@ __global__ void __launch_bounds__(NMS_MAX_WORDS) nms_block_kernel(NmsArgs a) {
     if (!s_last) return;
     __threadfence();
     nms_scan_image(a, b, st, R, ring);
+}
+
+// Whatever the sized launches leave over, in ONE launch.  The default schedule sizes its first super-block to finish
+// the job and lets one or two adaptive ones follow; covering the worst case (every candidate) used to take a further
+// row_stride / 2048 launches that found `done` set and returned -- 13 of them, ~2.5 us each, on the 30 000-candidate
+// configuration.  Here a cluster of 8 CTAs per image (co-resident by construction, so a cluster barrier is a safe
+// image-wide barrier) loops over super-blocks itself: the mask tiles are dealt over the cluster's CTAs, cluster
+// barrier, CTA 0 scans, cluster barrier, until keep_cap boxes are kept or the candidates run out.  An image that is
+// already done costs one state read.  Everything that crosses CTAs inside the loop is read from L2 (__ldcg /
+// cp.async.cg): state, removed words, mask, kept boxes.
+constexpr int NMS_TAIL_CL = 8;
+__global__ void __cluster_dims__(NMS_TAIL_CL, 1, 1) __launch_bounds__(NMS_MAX_WORDS) nms_tail_kernel(NmsArgs a) {
+    __shared__ float4 srow[NMS_KC];
+    __shared__ float sarea[NMS_KC];
+    __shared__ uint32_t R[NMS_MAX_WORDS];
+    __shared__ __align__(16) uint32_t ring[NMS_RING_STAGES * NMS_RING_WORDS * 32];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int b = blockIdx.x / NMS_TAIL_CL;
+    const int rank = (int)cluster.block_rank();
+    const int n = a.n_sel[b];
+    const int tiles_total = (int)a.tri_tiles + (a.len / NMS_CB) * ((a.keep_cap + NMS_KC - 1) / NMS_KC);
+    for (;;) {
+        NmsState st;
+        {
+            const int4 v = __ldcg(reinterpret_cast<const int4*>(a.state + b));
+            st.n_kept = v.x;
+            st.done = v.y;
+            st.c_next = v.z;
+            st.pad = v.w;
+        }
+        if (st.done) break;  // identical in every CTA of the cluster
+        if (st.c_next < n) {
+            for (int t = rank; t < tiles_total; t += NMS_TAIL_CL) {
+                nms_mask_tile(a, b, st, srow, sarea, t, tiles_total);
+                __syncthreads();  // srow / sarea are reused by the next tile
+            }
+        }
+        __threadfence();
+        cluster.sync();
+        if (rank == 0) nms_scan_image(a, b, st, R, ring);  // sets done when the candidates are exhausted
+        __threadfence();
+        cluster.sync();
+    }
 }
 
 // nets/rpn.py:65-69: pad with arange, truncate, gather
@@ -1153,6 +1197,28 @@ static int run_nms_sorted(const float* sorted_boxes, const int32_t* n_sel, int b
         lens.push_back(len);
         total += len;
         if (superblock <= 0) len = std::min(2 * len, a.S);
+    }
+    if (superblock <= 0 && s0 < row_stride && 2 * keep_cap <= row_stride) {  // (keep_cap ~ n: plain NMS, all rounds wide)
+        // default schedule: the first block (sized for keep_cap), one adaptive block -- two when the first cannot
+        // finish the job by itself -- and nms_tail_kernel for whatever is left (usually nothing)
+        const int n_adaptive = s0 < 2 * keep_cap ? 2 : 1;
+        a.adaptive = 1;
+        a.cover_after = 1 << 30;  // the tail covers every candidate: later blocks may be cut freely
+        for (int i = 0; i <= n_adaptive; ++i) {
+            a.len = i == 0 ? s0 : a.S;
+            const int ncb = a.len / NMS_CB;
+            a.tri_tiles = 2 * ncb * (ncb + 1);
+            const int prev_tiles = i > 0 ? ncb * cdiv(keep_cap, NMS_KC) : 0;
+            dim3 grid(a.tri_tiles + prev_tiles, batch);
+            nms_block_kernel<<<grid, NMS_CB, 0, stream>>>(a);
+            FRCNN_LAUNCH_CHECK();
+        }
+        a.len = std::min(a.S, 1024);  // 8 CTAs per image: 40 + 4 * ceil(keep_cap / 256) tiles per round
+        const int ncb = a.len / NMS_CB;
+        a.tri_tiles = 2 * ncb * (ncb + 1);
+        nms_tail_kernel<<<batch * NMS_TAIL_CL, NMS_CB, 0, stream>>>(a);
+        FRCNN_LAUNCH_CHECK();
+        return FRCNN_OK;
     }
     // Long schedules get one spare launch: its coverage is the slack that lets the device cut later super-blocks
     // to what an image still needs (nms_block_len); a no-op launch costs ~2 us, a needless 2048-wide mask ~100
