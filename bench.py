@@ -2,7 +2,7 @@
 """bench.py -- the proposal-and-RoI hot path on synthetic inputs.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
-                    [--no-extra-workloads] [--no-cpu-baseline]
+                    [--no-extra-workloads] [--no-cpu-baseline] [--no-graphs]
 
 A step = one pass of the hot path over one batch: RPN proposals (decode, clip, min-size, top-k, NMS,
 pad/gather) for B images, then the RoI head's coordinate map + RoI gather of every proposal.
@@ -238,6 +238,8 @@ class Workload:
                          for _ in range(2)] if world > 1 else None
         self.works = [None, None]
         self.wait_ev = []
+        self.graphs = None           # capture(): the step replayed from CUDA graphs
+        self.replayed_launches = 0   # kernels inside the graphs replayed so far (counted at capture time)
         n_alg = self.K * C * P * P * 4 * (2 if self.train else 1) + self.K * 20 + B * C * H * W * 4
         self.alg_bytes = n_alg  # gather kernel: output (+ int32 argmax when training) + rois + features once
 
@@ -256,17 +258,56 @@ class Workload:
         else:
             F.roi_align_forward(feat, rois5, P, 1.0, 2, False, out=self.pooled, rois_per_image=self.rois_per_image)
 
-    def step(self, i, ev=None, collective=True):
-        import torch.distributed as dist
+    def front(self, s):
+        """Proposal layer (+ target assignment when training) on input set s -> (rois, status, RoIs for the gather)."""
         F, cfg = self.F, self.cfg
-        loc, logits, feat = self.sets[i % 3]
-        if ev:
-            ev["p0"][i].record()
+        loc, logits, _ = self.sets[s]
         rois, src, n_keep, status = F.proposals(loc, logits, **self.pkw)
         sel = rois
         if self.train:
             F.anchor_targets(self.gt_box, self.n_gt, base=self.base, feat_stride=16, feat_hw=(cfg["H"], cfg["W"]))
             sel, _, _, _, _ = F.proposal_targets(rois, self.gt_box, self.gt_lab, self.n_gt)
+        return rois, status, sel
+
+    def capture(self):
+        """The step as CUDA graphs, one pair per input set: (proposal layer [+ targets]) and (RoI gather).  The only
+        thing between the two is the NCCL all-gather of the rois (N > 1), issued from the stream as before.  A step
+        is ~14-25 launches of 2-90 us kernels: replaying them removes the launch gaps (cfg2: ~30 us of 840)."""
+        from two_stage_object_detection_b200 import _lib
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):  # warm-up on a capture-like stream: per-stream workspaces, smem attributes
+            for s in range(3):
+                self.gather(self.sets[s][2], self.front(s)[2])
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        graphs = []
+        for s in range(3):
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(ga):
+                rois, status, sel = self.front(s)
+            n1 = _lib.launch_count()
+            with torch.cuda.graph(gb):
+                self.gather(self.sets[s][2], sel)
+            n2 = _lib.launch_count()
+            graphs.append(dict(front=ga, back=gb, rois=rois, status=status, launches=n2 - n0))
+        self.graphs = graphs
+
+    def step(self, i, ev=None, collective=True):
+        import torch.distributed as dist
+        F, cfg = self.F, self.cfg
+        loc, logits, feat = self.sets[i % 3]
+        g = self.graphs[i % 3] if self.graphs else None
+        if ev:
+            ev["p0"][i].record()
+        if g:
+            g["front"].replay()
+            rois, status = g["rois"], g["status"]
+            self.replayed_launches += g["launches"]
+        else:
+            rois, status, sel = self.front(i % 3)
         if ev:
             ev["p1"][i].record()
         if self.world > 1 and collective:
@@ -282,7 +323,10 @@ class Workload:
             self.works[slot] = dist.all_gather_into_tensor(self.gathered[slot], rois, async_op=True)
         if ev:
             ev["r0"][i].record()
-        self.gather(feat, sel)
+        if g:
+            g["back"].replay()
+        else:
+            self.gather(feat, sel)
         if ev:
             ev["r1"][i].record()
         return rois, status
@@ -315,13 +359,13 @@ def measure(wl, steps, warmup, clk=None):
     barrier(wl.world)  # ranks aligned, streams idle: nothing (NVML start-up, warm-up tails) leaks into the region
     if clk:
         clk.mark()
-    n0 = _lib.launch_count()
+    n0 = _lib.launch_count() + wl.replayed_launches
     t0.record()
     for i in range(warmup, total):
         rois, status = wl.step(i, ev)
     wl.drain()
     t1.record()
-    n1 = _lib.launch_count()
+    n1 = _lib.launch_count() + wl.replayed_launches
     barrier(wl.world)
     ms = t0.elapsed_time(t1)
     sl = slice(warmup, total)
@@ -342,7 +386,7 @@ def traffic_for(kernel_name):
         return None
     with open(tpath) as f:
         for rec in json.load(f).values():
-            if rec.get("kernel") == kernel_name:
+            if rec.get("kernel", "").replace(" ", "") == kernel_name.replace(" ", ""):
                 return rec.get("dram_bytes")
     return None
 
@@ -385,6 +429,15 @@ def run_ours(args):
     B, H, W, C, P = cfg["batch"], cfg["H"], cfg["W"], cfg["C"], cfg["P"]
     S, n_post = cfg["img"], cfg["n_post"]
     wl = Workload(name, dev, rank, world)
+    launch_mode = "stream launches (--no-graphs)"
+    if not args.no_graphs:
+        try:
+            wl.capture()
+            launch_mode = ("CUDA graph replay: one graph for the proposal layer, one for the RoI gather, per input set"
+                           + ("; the NCCL all-gather is issued from the stream between them" if world > 1 else ""))
+        except Exception as exc:  # the kernel-by-kernel path is always there
+            wl.graphs = None
+            launch_mode = f"stream launches (graph capture failed: {type(exc).__name__}: {exc})"
     clk = ClockSampler(local).start()  # NVML is open and sampling BEFORE the ranks are aligned
     m, rois = measure(wl, args.steps, args.warmup, clk)
     clk.stop()
@@ -407,35 +460,13 @@ def run_ours(args):
         sharded_parity = bool(flag.item() == 1.0)
         del other, exp
 
-    # ---- the same step replayed from CUDA graphs (one per input set; informational) -------------------
-    graph_ms = None
-    if world == 1 and not wl.train:
-        try:
-            side = torch.cuda.Stream(dev)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for i in range(3):
-                    wl.step(i)
-            torch.cuda.current_stream().wait_stream(side)
-            graphs = []
-            for i in range(3):
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr):
-                    wl.step(i)
-                graphs.append(gr)
-            for i in range(3):
-                graphs[i].replay()
-            torch.cuda.synchronize()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            for i in range(args.steps):
-                graphs[i % 3].replay()
-            g1.record()
-            torch.cuda.synchronize()
-            graph_ms = g0.elapsed_time(g1) / args.steps
-            del graphs
-        except Exception as exc:  # graphs are an extra, never the reported value
-            graph_ms = f"unavailable: {exc}"
+    # ---- the same step launched kernel by kernel from the stream (informational: what the graphs save) ----------
+    stream_ms = None
+    if wl.graphs and world == 1:
+        saved, wl.graphs = wl.graphs, None
+        ms2, _ = measure(wl, min(args.steps, 20), 3)
+        stream_ms = ms2["ms_step"]
+        wl.graphs = saved
 
     # ---- the head's gather when its classifier is the global average (HarDNet): fused kernel, [K,C] out ------
     fused_ms = None
@@ -468,7 +499,8 @@ def run_ours(args):
         "proposals_per_sec": world * B * n_post / (ms_step * 1e-3),
         "breakdown_ms": {"proposals": m["prop_ms"], "roi_gather": m["roi_ms"]},
         "fused_head_gather_ms": fused_ms,  # RoI gather + global-average classifier in one kernel (informational)
-        "cuda_graph_ms_per_step": graph_ms,
+        "launch_mode": launch_mode,
+        "stream_launch_ms_per_step": stream_ms,  # the same step without graphs (informational)
         "e2e": e2e,
         "gpu_launches": launches,  # counted by the library (frcnn_launch_count) over the timed region of this rank
         "roofline": roof,
@@ -488,13 +520,19 @@ def run_ours(args):
             if other == name:
                 continue
             w2 = Workload(other, dev, rank, world)
+            if not args.no_graphs:
+                try:
+                    w2.capture()
+                except Exception:
+                    w2.graphs = None
             m2, _ = measure(w2, min(args.steps, 20), max(3, min(args.warmup, 5)))
             ms2, = max_over_ranks([m2["ms_step"]], dev, world)
             c2 = WORKLOADS[other]
             extra[other] = {"desc": c2["desc"], "ms_per_step": ms2, "images_per_s": world * c2["batch"] / (ms2 * 1e-3),
                             "proposals_per_s": world * c2["batch"] * c2["n_post"] / (ms2 * 1e-3),
                             "breakdown_ms": {"proposals": m2["prop_ms"], "roi_gather": m2["roi_ms"]},
-                            "gpu_launches": m2["launches"], "roofline": roofline_obj(w2, m2)}
+                            "gpu_launches": m2["launches"], "graphs": w2.graphs is not None,
+                            "roofline": roofline_obj(w2, m2)}
             del w2
             torch.cuda.empty_cache()
         out["workloads"] = extra
@@ -725,6 +763,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-workloads", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the stream instead of replaying CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

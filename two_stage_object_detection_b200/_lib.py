@@ -157,6 +157,10 @@ _ws_cache: dict = {}
 
 def workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
     """Growable per-(device, stream) scratch buffer; reuse is safe because work is stream-ordered."""
+    if torch.cuda.is_current_stream_capturing():
+        # under CUDA-graph capture the buffer must belong to the graph being captured (its private memory pool):
+        # a cached one may come from the pool of a graph that no longer exists
+        return torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
     key = (dev.index, stream_ptr(dev))
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
