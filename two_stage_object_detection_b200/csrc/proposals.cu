@@ -362,7 +362,9 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
     return m;
 }
 
-__global__ void __cluster_dims__(TK_CL, 1, 1) __launch_bounds__(TK_THREADS)
+// CL = CTAs per cluster = per image (4 or 8; the launch sets the cluster dimension, see run_topk).
+template <int CL>
+__global__ void __launch_bounds__(TK_THREADS)
 topk_sort_dsmem_kernel(const uint32_t* __restrict__ keys_all, const float4* __restrict__ boxes_all, int n,
                        int k_cap, int seg, int* __restrict__ order_all, int* __restrict__ n_sel_all,
                        float4* __restrict__ sorted_all) {
@@ -377,7 +379,7 @@ topk_sort_dsmem_kernel(const uint32_t* __restrict__ keys_all, const float4* __re
     __shared__ uint32_t s_nzero;
 
     const int crank = (int)cluster.block_rank();
-    const int b = blockIdx.x / TK_CL;
+    const int b = blockIdx.x / CL;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* keys = keys_all + (size_t)b * n;
     const uint32_t lt = lanemask_lt();
@@ -436,7 +438,7 @@ topk_sort_dsmem_kernel(const uint32_t* __restrict__ keys_all, const float4* __re
                 const uint32_t pos = offs[d] + cnt[(e * TK_WARPS + warp) * 256 + d] + rank[e];
                 uint32_t dc = 0;  // owner of position pos
 #pragma unroll
-                for (int c = 1; c < TK_CL; ++c) dc += pos >= (uint32_t)(c * seg);
+                for (int c = 1; c < CL; ++c) dc += pos >= (uint32_t)(c * seg);
                 uint2* remote = cluster.map_shared_rank(buf0 + (size_t)dst * seg, dc);
                 remote[pos - dc * seg] = kv[e];
             }
@@ -479,7 +481,7 @@ topk_sort_dsmem_kernel(const uint32_t* __restrict__ keys_all, const float4* __re
         uint32_t total = 0, pre = 0;
         if (tid < 256) {
 #pragma unroll
-            for (int c = 0; c < TK_CL; ++c) {
+            for (int c = 0; c < CL; ++c) {
                 uint32_t v = cluster.map_shared_rank(hist, c)[tid];
                 pre += c < crank ? v : 0u;
                 total += v;
@@ -528,7 +530,7 @@ topk_sort_dsmem_kernel(const uint32_t* __restrict__ keys_all, const float4* __re
     }
     uint32_t nzero = 0;
 #pragma unroll
-    for (int c = 0; c < TK_CL; ++c) nzero += *cluster.map_shared_rank(&s_nzero, c);
+    for (int c = 0; c < CL; ++c) nzero += *cluster.map_shared_rank(&s_nzero, c);
     const int n_valid = n - (int)nzero;
     const int n_sel = n_valid < k_cap ? n_valid : k_cap;
     if (crank == 0 && tid == 0) n_sel_all[b] = n_sel;
@@ -1254,13 +1256,49 @@ static int run_topk(const uint32_t* keys, const float* boxes, int batch, int n, 
         set_error("topk: workspace too small or misaligned (%zu needed, %zu given)", ws.off, workspace_bytes);
         return FRCNN_ERR_WORKSPACE;
     }
-    const int seg = (n + TK_CL - 1) / TK_CL;
-    const size_t dsmem = TK_SMEM + (size_t)2 * seg * sizeof(uint2);
-    if (dsmem <= 200 * 1024 && k_cap <= n) {  // keys stay in distributed shared memory
-        FRCNN_SMEM(topk_sort_dsmem_kernel, dsmem);
-        topk_sort_dsmem_kernel<<<batch * TK_CL, TK_THREADS, dsmem, stream>>>(
-            keys, (const float4*)boxes, n, k_cap, seg, order, n_sel, (float4*)sorted_boxes);
-    } else {  // global-memory ping-pong buffers
+    // cluster size per image: 8 CTAs, or 4 when 8 per image would need well over one wave of the GPU and 4 fit in one
+    // (B = 32 images of 22 500 keys: 158 -> 131 us for the whole proposal stage).  16 (non-portable) was measured
+    // slower than 8 everywhere (B = 8 x 36 864 keys: 236 vs 205 us): the cluster barriers cost more than the shorter
+    // segments save.
+    static const int cl_override = []() { const char* v = getenv("FRCNN_TOPK_CL"); return v && *v ? atoi(v) : 0; }();
+    int cl = 8;
+    if (batch * 8 > sm_count() + sm_count() / 2 && batch * 4 <= sm_count()) cl = 4;
+    if (cl_override == 4 || cl_override == 8) cl = cl_override;
+    for (; k_cap <= n; cl = 8) {
+        const int seg = (n + cl - 1) / cl;
+        const size_t dsmem = TK_SMEM + (size_t)2 * seg * sizeof(uint2);
+        if (dsmem > 200 * 1024) {
+            if (cl == 8) break;
+            continue;
+        }
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(batch * cl);
+        cfg.blockDim = dim3(TK_THREADS);
+        cfg.dynamicSmemBytes = dsmem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = cl;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaSuccess;
+        const float4* bx = (const float4*)boxes;
+        float4* sb = (float4*)sorted_boxes;
+        if (cl == 4) {
+            FRCNN_SMEM(topk_sort_dsmem_kernel<4>, dsmem);
+            e = cudaLaunchKernelEx(&cfg, topk_sort_dsmem_kernel<4>, keys, bx, n, k_cap, seg, order, n_sel, sb);
+        } else {
+            FRCNN_SMEM(topk_sort_dsmem_kernel<8>, dsmem);
+            e = cudaLaunchKernelEx(&cfg, topk_sort_dsmem_kernel<8>, keys, bx, n, k_cap, seg, order, n_sel, sb);
+        }
+        FRCNN_CUDA(e);
+        count_launch();
+        return FRCNN_OK;
+    }
+    {  // global-memory ping-pong buffers
         FRCNN_SMEM(topk_sort_kernel, TK_SMEM);
         topk_sort_kernel<<<batch * TK_CL, TK_THREADS, TK_SMEM, stream>>>(keys, (const float4*)boxes, n, k_cap, wk, wi,
                                                                          order, n_sel, (float4*)sorted_boxes);
