@@ -193,13 +193,34 @@ def check_detections(rng, it):
     assert np.array_equal(N(F.bbox_iou(T(a), T(b2))), O.iou(a, b2)), tag + f" iou {na}x{nb}"
 
 
+def check_align_stream(rng, it):
+    """The streaming RoIAlign kernel (7x7 bins, 2x2 sampling grid, channels a multiple of four): ragged images, grouped
+    and bucketed RoI lists, degenerate / inverted / out-of-map RoIs, against the oracle at 1e-5 of the largest feature."""
+    B, Cc = int(rng.integers(1, 5)), 4 * int(rng.integers(1, 5))
+    H, W = int(rng.integers(5, 70)), int(rng.integers(5, 70))
+    per = int(rng.integers(1, 90))
+    grouped = bool(rng.integers(0, 2))
+    K = per * B if grouped else int(rng.integers(1, 300))
+    feat = rng.standard_normal((B, Cc, H, W)).astype(np.float32)
+    rois = rand_rois(rng, K, B, H, W)
+    if grouped:
+        rois[:, 0] = np.repeat(np.arange(B), per)
+    al = bool(rng.integers(0, 2))
+    scale = float(rng.choice([1.0, 0.5, 0.25]))
+    tag = f"align-stream it={it} B={B} C={Cc} H={H} W={W} K={K} grouped={grouped} aligned={al} scale={scale}"
+    ref = O.roi_align(feat, rois, 7, scale, 2, al)
+    got = N(F.roi_align_forward(T(feat), T(rois), 7, scale, 2, al, exact=False, rois_per_image=per if grouped else 0))
+    assert F._lib.last_roi_kernel().startswith("roi_align_stream2"), tag + " took " + F._lib.last_roi_kernel()
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(feat).max(), tag
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--seed", type=int, default=0)
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
-    checks = [check_roi, check_targets, check_proposals, check_detections, check_long_nms]
+    checks = [check_roi, check_targets, check_proposals, check_detections, check_long_nms, check_align_stream]
     counts = {c.__name__: 0 for c in checks}
     for it in range(args.iters):
         for c in checks:
