@@ -1741,76 +1741,78 @@ constexpr int AS_ROWS_OFF = 192; // row program starts here: 32 bytes per row {u
 constexpr int AS_MAX_ROWS = 30;
 constexpr int AS_STAGE = 800;    // bytes between staging blocks (784 used; 800: the four RoIs of a warp on distinct banks)
 
+// One WARP per RoI: lanes 0..6 compute the merged per-axis taps of the seven bin rows, lanes 8..14 those of the
+// seven bin columns (the column lanes write their weights / offsets straight into the record); the row lanes publish
+// theirs through shared memory, and then the warp's lanes are candidate pixel rows y_min + lane (32 at a time): a
+// lane whose row reaches a bin writes that row's {offset, 7 weights} at the position a ballot gives it.
 __global__ void __launch_bounds__(128) roi_align_stream_entries_kernel(RoiArgs a, unsigned char* __restrict__ rec) {
     constexpr int P = AS_P;
-    const int r = blockIdx.x * 128 + threadIdx.x;
+    __shared__ int s_py[4][P][4];
+    __shared__ float s_pw[4][P][4];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 4 + wid;
     if (r >= a.K) return;
     const float* rp = a.rois5 + (size_t)roi_at(a, r) * 5;
     unsigned char* base = rec + (size_t)r * AS_REC;
-    int py[P][4];
-    float pwt[P][4];
-    int y_min = 0x7FFFFFFF, y_max = -1;
-#pragma unroll
-    for (int ax = 0; ax < 2; ++ax) {
-        const bool is_row = ax == 0;
+    const bool is_row = lane < P, is_col = lane >= 8 && lane < 8 + P;
+    int y_lo = 0x7FFFFFFF, y_hi = -1;
+    if (is_row || is_col) {
+        const int p = is_row ? lane : lane - 8;
         const int limit = is_row ? a.H : a.W;
         const float c1 = __ldg(rp + (is_row ? 2 : 1)), c2 = __ldg(rp + (is_row ? 4 : 3));
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const AlignEntry s0 = align_entry(p, 0, P, 2, c1, c2, a.scale, a.aligned, limit, 1);
-            const AlignEntry s1 = align_entry(p, 1, P, 2, c1, c2, a.scale, a.aligned, limit, 1);
-            const bool v0 = s0.lohi >= 0, v1 = s1.lohi >= 0;
-            int x0 = s0.lohi & 0xFFFF, x1 = s1.lohi & 0xFFFF;
-            float h0 = v0 ? 1.f - s0.l : 0.f, l0 = v0 ? s0.l : 0.f;
-            float h1 = v1 ? 1.f - s1.l : 0.f, l1 = v1 ? s1.l : 0.f;
-            bool second = v1;
-            if (!v0) {
-                x0 = x1;
-                h0 = h1;
-                l0 = l1;
-                second = false;
-            }
-            float w0 = h0, w1 = l0, w2 = 0.f, w3 = 0.f;
-            int xb = 0;
-            if (second) {
-                if (x1 == x0) {
-                    w0 = w0 + h1;
-                    w1 = w1 + l1;
-                } else if (x1 == x0 + 1) {
-                    w1 = w1 + h1;
-                    w2 = l1;
-                    xb = min(x1 + 1, limit - 1);
-                } else {
-                    w2 = h1;
-                    w3 = l1;
-                    xb = x1;
-                }
-            }
-            if (!(v0 || v1)) x0 = 0;
-            if (is_row) {  // kept for the transposition below: pixel rows x0, x0+1, xb, xb+1 with weights / 4
-                py[p][0] = x0;
-                py[p][1] = x0 + 1;
-                py[p][2] = xb;
-                py[p][3] = xb + 1;
-                pwt[p][0] = w0 * 0.25f;
-                pwt[p][1] = w1 * 0.25f;
-                pwt[p][2] = w2 * 0.25f;
-                pwt[p][3] = w3 * 0.25f;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (pwt[p][q] != 0.f) {
-                        y_min = min(y_min, py[p][q]);
-                        y_max = max(y_max, py[p][q]);
-                    }
+        const AlignEntry s0 = align_entry(p, 0, P, 2, c1, c2, a.scale, a.aligned, limit, 1);
+        const AlignEntry s1 = align_entry(p, 1, P, 2, c1, c2, a.scale, a.aligned, limit, 1);
+        const bool v0 = s0.lohi >= 0, v1 = s1.lohi >= 0;
+        int x0 = s0.lohi & 0xFFFF, x1 = s1.lohi & 0xFFFF;
+        float h0 = v0 ? 1.f - s0.l : 0.f, l0 = v0 ? s0.l : 0.f;
+        float h1 = v1 ? 1.f - s1.l : 0.f, l1 = v1 ? s1.l : 0.f;
+        bool second = v1;
+        if (!v0) {
+            x0 = x1;
+            h0 = h1;
+            l0 = l1;
+            second = false;
+        }
+        float w0 = h0, w1 = l0, w2 = 0.f, w3 = 0.f;
+        int xb = 0;
+        if (second) {
+            if (x1 == x0) {
+                w0 = w0 + h1;
+                w1 = w1 + l1;
+            } else if (x1 == x0 + 1) {
+                w1 = w1 + h1;
+                w2 = l1;
+                xb = min(x1 + 1, limit - 1);
             } else {
-                reinterpret_cast<float4*>(base)[p] = make_float4(w0, w1, w2, w3);
-                reinterpret_cast<uint2*>(base + P * 16)[p] = make_uint2((uint32_t)x0 * 16u, (uint32_t)xb * 16u);
+                w2 = h1;
+                w3 = l1;
+                xb = x1;
             }
         }
+        if (!(v0 || v1)) x0 = 0;
+        if (is_row) {  // pixel rows x0, x0+1, xb, xb+1 with weights / 4
+            const int py[4] = {x0, x0 + 1, xb, xb + 1};
+            const float pw[4] = {w0 * 0.25f, w1 * 0.25f, w2 * 0.25f, w3 * 0.25f};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                s_py[wid][p][q] = py[q];
+                s_pw[wid][p][q] = pw[q];
+                if (pw[q] != 0.f) {
+                    y_lo = min(y_lo, py[q]);
+                    y_hi = max(y_hi, py[q]);
+                }
+            }
+        } else {
+            reinterpret_cast<float4*>(base)[p] = make_float4(w0, w1, w2, w3);
+            reinterpret_cast<uint2*>(base + P * 16)[p] = make_uint2((uint32_t)x0 * 16u, (uint32_t)xb * 16u);
+        }
     }
+    const int y_min = __reduce_min_sync(0xFFFFFFFFu, y_lo), y_max = __reduce_max_sync(0xFFFFFFFFu, y_hi);
+    __syncwarp();
     // row program: the pixel rows that reach at least one bin, top to bottom, each with its weight per bin row
     int n = 0;
-    for (int y = y_min; y <= y_max && n < AS_MAX_ROWS; ++y) {
+    for (int y0 = y_min; y0 <= y_max && n < AS_MAX_ROWS; y0 += 32) {
+        const int y = y0 + lane;
         float w[P];
         bool any = false;
 #pragma unroll
@@ -1818,18 +1820,22 @@ __global__ void __launch_bounds__(128) roi_align_stream_entries_kernel(RoiArgs a
             float t = 0.f;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (py[p][q] == y) t = t + pwt[p][q];  // a row appears at most twice in a bin (inverted RoIs)
+                if (s_py[wid][p][q] == y) t = t + s_pw[wid][p][q];  // a row appears at most twice in a bin (inverted RoIs)
             w[p] = t;
             any = any || t != 0.f;
         }
-        if (!any) continue;
-        uint4* dst = reinterpret_cast<uint4*>(base + AS_ROWS_OFF + n * 32);
-        dst[0] = make_uint4((uint32_t)y * (uint32_t)a.pitch * 16u, __float_as_uint(w[0]), __float_as_uint(w[1]),
-                            __float_as_uint(w[2]));
-        dst[1] = make_uint4(__float_as_uint(w[3]), __float_as_uint(w[4]), __float_as_uint(w[5]), __float_as_uint(w[6]));
-        ++n;
+        any = any && y <= y_max;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, any);
+        const int idx = n + __popc(bal & ((1u << lane) - 1u));
+        if (any && idx < AS_MAX_ROWS) {
+            uint4* dst = reinterpret_cast<uint4*>(base + AS_ROWS_OFF + idx * 32);
+            dst[0] = make_uint4((uint32_t)y * (uint32_t)a.pitch * 16u, __float_as_uint(w[0]), __float_as_uint(w[1]),
+                                __float_as_uint(w[2]));
+            dst[1] = make_uint4(__float_as_uint(w[3]), __float_as_uint(w[4]), __float_as_uint(w[5]), __float_as_uint(w[6]));
+        }
+        n = min(n + __popc(bal), AS_MAX_ROWS);
     }
-    *reinterpret_cast<int*>(base + P * 24) = n;
+    if (lane == 0) *reinterpret_cast<int*>(base + P * 24) = n;
 }
 
 // RoI rows of every image ordered by the length of their row program, longest first (counting sort, one CTA per
@@ -2559,7 +2565,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
                 return FRCNN_ERR_WORKSPACE;
             }
             FRCNN_CHECK_ARG(slabs <= 65535 && B <= 65535, "roi op: too many channel slabs / images");
-            roi_align_stream_entries_kernel<<<cdiv(K, 128), 128, 0, stream>>>(a, (unsigned char*)w.ent);
+            roi_align_stream_entries_kernel<<<cdiv(K, 4), 128, 0, stream>>>(a, (unsigned char*)w.ent);
             FRCNN_LAUNCH_CHECK();
             roi_align_stream_sort_kernel<<<B, 256, 0, stream>>>(a, (const unsigned char*)w.ent, w.sorted);
             FRCNN_LAUNCH_CHECK();
