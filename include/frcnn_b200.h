@@ -241,7 +241,8 @@ int frcnn_roi_align_mean_forward(const float* feat, int32_t batch, int32_t chann
                                  size_t workspace_bytes, frcnn_stream_t stream);
 /* Backward of torchvision RoIPool w.r.t. the features (the gradient the head's loss sends into the
  * extractor through nets/classify.py:43).  grad_in [B,C,H,W] must be zero-initialised by the caller; RoIs
- * whose batch index is outside [0,batch) contribute nothing.                                       */
+ * whose batch index is outside [0,batch) contribute nothing.  Maps whose 4-channel slab fits in shared
+ * memory: one CTA per (image, slab) accumulates there and adds to grad_in once (no global atomics).  */
 int frcnn_roi_pool_backward(const float* grad_out, const int32_t* argmax, const float* rois5,
                             int32_t num_rois, int32_t batch, int32_t channels, int32_t height, int32_t width,
                             int32_t pooled_h, int32_t pooled_w, float* grad_in, frcnn_stream_t stream);

@@ -741,6 +741,33 @@ def test_roi_align_backward_golden_and_oracle(F, O):
         assert err <= 1e-5, (sr, al, err)
 
 
+def test_roi_backward_large_map_and_14x14(F, O):
+    """The slab backward kernels keep an image's 4-channel gradient slab in shared memory; maps too large for that
+    (here 104 x 104) and RoIAlign grids above 8 x 8 take the one-atomic-per-element kernels.  Both against the oracle,
+    with a channel count that is not a multiple of four."""
+    rng = np.random.default_rng(47)
+    for (H, W, P) in ((104, 104, 7), (38, 38, 14), (30, 44, 7)):
+        B, Cc, K = 2, 6, 60
+        featn = rng.standard_normal((B, Cc, H, W)).astype(np.float32)
+        c = rng.uniform(-2, W + 2, (K, 2))
+        wh = rng.uniform(1, W * 0.7, (K, 2))
+        rois = np.concatenate([rng.integers(0, B, (K, 1)), c - wh / 2, c + wh / 2], 1).astype(np.float32)
+        rois[5, 0] = 7.0  # a RoI of no image
+        feat = T(featn).requires_grad_(True)
+        out = F.roi_pool(feat, T(rois), P, 1.0)
+        go = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+        (gi,) = torch.autograd.grad(out, feat, T(go))
+        _, am = O.roi_pool(featn, rois, P, 1.0, return_argmax=True)
+        want = O.roi_pool_backward(go, am, rois, featn.shape)
+        assert np.allclose(N(gi), want, rtol=0, atol=1e-5 * float(np.abs(want).max())), (H, W, P, "pool")
+        feat = T(featn).requires_grad_(True)
+        out = F.roi_align(feat, T(rois), P, 1.0, 2, False)
+        (gi,) = torch.autograd.grad(out, feat, T(go))
+        want = O.roi_align_backward(go, rois, featn.shape, 1.0, 2, False)
+        err = float(np.abs(N(gi) - want).max()) / float(np.abs(want).max())
+        assert err <= 1e-5, (H, W, P, "align", err)
+
+
 def test_cpu_tensors_fail_loudly(F):
     with pytest.raises(RuntimeError):
         F.bbox_iou(torch.zeros(2, 4), torch.zeros(2, 4))

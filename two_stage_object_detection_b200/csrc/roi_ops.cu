@@ -2336,6 +2336,120 @@ __global__ void roi_align_backward_kernel(const float* __restrict__ go, RoiArgs 
 }
 
 // ---------------------------------------------------------------------------------------------
+// RoIPool / RoIAlign backward, SLAB form (maps whose 4-channel gradient slab fits in shared memory).
+//
+// roi_pool_backward_kernel / roi_align_backward_kernel are torchvision's design: one thread per output element, one
+// (RoIPool) or 4 * samples (RoIAlign) global atomicAdd each -- 963 M L2 atomics for a cfg2-sized RoIPool gradient.
+// The forward kernels' decomposition works backwards too: a CTA owns the gradient of ONE image's 4-channel slab
+// [4][H*W], keeps it in shared memory, walks the RoIs of its image (compacted from the batch-index column in chunks --
+// no workspace, no bucketing pass), reads grad_out / argmax in 784-byte-contiguous runs and accumulates with
+// shared-memory atomics; the slab is added to grad_in once at the end by the only CTA that ever touches those planes:
+// no global atomic, 16 bytes of grad_in traffic per pixel instead of one L2 round trip per output element.
+// (Summation order inside a pixel is still unordered, as with any atomic accumulation.)
+// ---------------------------------------------------------------------------------------------
+constexpr int BW_THREADS = 512;
+constexpr int BW_LIST = 1024;  // RoIs compacted per pass
+
+// appends to s_list the RoI rows k in [k0, k0 + BW_LIST) whose batch index is b; returns their number
+__device__ __forceinline__ int bw_collect(const float* __restrict__ rois5, int K, int k0, int b, int* s_list, int* s_n) {
+    if (threadIdx.x == 0) *s_n = 0;
+    __syncthreads();
+    for (int k = k0 + threadIdx.x; k < min(k0 + BW_LIST, K); k += BW_THREADS)
+        if ((int)__ldg(rois5 + (size_t)k * 5) == b) s_list[atomicAdd(s_n, 1)] = k;
+    __syncthreads();
+    return *s_n;
+}
+
+__global__ void __launch_bounds__(BW_THREADS) roi_pool_backward_slab_kernel(const float* __restrict__ go,
+                                                                            const int* __restrict__ argmax,
+                                                                            const float* __restrict__ rois5, int K, int C,
+                                                                            int HW, int PP, float* __restrict__ gi) {
+    extern __shared__ __align__(16) float s_acc[];  // [4][HW]
+    __shared__ int s_list[BW_LIST];
+    __shared__ int s_n;
+    const int b = blockIdx.y, c0 = blockIdx.x * 4, cs = min(4, C - c0);
+    for (int i = threadIdx.x; i < 4 * HW; i += BW_THREADS) s_acc[i] = 0.f;
+    const int per = cs * PP;  // contiguous elements of one RoI that belong to this slab
+    for (int k0 = 0; k0 < K; k0 += BW_LIST) {
+        const int n = bw_collect(rois5, K, k0, b, s_list, &s_n);
+        for (int idx = threadIdx.x; idx < n * per; idx += BW_THREADS) {
+            const int j = idx / per, e = idx - j * per;
+            const size_t o = ((size_t)s_list[j] * C + c0) * PP + e;
+            const int am = __ldg(argmax + o);
+            if (am >= 0 && am < HW) atomicAdd(&s_acc[(e / PP) * HW + am], __ldg(go + o));
+        }
+        __syncthreads();  // s_list is rewritten by the next pass
+    }
+    float* dst = gi + ((size_t)b * C + c0) * HW;
+    for (int i = threadIdx.x; i < cs * HW; i += BW_THREADS) dst[i] += s_acc[i];
+}
+
+__global__ void __launch_bounds__(BW_THREADS) roi_align_backward_slab_kernel(const float* __restrict__ go, RoiArgs a,
+                                                                             float* __restrict__ gi) {
+    extern __shared__ __align__(16) float s_acc[];  // [4][HW]
+    __shared__ int s_list[BW_LIST];
+    __shared__ int s_n;
+    const int H = a.H, W = a.W, HW = H * W, PP = a.PH * a.PW;
+    const int b = blockIdx.y, c0 = blockIdx.x * 4, cs = min(4, a.C - c0);
+    for (int i = threadIdx.x; i < 4 * HW; i += BW_THREADS) s_acc[i] = 0.f;
+    for (int k0 = 0; k0 < a.K; k0 += BW_LIST) {
+        const int n = bw_collect(a.rois5, a.K, k0, b, s_list, &s_n);
+        // a thread owns one bin of one RoI for the slab's channels: the sample geometry is computed once for all of them
+        for (int idx = threadIdx.x; idx < n * PP; idx += BW_THREADS) {
+            const int j = idx / PP, e = idx - j * PP;
+            const int ph = e / a.PW, pw = e - ph * a.PW;
+            const int k = s_list[j];
+            const AlignRoi q = make_align_roi(a.rois5 + (size_t)k * 5, k, a.scale, a.PH, a.PW, a.sampling_ratio, a.aligned);
+            const float* gp = go + ((size_t)k * a.C + c0) * PP + e;
+            float g[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) g[c] = c < cs ? __ldg(gp + (size_t)c * PP) / q.count : 0.f;
+            for (int iy = 0; iy < q.gh; ++iy) {
+                float yy = q.sy + (float)ph * q.bin_h;
+                yy = yy + ((float)iy + .5f) * q.bin_h / (float)q.gh;
+                for (int ix = 0; ix < q.gw; ++ix) {
+                    float xx = q.sx + (float)pw * q.bin_w;
+                    xx = xx + ((float)ix + .5f) * q.bin_w / (float)q.gw;
+                    float y = yy, x = xx;
+                    if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) continue;
+                    if (y <= 0.f) y = 0.f;
+                    if (x <= 0.f) x = 0.f;
+                    int yl = (int)y, xl = (int)x, yh, xh;
+                    if (yl >= H - 1) {
+                        yh = yl = H - 1;
+                        y = (float)yl;
+                    } else {
+                        yh = yl + 1;
+                    }
+                    if (xl >= W - 1) {
+                        xh = xl = W - 1;
+                        x = (float)xl;
+                    } else {
+                        xh = xl + 1;
+                    }
+                    const float ly = y - (float)yl, lx = x - (float)xl;
+                    const float hy = 1.f - ly, hx = 1.f - lx;
+                    const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c < cs) {
+                            float* plane = s_acc + c * HW;
+                            atomicAdd(plane + yl * W + xl, g[c] * w1);
+                            atomicAdd(plane + yl * W + xh, g[c] * w2);
+                            atomicAdd(plane + yh * W + xl, g[c] * w3);
+                            atomicAdd(plane + yh * W + xh, g[c] * w4);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    float* dst = gi + ((size_t)b * a.C + c0) * HW;
+    for (int i = threadIdx.x; i < cs * HW; i += BW_THREADS) dst[i] += s_acc[i];
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 struct RoiWs {
@@ -2895,6 +3009,15 @@ int frcnn_roi_pool_backward(const float* grad_out, const int32_t* argmax, const 
     if (K == 0) return FRCNN_OK;
     FRCNN_CHECK_ARG(grad_out && argmax && rois5 && grad_in, "frcnn_roi_pool_backward: null pointer");
     size_t total = (size_t)K * C * PH * PW;
+    static const int bw_direct = env_int("FRCNN_BACKWARD_DIRECT", 0);  // experiments only: 1 = one global atomic per element
+    const size_t slab = (size_t)4 * H * W * sizeof(float);
+    if (slab <= 160 * 1024 && B <= 65535 && cdiv(C, 4) <= 65535 && !bw_direct) {
+        FRCNN_SMEM(roi_pool_backward_slab_kernel, slab);
+        roi_pool_backward_slab_kernel<<<dim3(cdiv(C, 4), B), BW_THREADS, slab, (cudaStream_t)stream>>>(
+            grad_out, argmax, rois5, K, C, H * W, PH * PW, grad_in);
+        FRCNN_LAUNCH_CHECK();
+        return FRCNN_OK;
+    }
     roi_pool_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         grad_out, argmax, rois5, total, B, C, H * W, PH * PW, grad_in);
     FRCNN_LAUNCH_CHECK();
@@ -2922,6 +3045,16 @@ int frcnn_roi_align_backward(const float* grad_out, const float* rois5, int32_t 
     a.sampling_ratio = sampling_ratio;
     a.aligned = aligned;
     size_t total = (size_t)K * C * PH * PW;
+    static const int bw_direct = env_int("FRCNN_BACKWARD_DIRECT", 0);  // experiments only
+    const size_t slab = (size_t)4 * H * W * sizeof(float);
+    // (grids above 8 x 8: 16 shared-memory CAS loops per bin and channel lose against the L2 atomics -- 26.6 vs 23.5 ms
+    //  for a cfg2-sized 14 x 14 gradient; 7 x 7: 4.8 vs 6.4 ms)
+    if (slab <= 160 * 1024 && PH * PW <= 64 && B <= 65535 && cdiv(C, 4) <= 65535 && !bw_direct) {
+        FRCNN_SMEM(roi_align_backward_slab_kernel, slab);
+        roi_align_backward_slab_kernel<<<dim3(cdiv(C, 4), B), BW_THREADS, slab, (cudaStream_t)stream>>>(grad_out, a, grad_in);
+        FRCNN_LAUNCH_CHECK();
+        return FRCNN_OK;
+    }
     roi_align_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grad_out, a,
                                                                                                   grad_in);
     FRCNN_LAUNCH_CHECK();
