@@ -2856,8 +2856,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             a.pitch = pitch_for(tcs ? tcs : 4);
             // maps whose four 4-channel tables do not fit: two tables (pixels, 2 x 2 windows) with four
             // channels per lookup instead of four tables with two
-            static const int pool_pitch = env_int("FRCNN_POOL_PITCH", 0);  // experiments only
-            const int pitch_d = pool_pitch >= W ? pool_pitch : pitch_for(4);
+            const int pitch_d = pitch_for(4);  // (a sweep over 65 ... 71 pixels on the 64-wide map moved the time by < 0.5 %)
             const size_t smemd = (size_t)2 * (size_t)((H * pitch_d + 3) & ~3) * 16;
             if (tcs == 2 && smemd + 40 * 1024 <= 220 * 1024) {
                 a.pitch = pitch_d;
