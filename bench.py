@@ -665,21 +665,22 @@ def cpu_step(cfg, O, loc, logits, feat, images):
     return O.roi_head_gather(feat[:B], rois, np.arange(B), (S, S), roi_size=P, spatial_scale=1.0, op=op, **kw)
 
 
-def cpu_baseline(cfg, images=2, reps=3):
+def cpu_baseline(cfg, images=2, budget_s=12.0, max_reps=40):
     from oracle import ref_port as O
     O.set_threads(len(os.sched_getaffinity(0)))
     loc, logits, feat = (t.numpy() for t in make_inputs(cfg, 7))
     images = min(images, cfg["batch"])
     cpu_step(cfg, O, loc, logits, feat, 2)  # warm-up (builds / loads the C library)
-    times = []
-    for _ in range(reps):
+    times, start = [], time.perf_counter()
+    while len(times) < 3 or (time.perf_counter() - start < budget_s and len(times) < max_reps):  # ~10 s of CPU work
         t0 = time.perf_counter()
         cpu_step(cfg, O, loc, logits, feat, images)
         times.append(time.perf_counter() - t0)
     dt = float(np.median(times))
     return {"value": images / dt, "unit": "images/s", "cores": O.max_threads(), "kind": "port",
-            "sample": f"{images} of {cfg['batch']} images of the same workload (oracle/ref_port.py + frcnn_oracle.c, "
-                      f"OpenMP over images and RoIs), median of {reps} passes, {dt:.2f} s each"}
+            "sample": f"{images} of {cfg['batch']} images of the same workload per pass (oracle/ref_port.py + "
+                      f"frcnn_oracle.c, OpenMP over images and RoIs), median of {len(times)} passes, {dt:.2f} s each, "
+                      f"{sum(times):.1f} s of CPU work"}
 
 
 def torchvision_baseline(cfg, images=2, budget_s=20.0):
