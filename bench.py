@@ -536,6 +536,10 @@ def run_ours(args):
             del w2
             torch.cuda.empty_cache()
         out["workloads"] = extra
+        try:
+            out["ddp_train_step"] = ddp_train_leg(dev, rank, world, local)
+        except Exception as exc:  # informational leg: never takes the line down
+            out["ddp_train_step"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(cfg, images=cfg["batch"])
@@ -546,6 +550,65 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ddp_train_leg(dev, rank, world, local, steps=6):
+    """BASELINE config 3 as a whole training step: FasterRCNNTrainer (batched trainer glue: proposals, anchor / proposal
+    targets, RoIPool forward AND backward in the sm_100a kernels) on 8 synthetic 600x600 images per GPU, stock DDP
+    gradient all-reduce over NCCL when N > 1, AdamW step.  The backbone is a two-conv stand-in (backbones are out of
+    scope), so the figure is about the path + the collective, not about a ResNet.  Checks: finite loss, replicas
+    bit-identical after the steps."""
+    import torch.distributed as dist
+    from torch import nn
+    from two_stage_object_detection_b200.nets import FasterRCNNTrainer
+
+    class TinyExtractor(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.net = nn.Sequential(nn.Conv2d(3, 32, 3, 4, 1), nn.ReLU(), nn.Conv2d(32, 512, 3, 4, 1), nn.ReLU())
+
+        def forward(self, x):
+            return self.net(x)
+
+    torch.manual_seed(0)
+    model = FasterRCNNTrainer("train", num_classes=20, extractor=TinyExtractor()).to(dev)
+    ddp = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4, weight_decay=1e-4)
+    g = torch.Generator().manual_seed(300 + rank)
+    B, S, G = 8, 600, 8
+    imgs = [torch.rand(3, S, S, generator=g).to(dev) for _ in range(B)]
+    boxes, labels = [], []
+    for _ in range(B):
+        c = torch.rand(G, 2, generator=g) * S
+        wh = 50 + torch.rand(G, 2, generator=g) * 200
+        boxes.append(torch.cat([c - wh / 2, c + wh / 2], 1).clamp(0, S).to(dev))
+        labels.append(torch.randint(0, 20, (G,), generator=g).to(dev))
+    finite = True
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for step in range(steps + 2):
+        if step == 2:
+            barrier(world)
+            t0.record()
+        losses, *_ = ddp(imgs, boxes, labels)
+        opt.zero_grad(set_to_none=True)
+        losses[-1].backward()
+        opt.step()
+        finite = finite and bool(torch.isfinite(losses[-1].detach()))
+    t1.record()
+    barrier(world)
+    ms, = max_over_ranks([t0.elapsed_time(t1) / steps], dev, world)
+    same = True
+    if world > 1:
+        flat = torch.cat([p.detach().flatten() for p in model.parameters()])
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        flag = torch.tensor([1.0 if torch.equal(flat, ref) and finite else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        same = bool(flag.item() == 1.0)
+    return {"ms_per_step": ms, "images_per_s": world * B / (ms * 1e-3), "batch_per_gpu": B, "steps": steps,
+            "loss_finite": finite, "replicas_identical": same,
+            "what": "FasterRCNNTrainer forward + backward + AdamW on 8 synthetic 600x600 images per GPU with 8 GT boxes each "
+                    "(stand-in two-conv extractor), DDP gradient all-reduce when N > 1"}
 
 
 def e2e_leg(args, wl, dev, rank, world, ProposalCreator, HarNetRoIHead, GlobalAvgClassifier):
