@@ -1,6 +1,6 @@
 """Randomised parity sweep: CUDA path vs the oracle on random shapes and box distributions (degenerate boxes,
 RoIs hanging over the map, channel tails, ragged GT counts).  Not part of the test suite (minutes, not seconds);
-run on a GPU box:   python tools/fuzz_parity.py [--iters 200] [--seed 0]
+run on a GPU box:   python tests/fuzz_parity.py [--iters 200] [--seed 0]
 Exits non-zero on the first mismatch and prints the case that produced it."""
 import argparse
 import os
