@@ -1742,16 +1742,18 @@ constexpr int AS_MAX_ROWS = 30;
 constexpr int AS_STAGE = 800;    // bytes between staging blocks (784 used; 800: the four RoIs of a warp on distinct banks)
 
 // One WARP per RoI: lanes 0..6 compute the merged per-axis taps of the seven bin rows, lanes 8..14 those of the
-// seven bin columns (the column lanes write their weights / offsets straight into the record); the row lanes publish
-// theirs through shared memory, and then the warp's lanes are candidate pixel rows y_min + lane (32 at a time): a
+// seven bin columns (their taps are dealt into the record's four tap slots by warp 0, see "Tap slots" below); the row
+// lanes publish theirs through shared memory, and then the warp's lanes are candidate pixel rows y_min + lane (32 at a time): a
 // lane whose row reaches a bin writes that row's {offset, 7 weights} at the position a ballot gives it.
 __global__ void __launch_bounds__(128) roi_align_stream_entries_kernel(RoiArgs a, unsigned char* __restrict__ rec) {
     constexpr int P = AS_P;
     __shared__ int s_py[4][P][4];
     __shared__ float s_pw[4][P][4];
+    __shared__ __align__(16) int s_cx[4][P][4];
+    __shared__ __align__(16) float s_cw[4][P][4];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * 4 + wid;
-    if (r >= a.K) return;
+    const bool live = blockIdx.x * 4 + wid < a.K;  // a warp past the end recomputes the last RoI and writes nothing
+    const int r = live ? blockIdx.x * 4 + wid : a.K - 1;
     const float* rp = a.rois5 + (size_t)roi_at(a, r) * 5;
     unsigned char* base = rec + (size_t)r * AS_REC;
     const bool is_row = lane < P, is_col = lane >= 8 && lane < 8 + P;
@@ -1803,8 +1805,62 @@ __global__ void __launch_bounds__(128) roi_align_stream_entries_kernel(RoiArgs a
                 }
             }
         } else {
-            reinterpret_cast<float4*>(base)[p] = make_float4(w0, w1, w2, w3);
-            reinterpret_cast<uint2*>(base + P * 16)[p] = make_uint2((uint32_t)x0 * 16u, (uint32_t)xb * 16u);
+            s_cx[wid][p][0] = x0;
+            s_cx[wid][p][1] = x0 + 1;
+            s_cx[wid][p][2] = xb;
+            s_cx[wid][p][3] = xb + 1;
+            s_cw[wid][p][0] = w0;
+            s_cw[wid][p][1] = w1;
+            s_cw[wid][p][2] = w2;
+            s_cw[wid][p][3] = w3;
+        }
+    }
+    // Tap slots.  The streaming kernel reads a bin column's pixels with four LDS.128 "slots"; the seven column lanes
+    // of a RoI share a quarter-warp, i.e. ONE shared-memory wavefront per slot as long as their pixels sit in distinct
+    // 16-byte bank groups (pixel column mod 8).  With the taps in their natural order (x0, x0+1, xb, xb+1) two lanes
+    // collide whenever their pixel columns differ by 8: 4.4 wavefronts per pixel row where 3.1 would do (ncu,
+    // profiles/r2_cfg4_roialign_stream2.md).  Which tap travels in which slot is free (a weighted sum), so the taps of
+    // columns 0..6 are dealt into slots greedily.  Warp 0 does it for the four RoIs of the CTA at once: a quarter-warp
+    // per RoI whose lanes 0..3 ARE the slots (occupant per bank group in a register, one nibble each); every tap is
+    // offered to all four and goes to the cheapest (minimum of cost * 4 + slot over the four slot lanes): 0 = a slot
+    // that is already open where it meets no other pixel of its bank group (the same pixel is a broadcast, not a
+    // conflict), 2 = a slot nobody uses yet (one more wavefront), 3 = a bank-group collision.  The occupant is
+    // remembered modulo 64 pixel columns: dealing only decides speed, never the result.
+    __syncthreads();
+    if (wid == 0) {
+        const int g = lane >> 3, sl = lane & 7;
+        const bool g_live = blockIdx.x * 4 + g < a.K;
+        unsigned char* gb = rec + (size_t)(blockIdx.x * 4 + g) * AS_REC;
+        unsigned occ = 0u;
+        bool open = false;
+#pragma unroll 1
+        for (int p = 0; p < P; ++p) {
+            const float4 w4 = *reinterpret_cast<const float4*>(s_cw[g][p]);
+            const int4 x4 = *reinterpret_cast<const int4*>(s_cx[g][p]);
+            const float wq[4] = {w4.x, w4.y, w4.z, w4.w};
+            const int xq[4] = {x4.x, x4.y, x4.z, x4.w};
+            float ow = 0.f;
+            unsigned ox = 0u;
+            bool used = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned x = (unsigned)xq[q], sh = (x & 7u) * 4u, id = 8u | ((x >> 3) & 7u);
+                const unsigned o = (occ >> sh) & 15u;
+                const unsigned cost = used ? 8u : (o != 0u && o != id) ? 3u : open ? 0u : 2u;
+                const unsigned key = (sl < 4 && wq[q] != 0.f) ? cost * 4u + (unsigned)sl : 0xFFu;
+                unsigned best = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, 1));  // (REDUX with a quarter-warp mask
+                best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, 2));         // serialises the four quarters)
+                if (key == best && key != 0xFFu) {
+                    used = open = true;
+                    ow = wq[q];
+                    ox = x;
+                    if (o == 0u) occ |= id << sh;
+                }
+            }
+            if (sl < 4 && g_live) {
+                reinterpret_cast<float*>(gb)[p * 4 + sl] = ow;
+                reinterpret_cast<unsigned short*>(gb + P * 16)[p * 4 + sl] = (unsigned short)(ox * 16u);
+            }
         }
     }
     const int y_min = __reduce_min_sync(0xFFFFFFFFu, y_lo), y_max = __reduce_max_sync(0xFFFFFFFFu, y_hi);
@@ -1827,7 +1883,7 @@ __global__ void __launch_bounds__(128) roi_align_stream_entries_kernel(RoiArgs a
         any = any && y <= y_max;
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, any);
         const int idx = n + __popc(bal & ((1u << lane) - 1u));
-        if (any && idx < AS_MAX_ROWS) {
+        if (any && idx < AS_MAX_ROWS && live) {
             uint4* dst = reinterpret_cast<uint4*>(base + AS_ROWS_OFF + idx * 32);
             dst[0] = make_uint4((uint32_t)y * (uint32_t)a.pitch * 16u, __float_as_uint(w[0]), __float_as_uint(w[1]),
                                 __float_as_uint(w[2]));
@@ -1835,7 +1891,7 @@ __global__ void __launch_bounds__(128) roi_align_stream_entries_kernel(RoiArgs a
         }
         n = min(n + __popc(bal), AS_MAX_ROWS);
     }
-    if (lane == 0) *reinterpret_cast<int*>(base + P * 24) = n;
+    if (lane == 0 && live) *reinterpret_cast<int*>(base + P * 24) = n;
 }
 
 // RoI rows of every image ordered by the length of their row program, longest first (counting sort, one CTA per
@@ -1950,13 +2006,14 @@ __global__ void __launch_bounds__(THREADS, MINB) roi_align_stream2_kernel(RoiArg
     unsigned char* stg_b = smem_raw + tab_bytes + (size_t)(tid >> 3) * AS_STAGE;
     float* stg = reinterpret_cast<float*>(stg_b);
     const uint32_t ring = smem_u32(smem_raw + tab_bytes + (size_t)NQ * AS_STAGE + (size_t)w * (RING * AS2_CHUNK));
-    const unsigned char* slot = prog + ((size_t)(as2_pass_base(r_begin, b, NQ) + pi0) * NW + w) * AS2_SLOT + lane * 16;
-    const size_t slot_stride = (size_t)a.groups * NW * AS2_SLOT;
+    // position in the program buffer in 16-byte units (32 bits: two registers less than a pointer and a stride)
+    uint32_t slot = (uint32_t)(((size_t)(as2_pass_base(r_begin, b, NQ) + pi0) * NW + w) * (AS2_SLOT / 16)) + lane;
+    const uint32_t slot_stride = (uint32_t)a.groups * NW * (AS2_SLOT / 16);
 
     // chunk `pos` of the warp's stream lives in ring slot pos % RING
-    auto fetch = [&](const unsigned char* src, int pos) {
+    auto fetch = [&](uint32_t src16, int pos) {
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (uint32_t)(pos % RING) * AS2_CHUNK + lane * 16),
-                     "l"(src)
+                     "l"(prog + (size_t)src16 * 16)
                      : "memory");
     };
     auto commit = [&]() { asm volatile("cp.async.commit_group;" ::: "memory"); };
@@ -1966,7 +2023,7 @@ __global__ void __launch_bounds__(THREADS, MINB) roi_align_stream2_kernel(RoiArg
     };
 #pragma unroll
     for (int j = 0; j < D; ++j) {  // header (+ first row chunk): on their way while the table is built
-        fetch(slot + j * AS2_CHUNK, j);
+        fetch(slot + j * (AS2_CHUNK / 16), j);
         commit();
     }
     {
@@ -1986,14 +2043,14 @@ __global__ void __launch_bounds__(THREADS, MINB) roi_align_stream2_kernel(RoiArg
     // after consuming chunk j of a pass with kk row chunks: start the copy of the chunk D positions further on
     auto prefetch = [&](int j, int kk, bool last_pass) {
         int jj = j + D;
-        const unsigned char* base = slot;
+        uint32_t base = slot;
         bool ok = true;
         if (jj >= AS2_HDR + kk) {
             jj -= AS2_HDR + kk;
             base += slot_stride;
             ok = !last_pass;
         }
-        if (ok) fetch(base + jj * AS2_CHUNK, pos + D);
+        if (ok) fetch(base + jj * (AS2_CHUNK / 16), pos + D);
         commit();
     };
     for (int ip = 0; ip < n_pass; ++ip, slot += slot_stride) {
@@ -2014,8 +2071,11 @@ __global__ void __launch_bounds__(THREADS, MINB) roi_align_stream2_kernel(RoiArg
         prefetch(1, kk, last_pass);
         ++pos;
         const bool cl0 = cw.x != 0.f, c1 = cw.y != 0.f, c2 = cw.z != 0.f, c3 = cw.w != 0.f;
-        const unsigned char* ca = smem_raw + hd.x;
-        const unsigned char* cb = smem_raw + hd.y;
+        // four independent tap slots (byte offsets of their pixel columns; dealt by roi_align_stream_entries_kernel)
+        const unsigned char* ca = smem_raw + (hd.x & 0xFFFFu);
+        const unsigned char* ca1 = smem_raw + (hd.x >> 16);
+        const unsigned char* cb = smem_raw + (hd.y & 0xFFFFu);
+        const unsigned char* cb1 = smem_raw + (hd.y >> 16);
         const uint32_t orow = hd.w;
         float2 acc[P][2];
 #pragma unroll
@@ -2026,7 +2086,9 @@ __global__ void __launch_bounds__(THREADS, MINB) roi_align_stream2_kernel(RoiArg
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
                          : "r"(raddr + 16));
             const unsigned char* pa = ca + lo.x;
+            const unsigned char* pa1 = ca1 + lo.x;
             const unsigned char* pb = cb + lo.x;
+            const unsigned char* pb1 = cb1 + lo.x;
             float2 t01 = make_float2(0.f, 0.f), t23 = make_float2(0.f, 0.f);
             if (cl0) {
                 const float4 v = *reinterpret_cast<const float4*>(pa);
@@ -2034,7 +2096,7 @@ __global__ void __launch_bounds__(THREADS, MINB) roi_align_stream2_kernel(RoiArg
                 fma2(t23, make_float2(v.z, v.w), cw.x);
             }
             if (c1) {
-                const float4 v = *reinterpret_cast<const float4*>(pa + 16);
+                const float4 v = *reinterpret_cast<const float4*>(pa1);
                 fma2(t01, make_float2(v.x, v.y), cw.y);
                 fma2(t23, make_float2(v.z, v.w), cw.y);
             }
@@ -2044,7 +2106,7 @@ __global__ void __launch_bounds__(THREADS, MINB) roi_align_stream2_kernel(RoiArg
                 fma2(t23, make_float2(v.z, v.w), cw.z);
             }
             if (c3) {
-                const float4 v = *reinterpret_cast<const float4*>(pb + 16);
+                const float4 v = *reinterpret_cast<const float4*>(pb1);
                 fma2(t01, make_float2(v.x, v.y), cw.w);
                 fma2(t23, make_float2(v.z, v.w), cw.w);
             }
@@ -2666,7 +2728,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
         const int NQ2 = T2 / 8, RING2 = T2 == 224 ? 3 : 4;
         const size_t tab2 = ((size_t)(H + 1) * a.pitch * 16 + 127) & ~(size_t)127;
         const size_t smem2 = tab2 + (size_t)NQ2 * AS_STAGE + (size_t)(T2 / 32) * RING2 * AS2_CHUNK;
-        if (smem2 <= 110 * 1024) {  // at least two CTAs per SM (three on maps up to 50 x 50)
+        if (smem2 <= 110 * 1024 && W < 4096) {  // at least two CTAs per SM (three on maps up to 50 x 50); 16-bit tap offsets
             a.CS = 4;
             const int slabs = C / 4;
             const int passes = cdiv(cdiv(K, B), NQ2);
@@ -2679,6 +2741,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
                 return FRCNN_ERR_WORKSPACE;
             }
             FRCNN_CHECK_ARG(slabs <= 65535 && B <= 65535, "roi op: too many channel slabs / images");
+            FRCNN_CHECK_ARG(((size_t)K / 24 + B + 2) * 8 * (AS2_SLOT / 16) < 0xFFFFFFFFull, "roi op: too many RoIs");
             roi_align_stream_entries_kernel<<<cdiv(K, 4), 128, 0, stream>>>(a, (unsigned char*)w.ent);
             FRCNN_LAUNCH_CHECK();
             roi_align_stream_sort_kernel<<<B, 256, 0, stream>>>(a, (const unsigned char*)w.ent, w.sorted);
