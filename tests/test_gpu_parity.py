@@ -793,6 +793,39 @@ def test_topk_and_nms_tiny_sizes(F, O, n):
     assert N(n_sel).tolist() == [0, 0] and (N(order) == -1).all() and not N(sb).any()
 
 
+@pytest.mark.parametrize("n,k", [(12996, 3000), (22500, 3000), (5000, 17), (4097, 2048), (36864, 6000), (700, 1)])
+def test_topk_preselection_equals_full_stable_sort(F, n, k):
+    """k <= n/2 takes the pre-selecting form of the cluster sort (12-bit histogram, threshold digit, index-ordered
+    compaction, then the LSD passes on the survivors).  Its first k positions must be those of a stable full sort
+    (key descending, index ascending) for every key distribution: spread, softmax-like, nearly all keys in ONE
+    histogram bin (compaction skipped), heavy exact ties across the threshold, mostly filtered (key 0) rows with fewer
+    valid keys than k, and different images of one batch on both sides of the skip rule."""
+    rng = np.random.default_rng(n + k)
+    B = 5
+    sc = np.empty((B, n), np.float32)
+    sc[0] = rng.uniform(0, 1, n)
+    sc[1] = 1.0 / (1.0 + np.exp(-rng.standard_normal(n) * 2.0))
+    sc[2] = 0.5 + rng.uniform(0, 1e-4, n)                      # one bin of the top 12 bits
+    sc[3] = np.round(rng.uniform(0, 1, n) * 6) / 6             # 7 distinct values: ties straddle the k-th key
+    sc[4] = rng.uniform(0, 1, n)
+    keys = sc.view(np.uint32) | np.uint32(0x80000000)          # order-preserving key of a non-negative float
+    valid4 = rng.permutation(n)[: max(1, min(n, k) // 3)]      # image 4: fewer valid keys than k
+    mask = np.zeros(n, bool)
+    mask[valid4] = True
+    keys[4][~mask] = 0
+    boxes = rng.uniform(0, 100, (B, n, 4)).astype(np.float32)
+    order, n_sel, sb = F.topk_sorted(T(keys.view(np.int32)), T(boxes), k)
+    order, n_sel, sb = N(order), N(n_sel), N(sb)
+    for b in range(B):
+        ref = np.argsort(-(keys[b].astype(np.int64)), kind="stable")
+        nv = int((keys[b] != 0).sum())
+        m = min(k, nv)
+        assert int(n_sel[b]) == m
+        assert np.array_equal(order[b, :m], ref[:m]), f"image {b}"
+        assert (order[b, m:] == -1).all()
+        assert np.array_equal(sb[b, :m], boxes[b][ref[:m]]) and not sb[b, m:].any()
+
+
 def test_proposals_ragged_validity_and_no_valid_boxes(F, O):
     """Images of one batch with very different numbers of boxes surviving the min-size filter,
     including none at all (the reference raises there: status flag)."""
