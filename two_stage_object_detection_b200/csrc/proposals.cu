@@ -363,7 +363,8 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
 }
 
 // CL = CTAs per cluster = per image (4 or 8; the launch sets the cluster dimension, see run_topk).
-template <int CL>
+// E = keys per thread per round (4; 9 where that makes a 4 608-key segment a single round, see run_topk).
+template <int CL, int E = TK_E>
 __global__ void __launch_bounds__(TK_THREADS)
 topk_sort_dsmem_kernel(const uint32_t* __restrict__ keys_all, const float4* __restrict__ boxes_all, int n,
                        int k_cap, int seg, int presel, int* __restrict__ order_all, int* __restrict__ n_sel_all,
@@ -371,8 +372,8 @@ topk_sort_dsmem_kernel(const uint32_t* __restrict__ keys_all, const float4* __re
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) uint32_t dyn[];
-    uint32_t* cnt = dyn;                                                     // [TK_E][TK_WARPS][256]
-    uint2* buf0 = reinterpret_cast<uint2*>(dyn + TK_E * TK_WARPS * 256);     // [2][seg] (key, index)
+    uint32_t* cnt = dyn;                                                     // [E][TK_WARPS][256]
+    uint2* buf0 = reinterpret_cast<uint2*>(dyn + E * TK_WARPS * 256);     // [2][seg] (key, index)
     __shared__ uint32_t hist[256];
     __shared__ uint32_t offs[256];
     __shared__ uint32_t warp_tot[8];
@@ -387,11 +388,11 @@ topk_sort_dsmem_kernel(const uint32_t* __restrict__ keys_all, const float4* __re
     const uint32_t lt = lanemask_lt();
     int lo = min(crank * seg, n), hi = min(lo + seg, n);
     int cnt_local = hi - lo;
-    int rounds = (seg + TK_ROUND - 1) / TK_ROUND;
+    int rounds = (seg + (E * TK_THREADS) - 1) / (E * TK_THREADS);
     int n_eff = n, seg_eff = seg;  // what is being sorted: everything, or the pre-selected keys (below)
     // rows of TK_THREADS keys a round really has (a pre-selected segment is often a single row): the per-row work of
     // counting, scanning and scattering is skipped for the others
-    int e_lim = rounds == 1 ? (seg + TK_THREADS - 1) / TK_THREADS : TK_E;
+    int e_lim = rounds == 1 ? (seg + TK_THREADS - 1) / TK_THREADS : E;
 
     // initial ordering: key = ~sortable key (ascending sort), index = anchor id
     if (tid == 0) s_nzero = 0;
@@ -515,20 +516,20 @@ topk_sort_dsmem_kernel(const uint32_t* __restrict__ keys_all, const float4* __re
             lo = min(crank * seg_eff, M);
             hi = min(lo + seg_eff, M);
             cnt_local = hi - lo;
-            rounds = (seg_eff + TK_ROUND - 1) / TK_ROUND;
+            rounds = (seg_eff + (E * TK_THREADS) - 1) / (E * TK_THREADS);
             if (rounds == 1) e_lim = (seg_eff + TK_THREADS - 1) / TK_THREADS;
         } else {
             cluster.sync();  // the counters h12 aliases are rewritten below: wait for the remote readers
         }
     }
 
-    uint2 kv[TK_E];
-    uint32_t rank[TK_E];
-    bool valid[TK_E];
+    uint2 kv[E];
+    uint32_t rank[E];
+    bool valid[E];
     auto load_round = [&](int r, const uint2* src) {
 #pragma unroll
-        for (int e = 0; e < TK_E; ++e) {
-            const int i = r * TK_ROUND + e * TK_THREADS + tid;
+        for (int e = 0; e < E; ++e) {
+            const int i = r * (E * TK_THREADS) + e * TK_THREADS + tid;
             valid[e] = i < cnt_local;
             kv[e] = valid[e] ? src[i] : make_uint2(0u, 0u);
         }
@@ -537,7 +538,7 @@ topk_sort_dsmem_kernel(const uint32_t* __restrict__ keys_all, const float4* __re
         for (int j = lane; j < e_lim * 256; j += 32) cnt[((j >> 8) * TK_WARPS + warp) * 256 + (j & 255)] = 0;
         __syncwarp();
 #pragma unroll
-        for (int e = 0; e < TK_E; ++e) {
+        for (int e = 0; e < E; ++e) {
             if (e >= e_lim) break;
             const uint32_t d = valid[e] ? ((kv[e].x >> shift) & 255u) : 256u;
             const uint32_t m = match_digit(d);
@@ -548,7 +549,7 @@ topk_sort_dsmem_kernel(const uint32_t* __restrict__ keys_all, const float4* __re
     auto scan_round = [&]() -> uint32_t {  // thread d < 256: counts of digit d -> exclusive prefixes
         uint32_t run = 0;
 #pragma unroll
-        for (int j0 = 0; j0 < TK_E * TK_WARPS; j0 += 16) {
+        for (int j0 = 0; j0 < E * TK_WARPS; j0 += 16) {
             if (j0 >= e_lim * TK_WARPS) break;
             uint32_t c[16];
 #pragma unroll
@@ -563,7 +564,7 @@ topk_sort_dsmem_kernel(const uint32_t* __restrict__ keys_all, const float4* __re
     };
     auto scatter_round = [&](int shift, int dst) {
 #pragma unroll
-        for (int e = 0; e < TK_E; ++e) {
+        for (int e = 0; e < E; ++e) {
             if (e >= e_lim) break;
             if (valid[e]) {
                 const uint32_t d = (kv[e].x >> shift) & 255u;
@@ -591,7 +592,7 @@ topk_sort_dsmem_kernel(const uint32_t* __restrict__ keys_all, const float4* __re
             for (int r = 0; r < rounds; ++r) {
                 load_round(r, src);
 #pragma unroll
-                for (int e = 0; e < TK_E; ++e) {
+                for (int e = 0; e < E; ++e) {
                     const uint32_t d = valid[e] ? ((kv[e].x >> shift) & 255u) : 256u;
                     const uint32_t m = match_digit(d);
                     if (valid[e] && (m & lt) == 0) atomicAdd(&hist[d], (uint32_t)__popc(m));
@@ -1392,10 +1393,17 @@ static int run_topk(const uint32_t* keys, const float* boxes, int batch, int n, 
     if (batch * 8 > sm_count() + sm_count() / 2 && batch * 4 <= sm_count()) cl = 4;
     if (want_presel) cl = 4;
     if (cl_override == 4 || cl_override == 8) cl = cl_override;
+    static const int e9_off = []() { const char* v = getenv("FRCNN_TOPK_NOE9"); return v && *v ? atoi(v) : 0; }();
     for (; k_cap <= n; cl = 8) {
         const int seg = (n + cl - 1) / cl;
-        const size_t dsmem = TK_SMEM + (size_t)2 * seg * sizeof(uint2);
-        if (dsmem > 200 * 1024) {
+        size_t dsmem = TK_SMEM + (size_t)2 * seg * sizeof(uint2);
+        // Nine keys per thread instead of four where that turns a multi-round segment into a single round (the
+        // multi-round passes re-load and re-synchronise per round): 8 x 36 864 keys, 30 000 wanted.  Needs 144 KB of
+        // per-(row, warp) digit counters, so only where the segment still fits beside them.
+        const size_t dsmem9 = (size_t)9 * TK_WARPS * 256 * sizeof(uint32_t) + (size_t)2 * seg * sizeof(uint2);
+        const bool e9 = cl == 8 && !want_presel && !e9_off && seg > TK_ROUND && seg <= 9 * TK_THREADS && dsmem9 <= 224 * 1024;
+        if (e9) dsmem = dsmem9;
+        if (!e9 && dsmem > 200 * 1024) {
             if (cl == 8) break;
             continue;
         }
@@ -1420,6 +1428,9 @@ static int run_topk(const uint32_t* keys, const float* boxes, int batch, int n, 
         if (cl == 4) {
             FRCNN_SMEM(topk_sort_dsmem_kernel<4>, dsmem);
             e = cudaLaunchKernelEx(&cfg, topk_sort_dsmem_kernel<4>, keys, bx, n, k_cap, seg, presel, order, n_sel, sb);
+        } else if (e9) {
+            FRCNN_SMEM((topk_sort_dsmem_kernel<8, 9>), dsmem);
+            e = cudaLaunchKernelEx(&cfg, topk_sort_dsmem_kernel<8, 9>, keys, bx, n, k_cap, seg, presel, order, n_sel, sb);
         } else {
             FRCNN_SMEM(topk_sort_dsmem_kernel<8>, dsmem);
             e = cudaLaunchKernelEx(&cfg, topk_sort_dsmem_kernel<8>, keys, bx, n, k_cap, seg, presel, order, n_sel, sb);
