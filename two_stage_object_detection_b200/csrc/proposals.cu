@@ -756,12 +756,22 @@ __device__ __forceinline__ void nms_mask_tile(const NmsArgs& a, int b, const Nms
         if (col0 + warp * 32 >= c1) return;
         uint32_t* mrow = a.mask + ((size_t)b * (a.S / 32) + cw) * a.S + (row0 - c0);
         uint32_t mine = 0;
+        if (row0 + NMS_RB <= c1) {  // every row of the tile exists (all but the last row block): no per-row test
+#pragma unroll 8
+            for (int r = 0; r < NMS_RB; ++r) {
+                const bool p = nms_suppresses(srow[r], sarea[r], cbx, ca, a.thr) && cvalid;
+                const uint32_t w = __ballot_sync(0xFFFFFFFFu, p);
+                if ((r & 31) == lane) mine = w;
+                if ((r & 31) == 31) mrow[(r - 31) + lane] = mine;
+            }
+        } else {
 #pragma unroll 4
-        for (int r = 0; r < NMS_RB; ++r) {
-            bool p = cvalid && (row0 + r < c1) && nms_suppresses(srow[r], sarea[r], cbx, ca, a.thr);
-            uint32_t w = __ballot_sync(0xFFFFFFFFu, p);
-            if ((r & 31) == lane) mine = w;
-            if ((r & 31) == 31) mrow[(r - 31) + lane] = mine;
+            for (int r = 0; r < NMS_RB; ++r) {
+                bool p = cvalid && (row0 + r < c1) && nms_suppresses(srow[r], sarea[r], cbx, ca, a.thr);
+                uint32_t w = __ballot_sync(0xFFFFFFFFu, p);
+                if ((r & 31) == lane) mine = w;
+                if ((r & 31) == 31) mrow[(r - 31) + lane] = mine;
+            }
         }
     } else {
         // suppression by boxes kept in earlier super-blocks
