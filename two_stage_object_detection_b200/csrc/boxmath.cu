@@ -45,6 +45,15 @@ void note_roi_kernel(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_roi_kernel, sizeof(g_roi_kernel), fmt, ap);
     va_end(ap);
+    // names come from stringified template argument lists: fold the one negated literal they contain
+    for (const char* pat : {"!(true)", "!(false)"}) {
+        const char* to = pat[2] == 't' ? "false" : "true";
+        for (char* q = strstr(g_roi_kernel, pat); q; q = strstr(q, pat)) {
+            const size_t lp = strlen(pat), lt = strlen(to);
+            memmove(q + lt, q + lp, strlen(q + lp) + 1);
+            memcpy(q, to, lt);
+        }
+    }
 }
 
 int sm_count() {
