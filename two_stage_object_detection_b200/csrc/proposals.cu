@@ -705,6 +705,21 @@ struct NmsArgs {
     int* keep;             // [B][keep_cap]
     int* n_keep;           // [B]
     int tri_tiles;
+    // the proposal layer's last step (nets/rpn.py:65-69), done by nms_tail_kernel when fin_rois is set
+    const int* fin_order;  // [B][row_stride] sorted position -> anchor index
+    float4* fin_rois;      // [B][keep_cap]
+    int* fin_src;          // [B][keep_cap] or null
+    int* fin_n_keep;       // [B] or null
+    int* fin_status;       // [B]
+};
+
+struct NmsFinalize {
+    const int* order;
+    float* rois;
+    int* roi_src;
+    int* n_keep;
+    int* status;
+    bool fused;  // out: the NMS launches did it (otherwise the caller launches finalize_kernel)
 };
 
 // Length of an image's super-block in this launch.  The first block is sized by the host for keep_cap; a
@@ -1212,6 +1227,27 @@ __global__ void __cluster_dims__(NMS_TAIL_CL, 1, 1) __launch_bounds__(NMS_MAX_WO
         __threadfence();
         cluster.sync();
     }
+    // Pad with arange / truncate / gather (finalize_kernel's job) by the cluster that has just seen the image done:
+    // one launch less per proposal layer.  keep_cap == n_post here.  A padded row r >= k takes sorted position
+    // r - k; the reference raises IndexError when that runs past the candidate list, i.e. iff n_post - 1 - k >= n.
+    if (a.fin_rois) {
+        const int k = __ldcg(a.n_keep + b), n_post = a.keep_cap;
+        for (int r = rank * NMS_CB + (int)threadIdx.x; r < n_post; r += NMS_TAIL_CL * NMS_CB) {
+            const int p = r < k ? __ldcg(a.keep + (size_t)b * n_post + r) : r - k;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            int src = -1;
+            if (p < n) {
+                v = __ldg(a.boxes + (size_t)b * a.row_stride + p);
+                src = __ldg(a.fin_order + (size_t)b * a.row_stride + p);
+            }
+            a.fin_rois[(size_t)b * n_post + r] = v;
+            if (a.fin_src) a.fin_src[(size_t)b * n_post + r] = src;
+        }
+        if (rank == 0 && threadIdx.x == 0) {
+            a.fin_status[b] = (k < n_post && n_post - 1 - k >= n) ? FRCNN_IMG_PAD_INDEX_ERROR : FRCNN_IMG_OK;
+            if (a.fin_n_keep) a.fin_n_keep[b] = k;
+        }
+    }
 }
 
 // nets/rpn.py:65-69: pad with arange, truncate, gather
@@ -1305,7 +1341,7 @@ static size_t nms_ws_layout(Workspace& ws, int batch, int n_rows, int keep_cap, 
 
 static int run_nms_sorted(const float* sorted_boxes, const int32_t* n_sel, int batch, int row_stride,
                           double thresh, int keep_cap, int superblock, int32_t* keep, int32_t* n_keep,
-                          void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream, NmsFinalize* fin = nullptr) {
     Workspace ws(workspace, workspace_bytes);
     NmsArgs a;
     memset(&a, 0, sizeof(a));
@@ -1350,6 +1386,14 @@ static int run_nms_sorted(const float* sorted_boxes, const int32_t* n_sel, int b
         a.len = std::min(a.S, 1024);  // 8 CTAs per image: 40 + 4 * ceil(keep_cap / 256) tiles per round
         const int ncb = a.len / NMS_CB;
         a.tri_tiles = 2 * ncb * (ncb + 1);
+        if (fin) {
+            a.fin_order = fin->order;
+            a.fin_rois = (float4*)fin->rois;
+            a.fin_src = fin->roi_src;
+            a.fin_n_keep = fin->n_keep;
+            a.fin_status = fin->status;
+            fin->fused = true;
+        }
         nms_tail_kernel<<<batch * NMS_TAIL_CL, NMS_CB, 0, stream>>>(a);
         FRCNN_LAUNCH_CHECK();
         return FRCNN_OK;
@@ -1642,9 +1686,11 @@ int frcnn_proposals(const frcnn_proposal_params* p, const frcnn_anchor_spec* anc
     if (rc) return rc;
     rc = run_topk(w.keys, w.boxes, B, N, rows, w.order, w.n_sel, w.sorted, w.topk_ws, w.topk_bytes, stream);
     if (rc) return rc;
+    NmsFinalize fin = {w.order, rois, roi_src, n_keep, status, false};
     rc = run_nms_sorted(w.sorted, w.n_sel, B, rows, p->nms_thresh, p->n_post_nms, p->nms_superblock, w.keep,
-                        w.n_keep, w.nms_ws, w.nms_bytes, stream);
+                        w.n_keep, w.nms_ws, w.nms_bytes, stream, &fin);
     if (rc) return rc;
+    if (fin.fused) return FRCNN_OK;  // nms_tail_kernel wrote rois / roi_src / n_keep / status
     // one CTA per image (the status flag is a CTA-wide OR); two dependent L2 round trips per row, so as many rows
     // in flight as the CTA can hold
     finalize_kernel<<<B, p->n_post_nms > 512 ? 1024 : (p->n_post_nms > 256 ? 512 : 256), 0, stream>>>((const float4*)w.sorted, w.order, w.n_sel, w.keep, w.n_keep, rows,
