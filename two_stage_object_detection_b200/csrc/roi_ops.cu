@@ -504,6 +504,58 @@ __device__ __forceinline__ void scan_first_max(float2& v, int2& idx, const float
 __device__ __forceinline__ void scan_first_max(float& v, int& idx, float t, int p) {
     if (t > v) v = t, idx = p;
 }
+#ifndef FRCNN_TRAIN_VARIANTS
+#define FRCNN_TRAIN_VARIANTS 7
+#endif
+#ifndef FRCNN_TRAIN_ROW_UNROLL
+#define FRCNN_TRAIN_ROW_UNROLL 1
+#endif
+#define FRCNN_PRAGMA_(x) _Pragma(#x)
+#define FRCNN_UNROLL(n) FRCNN_PRAGMA_(unroll n)
+// The same update under a per-lane predicate (a pixel column the bin may not have): the predicate joins the compare
+// (FSETP.GT.AND), so a column costs the same three instructions per channel whether it exists or not and the row
+// body stays straight-line.
+__device__ __forceinline__ void scan_first_max_if(float4& v, int4& idx, const float4& t, int p, bool on) {
+    const bool cx = on & (t.x > v.x), cy = on & (t.y > v.y), cz = on & (t.z > v.z), cw = on & (t.w > v.w);
+    v.x = cx ? t.x : v.x, idx.x = cx ? p : idx.x;
+    v.y = cy ? t.y : v.y, idx.y = cy ? p : idx.y;
+    v.z = cz ? t.z : v.z, idx.z = cz ? p : idx.z;
+    v.w = cw ? t.w : v.w, idx.w = cw ? p : idx.w;
+}
+__device__ __forceinline__ void scan_first_max_if(float2& v, int2& idx, const float2& t, int p, bool on) {
+    const bool cx = on & (t.x > v.x), cy = on & (t.y > v.y);
+    v.x = cx ? t.x : v.x, idx.x = cx ? p : idx.x;
+    v.y = cy ? t.y : v.y, idx.y = cy ? p : idx.y;
+}
+__device__ __forceinline__ void scan_first_max_if(float& v, int& idx, float t, int p, bool on) {
+    const bool c = on & (t > v);
+    v = c ? t : v, idx = c ? p : idx;
+}
+// Rows of a training bin, NW pixel columns per row as straight-line predicated code (row-major order, strict `>`:
+// the reference's first maximum).  `rp` = the window's first pixel in the interleaved table, `p` = its flat index
+// y * W + x in the plane; a row step is WP table elements / W plane elements.  Columns past the window are loaded
+// (they lie inside the table or the staging region behind it) and ignored.  LONG: windows wider than NW finish
+// each row in a loop.
+template <int NW, bool LONG, typename V, typename I>
+__device__ __forceinline__ void scan_rows(V& v, I& idx, const V* rp, int p, int hh, int ww, int WP, int W) {
+    const bool w1 = ww > 0, w2 = ww > 1, w3 = ww > 2, w4 = ww > 3, w5 = ww > 4, w6 = ww > 5;
+#ifdef FRCNN_TRAIN_ROW_UNROLL
+    FRCNN_UNROLL(FRCNN_TRAIN_ROW_UNROLL)
+#endif
+    for (int y = 0; y < hh; ++y, rp += WP, p += W) {
+        // all loads first
+        const V t0 = rp[0], t1 = rp[NW > 1 ? 1 : 0], t2 = rp[NW > 2 ? 2 : 0], t3 = rp[NW > 3 ? 3 : 0];
+        const V t4 = rp[NW > 4 ? 4 : 0], t5 = rp[NW > 5 ? 5 : 0];
+        scan_first_max_if(v, idx, t0, p, w1);
+        if (NW > 1) scan_first_max_if(v, idx, t1, p + 1, w2);
+        if (NW > 2) scan_first_max_if(v, idx, t2, p + 2, w3);
+        if (NW > 3) scan_first_max_if(v, idx, t3, p + 3, w4);
+        if (NW > 4) scan_first_max_if(v, idx, t4, p + 4, w5);
+        if (NW > 5) scan_first_max_if(v, idx, t5, p + 5, w6);
+        if (LONG)
+            for (int x = NW; x < ww; ++x) scan_first_max(v, idx, rp[x], p + x);
+    }
+}
 __device__ __forceinline__ void vneg(int& i) { i = -1; }
 __device__ __forceinline__ void vneg(int4& i) { i = make_int4(-1, -1, -1, -1); }
 __device__ __forceinline__ void vneg(int2& i) { i = make_int2(-1, -1); }
@@ -758,14 +810,40 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
                 vsplat(v, -FLT_MAX);
                 vneg(idx);
                 const unsigned m = (unsigned)((h.y & w.y) >> 31);  // all ones iff the bin is non-empty
-                int hr = 0, wr = 0;  // empty range unless the bin is non-empty
-                if (m) {
-                    hr = s_hraw[RAW ? cur : 0][RAW ? j : 0][RAW ? ph : 0];
-                    wr = s_wraw[RAW ? cur : 0][RAW ? j : 0][RAW ? pw : 0];
-                }
-                const int x0 = wr & 0xFFFF, x1 = wr >> 16;
-                for (int y = hr & 0xFFFF; y < (hr >> 16); ++y)
-                    for (int x = x0; x < x1; ++x) scan_first_max(v, idx, tab[y * WP + x], y * W + x);
+                // [lo,hi) per axis, hi >= lo: an empty axis gives zero rows or only predicated-off columns
+                const int hr = s_hraw[RAW ? cur : 0][RAW ? j : 0][RAW ? ph : 0];
+                const int wr = s_wraw[RAW ? cur : 0][RAW ? j : 0][RAW ? pw : 0];
+                const int y0 = hr & 0xFFFF, x0 = wr & 0xFFFF, hh = (hr >> 16) - y0, ww = (wr >> 16) - x0;
+                // the nested loops the compiler made of "for y, for x" spent two thirds of their instructions on
+                // control flow and re-derived addresses (450 per 32 bins x 4 channels, of which 120 compare /
+                // select); the row body is chosen per warp by the widest window among its lanes
+                const V* rp = tab + (y0 * WP + x0);
+                const int p0 = y0 * W + x0;
+#if FRCNN_TRAIN_VARIANTS == 1
+                scan_rows<4, true>(v, idx, rp, p0, hh, ww, WP, W);
+#elif FRCNN_TRAIN_VARIANTS == 2
+                if (!__any_sync(0xFFFFFFFFu, ww > 3)) scan_rows<3, false>(v, idx, rp, p0, hh, ww, WP, W);
+                else scan_rows<4, true>(v, idx, rp, p0, hh, ww, WP, W);
+#elif FRCNN_TRAIN_VARIANTS == 3
+                if (!__any_sync(0xFFFFFFFFu, ww > 2)) scan_rows<2, false>(v, idx, rp, p0, hh, ww, WP, W);
+                else if (!__any_sync(0xFFFFFFFFu, ww > 3)) scan_rows<3, false>(v, idx, rp, p0, hh, ww, WP, W);
+                else scan_rows<4, true>(v, idx, rp, p0, hh, ww, WP, W);
+#elif FRCNN_TRAIN_VARIANTS == 4
+                if (!__any_sync(0xFFFFFFFFu, ww > 2)) scan_rows<2, false>(v, idx, rp, p0, hh, ww, WP, W);
+                else if (!__any_sync(0xFFFFFFFFu, ww > 3)) scan_rows<3, false>(v, idx, rp, p0, hh, ww, WP, W);
+                else if (!__any_sync(0xFFFFFFFFu, ww > 4)) scan_rows<4, false>(v, idx, rp, p0, hh, ww, WP, W);
+                else scan_rows<4, true>(v, idx, rp, p0, hh, ww, WP, W);
+#else
+                if (!__any_sync(0xFFFFFFFFu, ww > 3)) {
+                    if (!__any_sync(0xFFFFFFFFu, ww > 1)) scan_rows<1, false>(v, idx, rp, p0, hh, ww, WP, W);
+                    else if (!__any_sync(0xFFFFFFFFu, ww > 2)) scan_rows<2, false>(v, idx, rp, p0, hh, ww, WP, W);
+                    else scan_rows<3, false>(v, idx, rp, p0, hh, ww, WP, W);
+                } else if (!__any_sync(0xFFFFFFFFu, ww > 6)) {
+                    if (!__any_sync(0xFFFFFFFFu, ww > 4)) scan_rows<4, false>(v, idx, rp, p0, hh, ww, WP, W);
+                    else if (!__any_sync(0xFFFFFFFFu, ww > 5)) scan_rows<5, false>(v, idx, rp, p0, hh, ww, WP, W);
+                    else scan_rows<6, false>(v, idx, rp, p0, hh, ww, WP, W);
+                } else scan_rows<4, true>(v, idx, rp, p0, hh, ww, WP, W);
+#endif
                 float* o = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.out) + s_ob[cur][j]) + e;
                 if (valid) {
                     vstore<false>(o, BINS, v, m, cs);
@@ -892,7 +970,12 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
           }
         };
         if (nb == NB && cs == CS) {
-            if constexpr (BPT == 2) {
+            if constexpr (ARGMAX) {
+                // rolled: unrolled over the 7 RoIs of a thread the training scan ran 0.170 ms instead of 0.100 ms
+                // (instruction footprint); sharing one copy of the bin code with the ragged path below costs 6 %
+#pragma unroll 1
+                for (int it = 0; it < ITERS; ++it) one_bin(it * RPI + ej, true, true);
+            } else if constexpr (BPT == 2) {
                 // not unrolled (registers); prefetching the next RoI's entries by hand was measured slower too
 #pragma unroll 1
                 for (int it = 0; it < ITERS; ++it) {
@@ -913,6 +996,157 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
             }
         }
         if (!prefetched) prefetch_boxes();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RoIPool forward for training (value + argmax, 7x7 / 14x14): persistent CTAs over (image, 4-channel slab) items.
+//
+// The table kernel above spends half of its time outside the scan when an image has only ~128 sampled RoIs
+// (ncu, training configuration: 24 % of the stall samples in the per-CTA prologue -- waiting for the slab -- and
+// 26 % in the per-batch bin geometry + CTA barrier, which every one of the 128 slab CTAs of an image repeats).
+// Here (1) the [lo,hi) ranges of every bin row / column are computed once per RoI by roi_pool_ranges_kernel and
+// a CTA copies the ranges of up to TR_CHUNK RoIs into shared memory in one go: no geometry arithmetic, no
+// per-batch barrier, no double buffering; (2) a CTA keeps taking items from an atomic counter and asks for the
+// NEXT item's planes (cp.async.bulk into the other of two staging buffers) before it touches the current one,
+// so the slab latency is paid once per CTA instead of once per item; (3) the bin scan is the predicated
+// straight-line row body (scan_rows).  Same mapping as before: thread = one bin of one RoI (392 = 8 x 49 =
+// 2 x 196), consecutive lanes = consecutive bins, value and argmax stored in 128-byte runs.
+// ---------------------------------------------------------------------------------------------
+constexpr int TR_THREADS = 392;
+constexpr int TR_CHUNK = 128;  // RoIs whose ranges are resident at a time (a training image has 128 samples)
+
+// rng[r][0..P) = bin rows, [P..2P) = bin columns of the RoI at position r of the image-ordered list, lo | hi << 16
+// (tab_entry: the same rounding / division / floor / ceil / clamp as every RoIPool kernel of this file).  Also
+// resets the work counter of the gather that follows.
+__global__ void __launch_bounds__(256) roi_pool_ranges_kernel(RoiArgs a, int* __restrict__ rng, int P,
+                                                              int* __restrict__ counter, int first_item) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx == 0) *counter = first_item;
+    if (idx >= a.K * 2 * P) return;
+    const int r = idx / (2 * P), ti = idx - r * 2 * P;
+    const float* rp = a.rois5 + (size_t)roi_at(a, r) * 5;
+    int raw;
+    if (ti < P) tab_entry<1>(ti, P, __ldg(rp + 2), __ldg(rp + 4), a.scale, a.H, 1, 0, 4, &raw);
+    else tab_entry<1>(ti - P, P, __ldg(rp + 1), __ldg(rp + 3), a.scale, a.W, 1, 0, 4, &raw);
+    rng[idx] = raw;
+}
+
+template <int P>
+__global__ void __launch_bounds__(TR_THREADS, 2)
+roi_pool_train_kernel(RoiArgs a, const int* __restrict__ rng, int* __restrict__ counter) {
+    typedef float4 V;
+    constexpr int CS = 4, BINS = P * P, RPI = TR_THREADS / BINS;
+    static_assert(RPI * BINS == TR_THREADS, "thread mapping");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ int s_rng[TR_CHUNK][2 * P];
+    __shared__ int s_k[TR_CHUNK];
+    __shared__ int s_next[2];
+    const int H = a.H, W = a.W, HW = H * W, WP = a.pitch, HWp = (H * WP + 3) & ~3;
+    V* tab = reinterpret_cast<V*>(smem_raw);
+    const int raw_elems = (CS * HW + 3) & ~3;
+    float* raw0 = reinterpret_cast<float*>(tab + HWp);
+    const int tid = threadIdx.x;
+    const int slabs = (a.C + CS - 1) / CS, items = a.B * slabs;
+    const int e = tid % BINS, ej = tid / BINS, ph = e / P, pw = e - ph * P;
+    int item = blockIdx.x;
+    if (item >= items) return;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+    }
+    __syncthreads();
+    auto slab_src = [&](int it, int& cs) {
+        const int b = it / slabs, c0 = (it - b * slabs) * CS;
+        cs = min(CS, a.C - c0);
+        return a.feat + ((size_t)b * a.C + c0) * HW;
+    };
+    // bulk copies need a 16-byte aligned source and size
+    auto tma_ok = [&](const float* src, int cs) {
+        return ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (((cs * HW) & 3) == 0);
+    };
+    auto request = [&](int it, int buf) {  // thread 0
+        int cs;
+        const float* src = slab_src(it, cs);
+        if (!tma_ok(src, cs)) return;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t bytes = (uint32_t)(cs * HW) * 4u;
+        mbar_expect_tx(&bar[buf], bytes);
+        for (uint32_t off = 0; off < bytes; off += 32768u)
+            bulk_g2s(reinterpret_cast<char*>(raw0 + buf * raw_elems) + off, reinterpret_cast<const char*>(src) + off,
+                     min(32768u, bytes - off), &bar[buf]);
+    };
+    if (tid == 0) request(item, 0);
+    uint32_t uses = 0;  // bit b: parity of staging buffer b's next completion
+    for (int n = 0; item < items; ++n) {
+        const int buf = n & 1;
+        const int b = item / slabs, c0 = (item - b * slabs) * CS;
+        int cs;
+        const float* src = slab_src(item, cs);
+        float* raw = raw0 + buf * raw_elems;
+        if (tid == 0) {
+            // the other staging buffer was read by the previous item's interleave pass, which every thread left
+            // before the barrier that closed that item
+            const int nxt = atomicAdd(counter, 1);
+            s_next[buf] = nxt;  // read after this item's closing barrier, rewritten two items later
+            if (nxt < items) request(nxt, buf ^ 1);
+        }
+        int r_begin, r_end;
+        roi_range(a, b, r_begin, r_end);
+        const int n_roi = r_end - r_begin;
+        auto load_ranges = [&](int first, int nc) {
+            const int* g = rng + (size_t)(r_begin + first) * (2 * P);
+            int* d = &s_rng[0][0];
+            for (int i = tid; i < nc * 2 * P; i += TR_THREADS) d[i] = __ldg(g + i);
+            for (int i = tid; i < nc; i += TR_THREADS) s_k[i] = roi_at(a, r_begin + first + i);
+        };
+        load_ranges(0, min(n_roi, TR_CHUNK));
+        if (tma_ok(src, cs)) {
+            mbar_wait(&bar[buf], (uses >> buf) & 1u);
+            uses ^= 1u << buf;
+        } else {
+            for (int i = tid; i < cs * HW; i += TR_THREADS) raw[i] = __ldg(src + i);
+            __syncthreads();
+        }
+        build_max_tables<V, 1, TR_THREADS>(tab, raw, cs, H, W, WP, HWp, tid);  // ends with a CTA barrier
+        for (int first = 0; first < n_roi; first += TR_CHUNK) {
+            const int nc = min(n_roi - first, TR_CHUNK);
+            if (first > 0) {
+                __syncthreads();
+                load_ranges(first, nc);
+                __syncthreads();
+            }
+#pragma unroll 1
+            for (int it = 0; it * RPI < nc; ++it) {
+                const int j = it * RPI + ej;
+                const bool valid = j < nc;
+                const int jj = valid ? j : 0;
+                const int hr = s_rng[jj][ph], wr = s_rng[jj][P + pw];
+                const int y0 = hr & 0xFFFF, x0 = wr & 0xFFFF, hh = (hr >> 16) - y0, ww = (wr >> 16) - x0;
+                V v;
+                int4 idx;
+                vsplat(v, -FLT_MAX);
+                vneg(idx);
+                const V* rp = tab + (y0 * WP + x0);
+                const int p0 = y0 * W + x0;
+                // row body by the widest window among the warp's lanes (hi >= lo on both axes: an empty axis
+                // gives zero rows or only predicated-off columns)
+                if (!__any_sync(0xFFFFFFFFu, ww > 3)) {
+                    if (!__any_sync(0xFFFFFFFFu, ww > 2)) scan_rows<2, false>(v, idx, rp, p0, hh, ww, WP, W);
+                    else scan_rows<3, false>(v, idx, rp, p0, hh, ww, WP, W);
+                } else if (!__any_sync(0xFFFFFFFFu, ww > 4)) scan_rows<4, false>(v, idx, rp, p0, hh, ww, WP, W);
+                else scan_rows<4, true>(v, idx, rp, p0, hh, ww, WP, W);
+                const unsigned m = (hh > 0 && ww > 0) ? 0xFFFFFFFFu : 0u;  // empty bin: 0, argmax -1
+                if (valid) {
+                    const size_t ob = ((size_t)s_k[jj] * a.C + c0) * BINS + e;
+                    vstore<false>(a.out + ob, BINS, v, m, cs);
+                    istore(a.argmax + ob, BINS, idx, cs);
+                }
+            }
+        }
+        __syncthreads();  // table, ranges and this item's staging buffer are free
+        item = s_next[buf];
     }
 }
 
@@ -2900,6 +3134,37 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
         }
         if (argmax) {
             a.pitch = W | 1;
+            // persistent kernel over (image, slab) items with precomputed bin ranges: interleaved pixels + two
+            // staging buffers (the next item's planes arrive while this one is scanned)
+            static const int train_impl = env_int("FRCNN_TRAIN_IMPL", 0);  // experiments only: 1 = table-kernel scan
+            const size_t tr_smem = (size_t)((H * a.pitch + 3) & ~3) * 16 + (size_t)2 * ((4 * H * W + 3) & ~3) * 4;
+            const size_t tr_static = (size_t)TR_CHUNK * (2 * PH + 1) * 4 + 64;
+            if (train_impl != 1 && tr_smem + tr_static <= 220 * 1024) {
+                Workspace ews(workspace, workspace_bytes);
+                RoiWs w;
+                roi_layout(ews, B, K, &w);
+                if (!ews.ok()) {
+                    set_error("%s: workspace too small or misaligned (%zu needed, %zu given)", who, ews.off, workspace_bytes);
+                    return FRCNN_ERR_WORKSPACE;
+                }
+                a.CS = 4;
+                const int items = B * cdiv(C, 4);
+                const int per_sm = tr_smem + tr_static + 1024 <= 113 * 1024 ? 2 : 1;
+                const int ctas = std::min(items, per_sm * sm_count());
+                int* const rng = reinterpret_cast<int*>(w.ent);
+                roi_pool_ranges_kernel<<<cdiv((int64_t)K * 2 * PH, 256), 256, 0, stream>>>(a, rng, PH, w.sorted, ctas);
+                FRCNN_LAUNCH_CHECK();
+                if (PH == 7) {
+                    FRCNN_SMEM(roi_pool_train_kernel<7>, tr_smem);
+                    roi_pool_train_kernel<7><<<ctas, TR_THREADS, tr_smem, stream>>>(a, rng, w.sorted);
+                } else {
+                    FRCNN_SMEM(roi_pool_train_kernel<14>, tr_smem);
+                    roi_pool_train_kernel<14><<<ctas, TR_THREADS, tr_smem, stream>>>(a, rng, w.sorted);
+                }
+                FRCNN_LAUNCH_CHECK();
+                note_roi_kernel("roi_pool_train_kernel<%d>", PH);
+                return FRCNN_OK;
+            }
             if (table_bytes(1, 4, a.pitch) <= budget2) {
                 if (PH == 7) FRCNN_TAB(7, 392, 4, 2, true, 1);
                 FRCNN_TAB(14, 392, 4, 2, true, 1);
