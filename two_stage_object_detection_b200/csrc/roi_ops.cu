@@ -1013,7 +1013,37 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
 // straight-line row body (scan_rows).  Same mapping as before: thread = one bin of one RoI (392 = 8 x 49 =
 // 2 x 196), consecutive lanes = consecutive bins, value and argmax stored in 128-byte runs.
 // ---------------------------------------------------------------------------------------------
-constexpr int TR_THREADS = 392;
+// Loads through 32-bit shared-window addresses kept in registers: with generic pointers into __shared__ arrays the
+// compiler re-derived the window base (S2R SR_CgaCtaId, MOV, LEA) in every iteration of the bin loop.
+__device__ __forceinline__ int lds_i32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF));
+    return v;
+}
+// scan_rows on a shared-window address (`row_bytes` = table pitch in bytes)
+template <int NW, bool LONG>
+__device__ __forceinline__ void scan_rows_s(float4& v, int4& idx, uint32_t addr, int p, int hh, int ww, int row_bytes,
+                                            int W) {
+    const bool w1 = ww > 0, w2 = ww > 1, w3 = ww > 2, w4 = ww > 3;
+#pragma unroll 1
+    for (int y = 0; y < hh; ++y, addr += row_bytes, p += W) {
+        constexpr int O2 = NW > 2 ? 32 : 0, O3 = NW > 3 ? 48 : 0;
+        const float4 t0 = lds_f4<0>(addr), t1 = lds_f4<16>(addr), t2 = lds_f4<O2>(addr), t3 = lds_f4<O3>(addr);
+        scan_first_max_if(v, idx, t0, p, w1);
+        scan_first_max_if(v, idx, t1, p + 1, w2);
+        if (NW > 2) scan_first_max_if(v, idx, t2, p + 2, w3);
+        if (NW > 3) scan_first_max_if(v, idx, t3, p + 3, w4);
+        if (LONG)
+            for (int x = NW; x < ww; ++x) scan_first_max(v, idx, lds_f4<0>(addr + 16 * x), p + x);
+    }
+}
+
 constexpr int TR_CHUNK = 128;  // RoIs whose ranges are resident at a time (a training image has 128 samples)
 
 // rng[r][0..P) = bin rows, [P..2P) = bin columns of the RoI at position r of the image-ordered list, lo | hi << 16
@@ -1032,12 +1062,12 @@ __global__ void __launch_bounds__(256) roi_pool_ranges_kernel(RoiArgs a, int* __
     rng[idx] = raw;
 }
 
-template <int P>
-__global__ void __launch_bounds__(TR_THREADS, 2)
+template <int P, int TR_THREADS>
+__global__ void __launch_bounds__(TR_THREADS, 1024 / TR_THREADS)
 roi_pool_train_kernel(RoiArgs a, const int* __restrict__ rng, int* __restrict__ counter) {
     typedef float4 V;
-    constexpr int CS = 4, BINS = P * P, RPI = TR_THREADS / BINS;
-    static_assert(RPI * BINS == TR_THREADS, "thread mapping");
+    constexpr int CS = 4, BINS = P * P;
+    static_assert(TR_THREADS % 128 == 0, "whole warps, evenly over the four schedulers");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ int s_rng[TR_CHUNK][2 * P];
@@ -1049,7 +1079,6 @@ roi_pool_train_kernel(RoiArgs a, const int* __restrict__ rng, int* __restrict__ 
     float* raw0 = reinterpret_cast<float*>(tab + HWp);
     const int tid = threadIdx.x;
     const int slabs = (a.C + CS - 1) / CS, items = a.B * slabs;
-    const int e = tid % BINS, ej = tid / BINS, ph = e / P, pw = e - ph * P;
     int item = blockIdx.x;
     if (item >= items) return;
     if (tid == 0) {
@@ -1077,8 +1106,18 @@ roi_pool_train_kernel(RoiArgs a, const int* __restrict__ rng, int* __restrict__ 
             bulk_g2s(reinterpret_cast<char*>(raw0 + buf * raw_elems) + off, reinterpret_cast<const char*>(src) + off,
                      min(32768u, bytes - off), &bar[buf]);
     };
-    if (tid == 0) request(item, 0);
+    int pending = 0;  // thread 0: the item after the next one
+    if (tid == 0) {
+        request(item, 0);
+        pending = atomicAdd(counter, 1);
+    }
     uint32_t uses = 0;  // bit b: parity of staging buffer b's next completion
+    uint32_t tab_s = smem_u32(tab), rng_s = smem_u32(&s_rng[0][0]), k_s = smem_u32(&s_k[0]);
+    // opaque copies: otherwise the window base is re-derived per bin instead of kept in a register
+    asm volatile("mov.u32 %0, %0;" : "+r"(tab_s));
+    asm volatile("mov.u32 %0, %0;" : "+r"(rng_s));
+    asm volatile("mov.u32 %0, %0;" : "+r"(k_s));
+    const uint32_t kstride_b = (uint32_t)a.C * BINS * 4u;  // bytes between two RoIs' output blocks (host: < 2^32)
     for (int n = 0; item < items; ++n) {
         const int buf = n & 1;
         const int b = item / slabs, c0 = (item - b * slabs) * CS;
@@ -1087,11 +1126,15 @@ roi_pool_train_kernel(RoiArgs a, const int* __restrict__ rng, int* __restrict__ 
         float* raw = raw0 + buf * raw_elems;
         if (tid == 0) {
             // the other staging buffer was read by the previous item's interleave pass, which every thread left
-            // before the barrier that closed that item
-            const int nxt = atomicAdd(counter, 1);
+            // before the barrier that closed that item.  The counter is read one item ahead of its use, so the
+            // atomic's round trip is not on any item's critical path.
+            const int nxt = pending;
             s_next[buf] = nxt;  // read after this item's closing barrier, rewritten two items later
             if (nxt < items) request(nxt, buf ^ 1);
+            pending = atomicAdd(counter, 1);
         }
+        unsigned char* const obase = reinterpret_cast<unsigned char*>(a.out + (size_t)c0 * BINS);
+        unsigned char* const abase = reinterpret_cast<unsigned char*>(a.argmax + (size_t)c0 * BINS);
         int r_begin, r_end;
         roi_range(a, b, r_begin, r_end);
         const int n_roi = r_end - r_begin;
@@ -1117,31 +1160,43 @@ roi_pool_train_kernel(RoiArgs a, const int* __restrict__ rng, int* __restrict__ 
                 load_ranges(first, nc);
                 __syncthreads();
             }
+            // task i = (RoI j, bin e) of the chunk, i = j * BINS + e: consecutive lanes are consecutive bins, a warp may
+            // straddle two RoIs; whole warps whatever BINS is (392 = 8 x 49 threads left a 13th warp of 8 lanes and
+            // 4 + 3 + 3 + 3 warps on the SM's four schedulers: the closing barrier waited for the first one's)
 #pragma unroll 1
-            for (int it = 0; it * RPI < nc; ++it) {
-                const int j = it * RPI + ej;
-                const bool valid = j < nc;
-                const int jj = valid ? j : 0;
-                const int hr = s_rng[jj][ph], wr = s_rng[jj][P + pw];
+            for (int i0 = 0; i0 < nc * BINS; i0 += TR_THREADS) {
+                const bool valid = i0 + tid < nc * BINS;
+                const int i = valid ? i0 + tid : 0;
+                const int j = i / BINS, e = i - j * BINS, ph = e / P, pw = e - ph * P;
+                const uint32_t rj = rng_s + (uint32_t)j * (2 * P * 4);
+                const int hr = lds_i32(rj + ph * 4), wr = lds_i32(rj + (P + pw) * 4);
                 const int y0 = hr & 0xFFFF, x0 = wr & 0xFFFF, hh = (hr >> 16) - y0, ww = (wr >> 16) - x0;
+                // an empty bin (hi >= lo on both axes: zero rows, or only predicated-off columns) scans nothing and
+                // keeps its initial value: 0 and argmax -1; a non-empty one starts from -FLT_MAX like the reference
                 V v;
                 int4 idx;
-                vsplat(v, -FLT_MAX);
+                vsplat(v, (hh > 0 && ww > 0) ? -FLT_MAX : 0.f);
                 vneg(idx);
-                const V* rp = tab + (y0 * WP + x0);
+                const uint32_t addr = tab_s + (uint32_t)(y0 * WP + x0) * 16u;
                 const int p0 = y0 * W + x0;
-                // row body by the widest window among the warp's lanes (hi >= lo on both axes: an empty axis
-                // gives zero rows or only predicated-off columns)
+                // row body by the widest window among the warp's lanes
                 if (!__any_sync(0xFFFFFFFFu, ww > 3)) {
-                    if (!__any_sync(0xFFFFFFFFu, ww > 2)) scan_rows<2, false>(v, idx, rp, p0, hh, ww, WP, W);
-                    else scan_rows<3, false>(v, idx, rp, p0, hh, ww, WP, W);
-                } else if (!__any_sync(0xFFFFFFFFu, ww > 4)) scan_rows<4, false>(v, idx, rp, p0, hh, ww, WP, W);
-                else scan_rows<4, true>(v, idx, rp, p0, hh, ww, WP, W);
-                const unsigned m = (hh > 0 && ww > 0) ? 0xFFFFFFFFu : 0u;  // empty bin: 0, argmax -1
+                    if (!__any_sync(0xFFFFFFFFu, ww > 2)) scan_rows_s<2, false>(v, idx, addr, p0, hh, ww, WP * 16, W);
+                    else scan_rows_s<3, false>(v, idx, addr, p0, hh, ww, WP * 16, W);
+                } else if (!__any_sync(0xFFFFFFFFu, ww > 4)) scan_rows_s<4, false>(v, idx, addr, p0, hh, ww, WP * 16, W);
+                else scan_rows_s<4, true>(v, idx, addr, p0, hh, ww, WP * 16, W);
                 if (valid) {
-                    const size_t ob = ((size_t)s_k[jj] * a.C + c0) * BINS + e;
-                    vstore<false>(a.out + ob, BINS, v, m, cs);
-                    istore(a.argmax + ob, BINS, idx, cs);
+                    const unsigned long long o =
+                        (unsigned long long)(unsigned)lds_i32(k_s + j * 4) * kstride_b + (unsigned)(e * 4);
+                    float* po = reinterpret_cast<float*>(obase + o);
+                    int* pa = reinterpret_cast<int*>(abase + o);
+                    if (cs == CS) {
+                        po[0] = v.x, po[BINS] = v.y, po[2 * BINS] = v.z, po[3 * BINS] = v.w;
+                        pa[0] = idx.x, pa[BINS] = idx.y, pa[2 * BINS] = idx.z, pa[3 * BINS] = idx.w;
+                    } else {
+                        vstore<false>(po, BINS, v, 0xFFFFFFFFu, cs);
+                        istore(pa, BINS, idx, cs);
+                    }
                 }
             }
         }
@@ -3147,6 +3202,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
                     set_error("%s: workspace too small or misaligned (%zu needed, %zu given)", who, ews.off, workspace_bytes);
                     return FRCNN_ERR_WORKSPACE;
                 }
+                FRCNN_CHECK_ARG((int64_t)C * PH * PW * 4 < ((int64_t)1 << 32), "%s: too many channels", who);
                 a.CS = 4;
                 const int items = B * cdiv(C, 4);
                 const int per_sm = tr_smem + tr_static + 1024 <= 113 * 1024 ? 2 : 1;
@@ -3154,16 +3210,22 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
                 int* const rng = reinterpret_cast<int*>(w.ent);
                 roi_pool_ranges_kernel<<<cdiv((int64_t)K * 2 * PH, 256), 256, 0, stream>>>(a, rng, PH, w.sorted, ctas);
                 FRCNN_LAUNCH_CHECK();
+                static const int tr_threads = env_int("FRCNN_TRAIN_THREADS", 512);  // experiments only
+#define FRCNN_TRAIN(PP_, TH_)                                                                   \
+    do {                                                                                       \
+        FRCNN_SMEM((roi_pool_train_kernel<PP_, TH_>), tr_smem);                                \
+        roi_pool_train_kernel<PP_, TH_><<<ctas, TH_, tr_smem, stream>>>(a, rng, w.sorted);     \
+        FRCNN_LAUNCH_CHECK();                                                                  \
+        note_roi_kernel("roi_pool_train_kernel<%d,%d>", PP_, TH_);                             \
+        return FRCNN_OK;                                                                       \
+    } while (0)
                 if (PH == 7) {
-                    FRCNN_SMEM(roi_pool_train_kernel<7>, tr_smem);
-                    roi_pool_train_kernel<7><<<ctas, TR_THREADS, tr_smem, stream>>>(a, rng, w.sorted);
-                } else {
-                    FRCNN_SMEM(roi_pool_train_kernel<14>, tr_smem);
-                    roi_pool_train_kernel<14><<<ctas, TR_THREADS, tr_smem, stream>>>(a, rng, w.sorted);
+                    if (tr_threads == 384) FRCNN_TRAIN(7, 384);
+                    FRCNN_TRAIN(7, 512);
                 }
-                FRCNN_LAUNCH_CHECK();
-                note_roi_kernel("roi_pool_train_kernel<%d>", PH);
-                return FRCNN_OK;
+                if (tr_threads == 384) FRCNN_TRAIN(14, 384);
+                FRCNN_TRAIN(14, 512);
+#undef FRCNN_TRAIN
             }
             if (table_bytes(1, 4, a.pitch) <= budget2) {
                 if (PH == 7) FRCNN_TAB(7, 392, 4, 2, true, 1);
