@@ -999,6 +999,188 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
     }
 }
 
+// Loads through 32-bit shared-window addresses kept in registers: with generic pointers into __shared__ arrays the
+// compiler re-derived the window base (S2R SR_CgaCtaId, MOV, LEA) in every iteration of the bin loop.
+__device__ __forceinline__ int lds_i32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF));
+    return v;
+}
+// ---------------------------------------------------------------------------------------------
+// RoIPool forward (inference) from per-bin lookup lists.
+//
+// roi_pool_tab_kernel decides per bin and per slab CTA which table and which corners to read (window levels, the
+// thin-bin cases of the two-table form, coinciding lookups, 5..8-long bins): ~130 warp instructions per 32 bins x 4
+// channels, of which 24 are the lookups, maxima and stores themselves (ncu, 64 x 64 map).  None of that depends on
+// the channel.  Here roi_pool_desc_kernel works it out ONCE per (RoI, bin) and writes the result as a list of up to
+// 16 table positions (16-bit offsets into [pixels | 2 x 2 windows | a zero pixel | a -FLT_MAX pixel]); the gather of
+// a slab only loads the list, takes the maximum of what it points at and stores.  A bin's first four positions
+// are read without a predicate (unused slots point at the -FLT_MAX pixel, an empty bin at the zero pixel), the
+// other twelve only by the lanes that have them, a bin needing more is scanned.  max is exact and commutative, so
+// the value is the same bit pattern whatever covers the bin.
+//   thin bin (1 x L or L x 1, L <= 16): its pixels;  otherwise 2-windows anchored at lo, lo + 2, ... and hi - 2 per
+//   axis (ceil(L / 2) of them): the product of the two axes' anchors, at most 16 (L <= 8 on both axes always fits).
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned PD_MASK = 0x7FFFu;
+
+struct PoolDescTab {
+    int HWp;   // table stride: pixels at 0, 2 x 2 windows at HWp, zero pixel at 2 * HWp, -FLT_MAX pixel at 2 * HWp + 1
+    int WP;
+};
+
+// windows of side s covering [lo, hi), hi - lo >= s: lo, lo + s, ... and hi - s for the remainder
+__device__ __forceinline__ int pd_anchors(int lo, int hi, int s, int* out) {
+    int n = 0;
+    for (int x = lo; x + s <= hi; x += s) out[n++] = x;
+    if ((hi - lo) % s) out[n++] = hi - s;
+    return n;
+}
+
+// smax = side of the largest window table the gather builds (2 or 3)
+__global__ void __launch_bounds__(256) roi_pool_desc_kernel(RoiArgs a, uint2* __restrict__ desc,
+                                                            uint2* __restrict__ extra, int P, int HWp, int smax) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int BINS = P * P;
+    if (idx >= a.K * BINS) return;
+    const int r = idx / BINS, e = idx - r * BINS, ph = e / P, pw = e - ph * P;
+    const float* rp = a.rois5 + (size_t)roi_at(a, r) * 5;
+    int hr, wr;
+    tab_entry<1>(ph, P, __ldg(rp + 2), __ldg(rp + 4), a.scale, a.H, 1, 0, 4, &hr);
+    tab_entry<1>(pw, P, __ldg(rp + 1), __ldg(rp + 3), a.scale, a.W, 1, 0, 4, &wr);
+    const int y0 = hr & 0xFFFF, y1 = hr >> 16, x0 = wr & 0xFFFF, x1 = wr >> 16, hh = y1 - y0, ww = x1 - x0;
+    const int WP = a.pitch;
+    const unsigned zero = (unsigned)(smax * HWp), none = zero + 1u;
+    unsigned o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = none;
+    int n = 0;
+    bool big = false;
+    if (hh <= 0 || ww <= 0) {
+        o[0] = zero;
+    } else {
+        // square windows of side s = min(smax, hh, ww) from table s - 1: a 3 x 3 bin is one lookup, 2 x 3 two, ...
+        const int s = min(smax, min(hh, ww));
+        const int nry = (hh + s - 1) / s, ncx = (ww + s - 1) / s;
+        if (nry * ncx <= 16) {
+            int ry[16], cx[16];
+            pd_anchors(y0, y1, s, ry);
+            pd_anchors(x0, x1, s, cx);
+            for (int i = 0; i < nry; ++i)
+                for (int j = 0; j < ncx; ++j) o[n++] = (s - 1) * HWp + ry[i] * WP + cx[j];
+        } else big = true;
+    }
+    desc[idx] = make_uint2(o[0] | (o[1] << 16) | (n > 4 ? 0x80000000u : 0u), o[2] | (o[3] << 16) | (big ? 0x80000000u : 0u));
+    if (n > 4) {
+        uint2* x = extra + (size_t)idx * 3;
+        x[0] = make_uint2(o[4] | (o[5] << 16), o[6] | (o[7] << 16));
+        x[1] = make_uint2(o[8] | (o[9] << 16), o[10] | (o[11] << 16));
+        x[2] = make_uint2(o[12] | (o[13] << 16), o[14] | (o[15] << 16));
+    }
+}
+
+// positions 5..16 of a bin's list (the lanes that have them): stops at the first unused slot
+__device__ __noinline__ float4 pool_desc_more(float4 v, uint32_t tab_s, const uint2* __restrict__ x, unsigned none) {
+    for (int q = 0; q < 3; ++q) {
+        const uint2 d = __ldg(x + q);
+        const unsigned o[4] = {d.x & 0xFFFFu, d.x >> 16, d.y & 0xFFFFu, d.y >> 16};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (o[i] == none) return v;
+            v = vmax(v, lds_f4<0>(tab_s + o[i] * 16u));
+        }
+    }
+    return v;
+}
+// a bin too large for a list: its ranges again from the RoI, every pixel read
+__device__ __noinline__ float4 pool_desc_scan(const float* __restrict__ rp, float scale, int HW16, int pitch,
+                                              uint32_t tab_s, int ph, int pw, int P) {
+    int hr, wr;
+    tab_entry<1>(ph, P, __ldg(rp + 2), __ldg(rp + 4), scale, HW16 >> 16, 1, 0, 4, &hr);
+    tab_entry<1>(pw, P, __ldg(rp + 1), __ldg(rp + 3), scale, HW16 & 0xFFFF, 1, 0, 4, &wr);
+    float4 v = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (int y = hr & 0xFFFF; y < (hr >> 16); ++y)
+        for (int x = wr & 0xFFFF; x < (wr >> 16); ++x) v = vmax(v, lds_f4<0>(tab_s + (uint32_t)(y * pitch + x) * 16u));
+    return v;
+}
+
+template <int P, int THREADS, int MINB, int NT>
+__global__ void __launch_bounds__(THREADS, MINB)
+roi_pool_gather_kernel(RoiArgs a, const uint2* __restrict__ desc, const uint2* __restrict__ extra) {
+    typedef float4 V;
+    constexpr int BINS = P * P;
+    static_assert(NT == 2 || NT == 3, "window tables: 1, 2 (, 3)");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const int H = a.H, W = a.W, HW = H * W, WP = a.pitch, HWp = (H * WP + 3) & ~3;
+    V* tab = reinterpret_cast<V*>(smem_raw);
+    const int tid = threadIdx.x, b = blockIdx.z, c0 = blockIdx.y * 4;
+    int r_begin, r_end;
+    roi_range(a, b, r_begin, r_end);
+    const int n_task = (r_end - r_begin) * BINS, step = a.groups * THREADS;
+    if ((int)blockIdx.x * THREADS >= n_task) return;
+    // planes staged where the last window table will be (dead once the pixels are interleaved)
+    float* raw = reinterpret_cast<float*>(tab + (NT - 1) * HWp);
+    stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, 4 * HW, &bar);
+    build_max_tables<V, 1, THREADS>(tab, raw, 4, H, W, WP, HWp, tid);  // pixels, clamped; ends with a CTA barrier
+    for (int p = tid; p < HW; p += THREADS) {
+        // windows anchored at (y, x), clamped at the map's edge (the lists never point at a clamped one)
+        const int y = p / W, x = p - y * W, q = y * WP + x;
+        const int d1 = x + 1 < W ? 1 : 0, d2 = x + 2 < W ? 2 : d1;
+        const int q1 = y + 1 < H ? q + WP : q, q2 = y + 2 < H ? q + 2 * WP : q1;
+        const V m2 = vmax(vmax(tab[q], tab[q + d1]), vmax(tab[q1], tab[q1 + d1]));
+        tab[HWp + q] = m2;
+        if (NT == 3) {
+            const V c = vmax(vmax(tab[q + d2], tab[q1 + d2]), vmax(tab[q2], tab[q2 + d1]));
+            tab[2 * HWp + q] = vmax(vmax(m2, c), tab[q2 + d2]);
+        }
+    }
+    if (tid == 0) {
+        tab[NT * HWp] = make_float4(0.f, 0.f, 0.f, 0.f);
+        tab[NT * HWp + 1] = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    }
+    __syncthreads();
+    uint32_t tab_s = smem_u32(tab);
+    asm volatile("mov.u32 %0, %0;" : "+r"(tab_s));
+    const unsigned none = (unsigned)(NT * HWp) + 1u;
+    const uint2 idle = make_uint2(none | (none << 16), none | (none << 16));
+    const uint2* const dbase = desc + (size_t)r_begin * BINS;
+    unsigned char* const obase = reinterpret_cast<unsigned char*>(a.out + (size_t)c0 * BINS);
+    const uint32_t kstride_b = (uint32_t)a.C * BINS * 4u;
+    int i = blockIdx.x * THREADS + tid;
+    uint2 d = i < n_task ? __ldg(dbase + i) : idle;
+#pragma unroll 1
+    for (int i0 = blockIdx.x * THREADS; i0 < n_task; i0 += step, i += step) {
+        const bool valid = i < n_task;
+        const uint2 dn = i + step < n_task ? __ldg(dbase + i + step) : idle;  // the next task's list
+        const V t0 = lds_f4<0>(tab_s + (d.x & PD_MASK) * 16u), t1 = lds_f4<0>(tab_s + ((d.x >> 16) & PD_MASK) * 16u);
+        V v = vmax(t0, t1);
+        if (__any_sync(0xFFFFFFFFu, (d.y & PD_MASK) != none)) {  // slots 3 and 4: only when some lane has a third position
+            const V t2 = lds_f4<0>(tab_s + (d.y & PD_MASK) * 16u), t3 = lds_f4<0>(tab_s + ((d.y >> 16) & PD_MASK) * 16u);
+            v = vmax(v, vmax(t2, t3));
+        }
+        const bool more = (int)d.x < 0, big = (int)d.y < 0;
+        const int rl = i / BINS, e = i - rl * BINS;
+        if (__any_sync(0xFFFFFFFFu, more)) {
+            if (more) v = pool_desc_more(v, tab_s, extra + ((size_t)r_begin * BINS + i) * 3, none);
+        }
+        const int k = valid ? roi_at(a, r_begin + rl) : 0;
+        if (__any_sync(0xFFFFFFFFu, big)) {
+            if (big) v = pool_desc_scan(a.rois5 + (size_t)k * 5, a.scale, (H << 16) | W, WP, tab_s, e / P, e % P, P);
+        }
+        if (valid) {
+            float* po = reinterpret_cast<float*>(obase + ((unsigned long long)(unsigned)k * kstride_b + (unsigned)(e * 4)));
+            po[0] = v.x, po[BINS] = v.y, po[2 * BINS] = v.z, po[3 * BINS] = v.w;
+        }
+        d = dn;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // RoIPool forward for training (value + argmax, 7x7 / 14x14): persistent CTAs over (image, 4-channel slab) items.
 //
@@ -1013,19 +1195,6 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
 // straight-line row body (scan_rows).  Same mapping as before: thread = one bin of one RoI (392 = 8 x 49 =
 // 2 x 196), consecutive lanes = consecutive bins, value and argmax stored in 128-byte runs.
 // ---------------------------------------------------------------------------------------------
-// Loads through 32-bit shared-window addresses kept in registers: with generic pointers into __shared__ arrays the
-// compiler re-derived the window base (S2R SR_CgaCtaId, MOV, LEA) in every iteration of the bin loop.
-__device__ __forceinline__ int lds_i32(uint32_t addr) {
-    int v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-template <int OFF>
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-    float4 v;
-    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF));
-    return v;
-}
 // scan_rows on a shared-window address (`row_bytes` = table pitch in bytes)
 template <int NW, bool LONG>
 __device__ __forceinline__ void scan_rows_s(float4& v, int4& idx, uint32_t addr, int p, int hh, int ww, int row_bytes,
@@ -2818,7 +2987,8 @@ static size_t roi_layout(Workspace& ws, int batch, int num_rois, RoiWs* out) {
     w.perm = ws.take<int>(num_rois > 0 ? num_rois : 1);
     w.offs = ws.take<int>(batch + 2);
     w.sorted = ws.take<int>(num_rois > 0 ? num_rois : 1);
-    w.ent = ws.take<int2>((size_t)(num_rois > 0 ? num_rois : 1) * 144);  // up to 1152 bytes per RoI (streaming RoIAlign)
+    // up to 1152 bytes per RoI for the streaming RoIAlign records, 1568 for the 7x7 RoIPool lookup lists
+    w.ent = ws.take<int2>((size_t)(num_rois > 0 ? num_rois : 1) * 200);
     // streaming RoIAlign, packed per-warp programs: one AS2_SLOT per 4 RoIs, passes of >= 24 RoIs, one ragged pass per image
     w.prog = ws.take<unsigned char>(((size_t)(num_rois > 0 ? num_rois : 1) / 24 + batch + 2) * 8 * AS2_SLOT);
     if (out) *out = w;
@@ -3244,6 +3414,63 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             else if (smem4 <= 200 * 1024) tcs = 4, minb = 1;
             else if (smem2 <= 200 * 1024) tcs = 2, minb = 1;
             a.pitch = pitch_for(tcs ? tcs : 4);
+            // 7x7: the gather driven by per-bin lookup lists, computed once per RoI for all slabs (roi_pool_gather_kernel).
+            // Window tables: pixels, 2 x 2 and -- when that does not cost a CTA per SM -- 3 x 3, with which a typical
+            // 2..3 pixel bin is one or two lookups instead of four (64 x 64 map, one CTA per SM either way: 0.562 vs
+            // 0.616 ms, table kernel 0.595; 50 x 50 map: two tables and two CTAs per SM 0.362 ms, three tables and one
+            // CTA 0.384, table kernel 0.383).
+            constexpr int FRCNN_LIST_NA = 1 << 20;
+            auto launch_list = [&](int pitch) -> int {
+                static const int pool_impl = env_int("FRCNN_POOL_IMPL", 0);  // experiments only: 1 = table kernel
+                const int HWp_d = (H * pitch + 3) & ~3;
+                if (!(PH == 7 && C % 4 == 0 && 2 * HWp_d + 2 <= (int)PD_MASK && pool_impl != 1 &&
+                      (int64_t)C * 49 * 4 < ((int64_t)1 << 32)))
+                    return FRCNN_LIST_NA;
+                static const int pool_tables = env_int("FRCNN_POOL_TABLES", 0);  // experiments only: force 2 / 3
+                const size_t smem2t = (size_t)2 * HWp_d * 16 + 32, smem3t = (size_t)3 * HWp_d * 16 + 32;
+                auto ctas_per_sm = [](size_t bytes) { return bytes + 2048 <= 113 * 1024 ? 2 : 1; };
+                if (smem2t > 220 * 1024) return FRCNN_LIST_NA;
+                bool three = smem3t <= 220 * 1024 && 3 * HWp_d + 2 <= (int)PD_MASK && ctas_per_sm(smem3t) == ctas_per_sm(smem2t);
+                if (pool_tables == 2) three = false;
+                if (pool_tables == 3 && smem3t <= 220 * 1024 && 3 * HWp_d + 2 <= (int)PD_MASK) three = true;
+                const size_t gsmem = three ? smem3t : smem2t;
+                const int per_sm = ctas_per_sm(gsmem);
+                Workspace ews(workspace, workspace_bytes);
+                RoiWs w;
+                roi_layout(ews, B, K, &w);
+                if (!ews.ok()) {
+                    set_error("%s: workspace too small or misaligned (%zu needed, %zu given)", who, ews.off, workspace_bytes);
+                    return FRCNN_ERR_WORKSPACE;
+                }
+                uint2* const desc = reinterpret_cast<uint2*>(w.ent);
+                uint2* const extra = desc + (size_t)K * 49;
+                a.pitch = pitch;
+                a.CS = 4;
+                const int slabs = C / 4, th = per_sm == 2 ? 512 : 1024;
+                FRCNN_CHECK_ARG(slabs <= 65535 && B <= 65535, "roi op: too many channel slabs / images");
+                // every CTA builds the slab's tables: split an image's RoIs over several only to reach ~4 waves
+                a.groups = std::max(1, std::min(cdiv(4 * per_sm * sm_count(), B * slabs), cdiv((int64_t)per_image_rois * 49, 8 * th)));
+                static const int groups_override = env_int("FRCNN_POOL_GROUPS", 0);  // experiments only
+                if (groups_override > 0) a.groups = groups_override;
+                roi_pool_desc_kernel<<<cdiv((int64_t)K * 49, 256), 256, 0, stream>>>(a, desc, extra, 7, HWp_d, three ? 3 : 2);
+                FRCNN_LAUNCH_CHECK();
+                const dim3 grid(a.groups, slabs, B);
+#define FRCNN_GATHER(TH_, MB_, NT_)                                                                      \
+    do {                                                                                                \
+        FRCNN_SMEM((roi_pool_gather_kernel<7, TH_, MB_, NT_>), gsmem);                                  \
+        roi_pool_gather_kernel<7, TH_, MB_, NT_><<<grid, TH_, gsmem, stream>>>(a, desc, extra);         \
+        FRCNN_LAUNCH_CHECK();                                                                           \
+        note_roi_kernel("roi_pool_gather_kernel<7,%d,%d,%d>", TH_, MB_, NT_);                           \
+        return FRCNN_OK;                                                                                \
+    } while (0)
+                if (three) {
+                    if (per_sm == 2) FRCNN_GATHER(512, 2, 3);
+                    FRCNN_GATHER(1024, 1, 3);
+                }
+                if (per_sm == 2) FRCNN_GATHER(512, 2, 2);
+                FRCNN_GATHER(1024, 1, 2);
+#undef FRCNN_GATHER
+            };
             // maps whose four 4-channel tables do not fit: two tables (pixels, 2 x 2 windows) with four
             // channels per lookup instead of four tables with two
             const int pitch_d = pitch_for(4);  // (a sweep over 65 ... 71 pixels on the 64-wide map moved the time by < 0.5 %)
@@ -3251,6 +3478,10 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             if (tcs == 2 && smemd + 40 * 1024 <= 220 * 1024) {
                 a.pitch = pitch_d;
                 const bool two = smemd <= budget2;
+                {
+                    const int rc_ = launch_list(pitch_d);
+                    if (rc_ != FRCNN_LIST_NA) return rc_;
+                }
 #define FRCNN_TABD(PP_, TH_, MB_)                                                                            \
     do {                                                                                                    \
         set_groups(4, TH_);                                                                                 \
@@ -3267,6 +3498,12 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
 #undef FRCNN_TABD
             }
             if (tcs == 4 && minb == 2) {
+                // maps small enough for the four-table kernel at two CTAs per SM take the list gather too (38 x 38 x 1024,
+                // 4 800 RoIs: 0.308 vs 0.336 ms)
+                if (PH == 7) {
+                    const int rc_ = launch_list(pitch_for(4));
+                    if (rc_ != FRCNN_LIST_NA) return rc_;
+                }
                 if (PH == 7) FRCNN_TAB(7, 392, 4, 2, false, 2);
                 set_groups(4, 392);  // 14x14: two adjacent bins per thread
                 return launch_tab(FRCNN_STR(roi_pool_tab_kernel<14, 392, 4, 2, false, 2, 2, true>), roi_pool_tab_kernel<14, 392, 4, 2, false, 2, 2, true>, a, table_bytes(2, 4, a.pitch), 392,
