@@ -912,6 +912,67 @@ def test_roi_pool_two_table_variants(F, O, shape):
                           O.roi_pool(feat, grouped, P, 1.0))
 
 
+@pytest.mark.parametrize("shape", [(2, 8, 38, 38, 7), (1, 12, 50, 50, 7), (1, 8, 64, 64, 7), (1, 4, 70, 80, 7),
+                                   (3, 4, 21, 33, 7)])
+def test_roi_pool_list_gather_kernel(F, O, shape):
+    """7x7 inference RoIPool with C % 4 == 0: the gather driven by per-bin lookup lists (roi_pool_gather_kernel).
+    RoI families chosen per list form: tiny (one pixel / one window), 2..3 pixel bins (one or two lookups),
+    5..12 pixel bins (positions 5..16 of the list), thin-and-long both ways (pixel lists), larger than the map and,
+    on the 70 x 80 map (two tables: 36 windows per bin), bins too large for a list (scanned), empty / inverted."""
+    from two_stage_object_detection_b200 import _lib
+    B, Cc, H, W, P = shape
+    rng = np.random.default_rng(H * 977 + W)
+    feat = rng.standard_normal((B, Cc, H, W)).astype(np.float32)
+    feat[0, 0, : H // 2] = np.round(feat[0, 0, : H // 2])  # ties
+    fam, n = [], 70
+    for (wlo, whi, hlo, hhi) in [(0.2, 3, 0.2, 3), (P * 2, P * 3.2, P * 2, P * 3.2), (P * 5, P * 12, P * 5, P * 12),
+                                 (0.5, 5, P * 2, H * 1.2), (P * 2, W * 1.2, 0.5, 5), (W * 0.9, W * 1.5, H * 0.9, H * 1.5),
+                                 (0, 0.3, 0, 0.3)]:
+        c = np.stack([rng.uniform(-3, W + 3, n), rng.uniform(-3, H + 3, n)], 1)
+        wh = np.stack([rng.uniform(wlo, whi, n), rng.uniform(hlo, hhi, n)], 1)
+        fam.append(np.concatenate([c - wh / 2, c + wh / 2], 1))
+    boxes = np.concatenate(fam)
+    boxes[5, [0, 2]] = boxes[5, [2, 0]]  # inverted
+    rois = np.concatenate([rng.integers(0, B, (len(boxes), 1)), boxes], 1).astype(np.float32)
+    rois = rois[rng.permutation(len(rois))]
+    for scale in (1.0, 0.5):
+        got = N(F.roi_pool_forward(T(feat), T(rois), P, scale))
+        assert _lib.last_roi_kernel().startswith("roi_pool_gather_kernel"), _lib.last_roi_kernel()
+        assert np.array_equal(got, O.roi_pool(feat, rois, P, scale)), (shape, scale)
+    order = np.argsort(rois[:, 0], kind="stable")
+    per = int(np.bincount(rois[:, 0].astype(int), minlength=B).min())
+    grouped = np.concatenate([rois[order][rois[order][:, 0] == b][:per] for b in range(B)])
+    assert np.array_equal(N(F.roi_pool_forward(T(feat), T(grouped), P, 1.0, rois_per_image=per)),
+                          O.roi_pool(feat, grouped, P, 1.0)), shape
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 38, 38, 7, 300), (1, 6, 37, 41, 7, 150), (2, 4, 50, 50, 14, 40),
+                                   (1, 5, 64, 64, 7, 129), (3, 12, 16, 20, 7, 7)])
+def test_roi_pool_training_kernel(F, O, shape):
+    """value + argmax (roi_pool_train_kernel): more RoIs per image than one resident chunk of ranges (128), channel
+    tails, planes whose size is not a multiple of 16 bytes (plain loads instead of bulk copies), more (image, slab)
+    items than resident CTAs would take in one go, ungrouped and grouped RoI lists, ties (first index wins)."""
+    from two_stage_object_detection_b200 import _lib
+    B, Cc, H, W, P, per = shape
+    rng = np.random.default_rng(H * 31 + W + per)
+    feat = np.round(rng.standard_normal((B, Cc, H, W)) * 2).astype(np.float32) / 2  # many ties
+    K = B * per
+    c = np.stack([rng.uniform(-3, W + 3, K), rng.uniform(-3, H + 3, K)], 1)
+    wh = np.concatenate([rng.uniform(0.3, 9, (K // 3, 2)), rng.uniform(P, 4 * P, (K // 3, 2)),
+                         rng.uniform(W * 0.5, W * 1.3, (K - 2 * (K // 3), 2))])
+    grouped = np.concatenate([np.repeat(np.arange(B), per)[:, None], c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    out, am = F.roi_pool_forward(T(feat), T(grouped), P, 1.0, with_argmax=True, rois_per_image=per)
+    assert _lib.last_roi_kernel().startswith("roi_pool_train_kernel"), _lib.last_roi_kernel()
+    ro, ra = O.roi_pool(feat, grouped, P, 1.0, return_argmax=True)
+    assert np.array_equal(N(out), ro) and np.array_equal(N(am), ra), shape
+    shuffled = grouped[rng.permutation(K)]
+    shuffled[0, 0] = B + 3  # belongs to no image: zeros, argmax -1
+    out, am = F.roi_pool_forward(T(feat), T(shuffled), P, 0.5, with_argmax=True)
+    ro, ra = O.roi_pool(feat, shuffled[1:], P, 0.5, return_argmax=True)
+    assert np.array_equal(N(out)[1:], ro) and np.array_equal(N(am)[1:], ra), shape
+    assert not N(out)[0].any() and (N(am)[0] == -1).all()
+
+
 def test_nan_and_inf_features_in_roi_pool(F, O):
     """The reference's `v > best` scan never selects NaN / -inf; all-NaN bins give -FLT_MAX."""
     rng = np.random.default_rng(3)
