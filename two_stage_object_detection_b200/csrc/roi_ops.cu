@@ -1034,13 +1034,8 @@ struct PoolDescTab {
     int WP;
 };
 
-// windows of side s covering [lo, hi), hi - lo >= s: lo, lo + s, ... and hi - s for the remainder
-__device__ __forceinline__ int pd_anchors(int lo, int hi, int s, int* out) {
-    int n = 0;
-    for (int x = lo; x + s <= hi; x += s) out[n++] = x;
-    if ((hi - lo) % s) out[n++] = hi - s;
-    return n;
-}
+// k-th window of side s covering [lo, hi), hi - lo >= s: lo, lo + s, ... and hi - s for the remainder
+__device__ __forceinline__ int pd_anchor(int lo, int hi, int s, int full, int k) { return k < full ? lo + k * s : hi - s; }
 
 // smax = side of the largest window table the gather builds (2 or 3)
 __global__ void __launch_bounds__(256) roi_pool_desc_kernel(RoiArgs a, uint2* __restrict__ desc,
@@ -1056,27 +1051,25 @@ __global__ void __launch_bounds__(256) roi_pool_desc_kernel(RoiArgs a, uint2* __
     const int y0 = hr & 0xFFFF, y1 = hr >> 16, x0 = wr & 0xFFFF, x1 = wr >> 16, hh = y1 - y0, ww = x1 - x0;
     const int WP = a.pitch;
     const unsigned zero = (unsigned)(smax * HWp), none = zero + 1u;
-    unsigned o[16];
+    // square windows of side s = min(smax, hh, ww) from table s - 1: a 3 x 3 bin is one lookup, 2 x 3 two, ...
+    const bool empty = hh <= 0 || ww <= 0;
+    const int s = empty ? 1 : min(smax, min(hh, ww));
+    const int fy = hh / s, fx = ww / s, nry = (hh + s - 1) / s, ncx = (ww + s - 1) / s;
+    const int n = empty ? 0 : nry * ncx;
+    const bool big = n > 16;
+    const int base = (s - 1) * HWp;
+    unsigned o[16];  // static indices only: registers
+    int i = 0, j = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) o[i] = none;
-    int n = 0;
-    bool big = false;
-    if (hh <= 0 || ww <= 0) {
-        o[0] = zero;
-    } else {
-        // square windows of side s = min(smax, hh, ww) from table s - 1: a 3 x 3 bin is one lookup, 2 x 3 two, ...
-        const int s = min(smax, min(hh, ww));
-        const int nry = (hh + s - 1) / s, ncx = (ww + s - 1) / s;
-        if (nry * ncx <= 16) {
-            int ry[16], cx[16];
-            pd_anchors(y0, y1, s, ry);
-            pd_anchors(x0, x1, s, cx);
-            for (int i = 0; i < nry; ++i)
-                for (int j = 0; j < ncx; ++j) o[n++] = (s - 1) * HWp + ry[i] * WP + cx[j];
-        } else big = true;
+    for (int t = 0; t < 16; ++t) {
+        o[t] = (t < n && !big) ? (unsigned)(base + pd_anchor(y0, y1, s, fy, i) * WP + pd_anchor(x0, x1, s, fx, j)) : none;
+        if (++j == ncx) j = 0, ++i;
+        if (t == 3 && n <= 4) break;  // (the other twelve are only stored for longer lists)
     }
-    desc[idx] = make_uint2(o[0] | (o[1] << 16) | (n > 4 ? 0x80000000u : 0u), o[2] | (o[3] << 16) | (big ? 0x80000000u : 0u));
-    if (n > 4) {
+    if (empty) o[0] = zero;
+    const bool more = n > 4 && !big;
+    desc[idx] = make_uint2(o[0] | (o[1] << 16) | (more ? 0x80000000u : 0u), o[2] | (o[3] << 16) | (big ? 0x80000000u : 0u));
+    if (more) {
         uint2* x = extra + (size_t)idx * 3;
         x[0] = make_uint2(o[4] | (o[5] << 16), o[6] | (o[7] << 16));
         x[1] = make_uint2(o[8] | (o[9] << 16), o[10] | (o[11] << 16));
