@@ -23,3 +23,10 @@ b.record(); torch.cuda.synchronize()
 t = a.elapsed_time(b) / 30
 alg = K * C * 49 * 4 + K * 20 + B * C * H * W * 4
 print(f"{name} map {H}x{W} C={C} K={K}: {_lib.last_roi_kernel()}  {t:.4f} ms  {alg / t / 1e6 / 6552.6:.3f} of peak")
+fn = lambda: F.roi_pool_mean(feat, rois5, 7, 1.0, rois_per_image=cfg["n_post"])
+for _ in range(5): fn()
+torch.cuda.synchronize()
+a.record()
+for _ in range(30): fn()
+b.record(); torch.cuda.synchronize()
+print(f"{name} fused pool + mean: {_lib.last_roi_kernel()}  {a.elapsed_time(b) / 30:.4f} ms")

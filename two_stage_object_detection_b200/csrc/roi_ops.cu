@@ -1102,24 +1102,15 @@ __device__ __noinline__ float4 pool_desc_scan(const float* __restrict__ rp, floa
     return v;
 }
 
-template <int P, int THREADS, int MINB, int NT>
-__global__ void __launch_bounds__(THREADS, MINB)
-roi_pool_gather_kernel(RoiArgs a, const uint2* __restrict__ desc, const uint2* __restrict__ extra) {
+// the slab's window tables: pixels (clamped), 2 x 2 (, 3 x 3) windows, the zero pixel and the -FLT_MAX pixel
+template <int THREADS, int NT>
+__device__ __forceinline__ void pool_list_tables(const RoiArgs& a, float4* tab, int b, int c0, uint64_t* bar) {
     typedef float4 V;
-    constexpr int BINS = P * P;
-    static_assert(NT == 2 || NT == 3, "window tables: 1, 2 (, 3)");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
     const int H = a.H, W = a.W, HW = H * W, WP = a.pitch, HWp = (H * WP + 3) & ~3;
-    V* tab = reinterpret_cast<V*>(smem_raw);
-    const int tid = threadIdx.x, b = blockIdx.z, c0 = blockIdx.y * 4;
-    int r_begin, r_end;
-    roi_range(a, b, r_begin, r_end);
-    const int n_task = (r_end - r_begin) * BINS, step = a.groups * THREADS;
-    if ((int)blockIdx.x * THREADS >= n_task) return;
+    const int tid = threadIdx.x;
     // planes staged where the last window table will be (dead once the pixels are interleaved)
     float* raw = reinterpret_cast<float*>(tab + (NT - 1) * HWp);
-    stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, 4 * HW, &bar);
+    stage_slab(raw, a.feat + ((size_t)b * a.C + c0) * HW, 4 * HW, bar);
     build_max_tables<V, 1, THREADS>(tab, raw, 4, H, W, WP, HWp, tid);  // pixels, clamped; ends with a CTA barrier
     for (int p = tid; p < HW; p += THREADS) {
         // windows anchored at (y, x), clamped at the map's edge (the lists never point at a clamped one)
@@ -1138,6 +1129,44 @@ roi_pool_gather_kernel(RoiArgs a, const uint2* __restrict__ desc, const uint2* _
         tab[NT * HWp + 1] = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
     }
     __syncthreads();
+}
+
+// maximum over one bin's list (called by whole warps: the votes skip what no lane needs)
+__device__ __forceinline__ float4 pool_list_max(const uint2& d, uint32_t tab_s, unsigned none, const uint2* __restrict__ xtra,
+                                                const float* __restrict__ roi, float scale, int HW16, int WP, int e, int P) {
+    typedef float4 V;
+    const V t0 = lds_f4<0>(tab_s + (d.x & PD_MASK) * 16u), t1 = lds_f4<0>(tab_s + ((d.x >> 16) & PD_MASK) * 16u);
+    V v = vmax(t0, t1);
+    if (__any_sync(0xFFFFFFFFu, (d.y & PD_MASK) != none)) {  // slots 3 and 4: only when some lane has a third position
+        const V t2 = lds_f4<0>(tab_s + (d.y & PD_MASK) * 16u), t3 = lds_f4<0>(tab_s + ((d.y >> 16) & PD_MASK) * 16u);
+        v = vmax(v, vmax(t2, t3));
+    }
+    const bool more = (int)d.x < 0, big = (int)d.y < 0;
+    if (__any_sync(0xFFFFFFFFu, more)) {
+        if (more) v = pool_desc_more(v, tab_s, xtra, none);
+    }
+    if (__any_sync(0xFFFFFFFFu, big)) {
+        if (big) v = pool_desc_scan(roi, scale, HW16, WP, tab_s, e / P, e % P, P);
+    }
+    return v;
+}
+
+template <int P, int THREADS, int MINB, int NT>
+__global__ void __launch_bounds__(THREADS, MINB)
+roi_pool_gather_kernel(RoiArgs a, const uint2* __restrict__ desc, const uint2* __restrict__ extra) {
+    typedef float4 V;
+    constexpr int BINS = P * P;
+    static_assert(NT == 2 || NT == 3, "window tables: 1, 2 (, 3)");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const int H = a.H, W = a.W, WP = a.pitch, HWp = (H * WP + 3) & ~3;
+    V* tab = reinterpret_cast<V*>(smem_raw);
+    const int tid = threadIdx.x, b = blockIdx.z, c0 = blockIdx.y * 4;
+    int r_begin, r_end;
+    roi_range(a, b, r_begin, r_end);
+    const int n_task = (r_end - r_begin) * BINS, step = a.groups * THREADS;
+    if ((int)blockIdx.x * THREADS >= n_task) return;
+    pool_list_tables<THREADS, NT>(a, tab, b, c0, &bar);
     uint32_t tab_s = smem_u32(tab);
     asm volatile("mov.u32 %0, %0;" : "+r"(tab_s));
     const unsigned none = (unsigned)(NT * HWp) + 1u;
@@ -1151,26 +1180,69 @@ roi_pool_gather_kernel(RoiArgs a, const uint2* __restrict__ desc, const uint2* _
     for (int i0 = blockIdx.x * THREADS; i0 < n_task; i0 += step, i += step) {
         const bool valid = i < n_task;
         const uint2 dn = i + step < n_task ? __ldg(dbase + i + step) : idle;  // the next task's list
-        const V t0 = lds_f4<0>(tab_s + (d.x & PD_MASK) * 16u), t1 = lds_f4<0>(tab_s + ((d.x >> 16) & PD_MASK) * 16u);
-        V v = vmax(t0, t1);
-        if (__any_sync(0xFFFFFFFFu, (d.y & PD_MASK) != none)) {  // slots 3 and 4: only when some lane has a third position
-            const V t2 = lds_f4<0>(tab_s + (d.y & PD_MASK) * 16u), t3 = lds_f4<0>(tab_s + ((d.y >> 16) & PD_MASK) * 16u);
-            v = vmax(v, vmax(t2, t3));
-        }
-        const bool more = (int)d.x < 0, big = (int)d.y < 0;
         const int rl = i / BINS, e = i - rl * BINS;
-        if (__any_sync(0xFFFFFFFFu, more)) {
-            if (more) v = pool_desc_more(v, tab_s, extra + ((size_t)r_begin * BINS + i) * 3, none);
-        }
         const int k = valid ? roi_at(a, r_begin + rl) : 0;
-        if (__any_sync(0xFFFFFFFFu, big)) {
-            if (big) v = pool_desc_scan(a.rois5 + (size_t)k * 5, a.scale, (H << 16) | W, WP, tab_s, e / P, e % P, P);
-        }
+        const V v = pool_list_max(d, tab_s, none, extra + ((size_t)r_begin * BINS + i) * 3, a.rois5 + (size_t)k * 5, a.scale,
+                                  (H << 16) | W, WP, e, P);
         if (valid) {
             float* po = reinterpret_cast<float*>(obase + ((unsigned long long)(unsigned)k * kstride_b + (unsigned)(e * 4)));
             po[0] = v.x, po[BINS] = v.y, po[2 * BINS] = v.z, po[3 * BINS] = v.w;
         }
         d = dn;
+    }
+}
+
+// RoIPool + the head's global average from the same lists: [K,C] instead of [K,C,P,P].  A warp owns a RoI: lane l
+// takes bins l and l + 32, the 49 bin maxima are added in a fixed order (own two bins, then an xor tree), so the
+// result does not depend on how the RoIs are grouped and is run-to-run identical; it agrees with pool().mean() to
+// fp32 rounding, not bit for bit.
+template <int P, int THREADS, int MINB, int NT>
+__global__ void __launch_bounds__(THREADS, MINB)
+roi_pool_mean_list_kernel(RoiArgs a, const uint2* __restrict__ desc, const uint2* __restrict__ extra) {
+    typedef float4 V;
+    constexpr int BINS = P * P, WARPS = THREADS / 32;
+    static_assert(BINS > 32 && BINS <= 64, "two bins per lane");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const int H = a.H, W = a.W, WP = a.pitch, HWp = (H * WP + 3) & ~3;
+    V* tab = reinterpret_cast<V*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, b = blockIdx.z, c0 = blockIdx.y * 4;
+    int r_begin, r_end;
+    roi_range(a, b, r_begin, r_end);
+    const int n_roi = r_end - r_begin, step = a.groups * WARPS;
+    if ((int)blockIdx.x * WARPS >= n_roi) return;
+    pool_list_tables<THREADS, NT>(a, tab, b, c0, &bar);
+    uint32_t tab_s = smem_u32(tab);
+    asm volatile("mov.u32 %0, %0;" : "+r"(tab_s));
+    const unsigned none = (unsigned)(NT * HWp) + 1u;
+    const uint2 idle = make_uint2(none | (none << 16), none | (none << 16));
+    const bool second = lane + 32 < BINS;
+    int rl = blockIdx.x * WARPS + (tid >> 5);
+    auto list = [&](int r, int e, bool on) {
+        return on && r < n_roi ? __ldg(desc + (size_t)(r_begin + r) * BINS + e) : idle;
+    };
+    uint2 d0 = list(rl, lane, true), d1 = list(rl, lane + 32, second);
+#pragma unroll 1
+    for (; rl < n_roi; rl += step) {
+        const uint2 n0 = list(rl + step, lane, true), n1 = list(rl + step, lane + 32, second);  // the next RoI's lists
+        const int k = roi_at(a, r_begin + rl);
+        const float* roi = a.rois5 + (size_t)k * 5;
+        const uint2* x = extra + ((size_t)(r_begin + rl) * BINS + lane) * 3;
+        V s = pool_list_max(d0, tab_s, none, x, roi, a.scale, (H << 16) | W, WP, lane, P);
+        const V v1 = pool_list_max(d1, tab_s, none, x + 32 * 3, roi, a.scale, (H << 16) | W, WP, second ? lane + 32 : 0, P);
+        if (second) s.x += v1.x, s.y += v1.y, s.z += v1.z, s.w += v1.w;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            s.x += __shfl_xor_sync(0xFFFFFFFFu, s.x, m);
+            s.y += __shfl_xor_sync(0xFFFFFFFFu, s.y, m);
+            s.z += __shfl_xor_sync(0xFFFFFFFFu, s.z, m);
+            s.w += __shfl_xor_sync(0xFFFFFFFFu, s.w, m);
+        }
+        if (lane == 0) {
+            float* o = a.out + (size_t)k * a.C + c0;
+            o[0] = s.x / (float)BINS, o[1] = s.y / (float)BINS, o[2] = s.z / (float)BINS, o[3] = s.w / (float)BINS;
+        }
+        d0 = n0, d1 = n1;
     }
 }
 
@@ -3320,6 +3392,91 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
         // rows whose byte length is a multiple of 64 would put vertically adjacent bins on the same banks
         // (64-wide maps: 45 % of the shared-memory wavefronts were conflicts): pad the pitch by one pixel
         auto pitch_for = [&](int tcs) { return (W * 4 * tcs) % 64 == 0 ? W + 1 : W; };
+        // 7x7: the gather driven by per-bin lookup lists, computed once per RoI for all slabs (roi_pool_gather_kernel).
+        // Window tables: pixels, 2 x 2 and -- when that does not cost a CTA per SM -- 3 x 3, with which a typical
+        // 2..3 pixel bin is one or two lookups instead of four (64 x 64 map, one CTA per SM either way: 0.562 vs
+        // 0.616 ms, table kernel 0.595; 50 x 50 map: two tables and two CTAs per SM 0.362 ms, three tables and one
+        // CTA 0.384, table kernel 0.383).
+        constexpr int FRCNN_LIST_NA = 1 << 20;
+        auto launch_list = [&](int pitch, bool mean_out) -> int {
+            static const int pool_impl = env_int("FRCNN_POOL_IMPL", 0);  // experiments only: 1 = table kernel
+            const int HWp_d = (H * pitch + 3) & ~3;
+            if (!(PH == 7 && C % 4 == 0 && 2 * HWp_d + 2 <= (int)PD_MASK && pool_impl != 1 &&
+                  (int64_t)C * 49 * 4 < ((int64_t)1 << 32)))
+                return FRCNN_LIST_NA;
+            static const int pool_tables = env_int("FRCNN_POOL_TABLES", 0);  // experiments only: force 2 / 3
+            const size_t smem2t = (size_t)2 * HWp_d * 16 + 32, smem3t = (size_t)3 * HWp_d * 16 + 32;
+            auto ctas_per_sm = [](size_t bytes) { return bytes + 2048 <= 113 * 1024 ? 2 : 1; };
+            if (smem2t > 220 * 1024) return FRCNN_LIST_NA;
+            bool three = smem3t <= 220 * 1024 && 3 * HWp_d + 2 <= (int)PD_MASK && ctas_per_sm(smem3t) == ctas_per_sm(smem2t);
+            if (pool_tables == 2) three = false;
+            if (pool_tables == 3 && smem3t <= 220 * 1024 && 3 * HWp_d + 2 <= (int)PD_MASK) three = true;
+            const size_t gsmem = three ? smem3t : smem2t;
+            const int per_sm = ctas_per_sm(gsmem);
+            // fused pool + mean: a warp per RoI leaves 15 of 64 lane slots idle, which only pays where the table kernel is
+            // down to one CTA per SM (64 x 64: 0.573 vs 0.641 ms; 50 x 50: 0.409 vs 0.404; 38 x 38: 0.375 vs 0.280)
+            if (mean_out && per_sm == 2) return FRCNN_LIST_NA;
+            Workspace ews(workspace, workspace_bytes);
+            RoiWs w;
+            roi_layout(ews, B, K, &w);
+            if (!ews.ok()) {
+                set_error("%s: workspace too small or misaligned (%zu needed, %zu given)", who, ews.off, workspace_bytes);
+                return FRCNN_ERR_WORKSPACE;
+            }
+            uint2* const desc = reinterpret_cast<uint2*>(w.ent);
+            uint2* const extra = desc + (size_t)K * 49;
+            a.pitch = pitch;
+            a.CS = 4;
+            const int slabs = C / 4, th = per_sm == 2 ? 512 : 1024;
+            FRCNN_CHECK_ARG(slabs <= 65535 && B <= 65535, "roi op: too many channel slabs / images");
+            // every CTA builds the slab's tables: split an image's RoIs over several only to reach ~4 waves
+            a.groups = std::max(1, std::min(cdiv(4 * per_sm * sm_count(), B * slabs),
+                                            mean_out ? cdiv(per_image_rois, 4 * (th / 32)) : cdiv((int64_t)per_image_rois * 49, 8 * th)));
+            static const int groups_override = env_int("FRCNN_POOL_GROUPS", 0);  // experiments only
+            if (groups_override > 0) a.groups = groups_override;
+            roi_pool_desc_kernel<<<cdiv((int64_t)K * 49, 256), 256, 0, stream>>>(a, desc, extra, 7, HWp_d, three ? 3 : 2);
+            FRCNN_LAUNCH_CHECK();
+            const dim3 grid(a.groups, slabs, B);
+#define FRCNN_GATHER(TH_, MB_, NT_)                                                                      \
+do {                                                                                                \
+    FRCNN_SMEM((roi_pool_gather_kernel<7, TH_, MB_, NT_>), gsmem);                                  \
+    roi_pool_gather_kernel<7, TH_, MB_, NT_><<<grid, TH_, gsmem, stream>>>(a, desc, extra);         \
+    FRCNN_LAUNCH_CHECK();                                                                           \
+    note_roi_kernel("roi_pool_gather_kernel<7,%d,%d,%d>", TH_, MB_, NT_);                           \
+    return FRCNN_OK;                                                                                \
+} while (0)
+#define FRCNN_MEANL(TH_, MB_, NT_)                                                                       \
+do {                                                                                                \
+    FRCNN_SMEM((roi_pool_mean_list_kernel<7, TH_, MB_, NT_>), gsmem);                               \
+    roi_pool_mean_list_kernel<7, TH_, MB_, NT_><<<grid, TH_, gsmem, stream>>>(a, desc, extra);      \
+    FRCNN_LAUNCH_CHECK();                                                                           \
+    note_roi_kernel("roi_pool_mean_list_kernel<7,%d,%d,%d>", TH_, MB_, NT_);                        \
+    return FRCNN_OK;                                                                                \
+} while (0)
+            if (mean_out) {
+                if (three) {
+                    if (per_sm == 2) FRCNN_MEANL(512, 2, 3);
+                    FRCNN_MEANL(1024, 1, 3);
+                }
+                if (per_sm == 2) FRCNN_MEANL(512, 2, 2);
+                FRCNN_MEANL(1024, 1, 2);
+            }
+            if (three) {
+                if (per_sm == 2) FRCNN_GATHER(512, 2, 3);
+                FRCNN_GATHER(1024, 1, 3);
+            }
+            if (per_sm == 2) FRCNN_GATHER(512, 2, 2);
+            FRCNN_GATHER(1024, 1, 2);
+#undef FRCNN_GATHER
+#undef FRCNN_MEANL
+        };
+        if (mean && !argmax) {
+            static const int mean_impl = env_int("FRCNN_MEAN_IMPL", 0);  // experiments only: 1 = table kernel
+            if (mean_impl != 1) {
+                const int rc_ = launch_list(pitch_for(4), true);
+                if (rc_ != FRCNN_LIST_NA) return rc_;
+            }
+        }
         if (mean) {  // [K,C] = mean over the bins of RoIPool, never materialising [K,C,P,P]
             // four 4-channel tables when they fit, else two (pixels, 2 x 2 windows: same bytes as four 2-channel
             // tables, twice the channels per lookup); one CTA per SM when the tables are that large -> 1024 threads
@@ -3407,63 +3564,6 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
             else if (smem4 <= 200 * 1024) tcs = 4, minb = 1;
             else if (smem2 <= 200 * 1024) tcs = 2, minb = 1;
             a.pitch = pitch_for(tcs ? tcs : 4);
-            // 7x7: the gather driven by per-bin lookup lists, computed once per RoI for all slabs (roi_pool_gather_kernel).
-            // Window tables: pixels, 2 x 2 and -- when that does not cost a CTA per SM -- 3 x 3, with which a typical
-            // 2..3 pixel bin is one or two lookups instead of four (64 x 64 map, one CTA per SM either way: 0.562 vs
-            // 0.616 ms, table kernel 0.595; 50 x 50 map: two tables and two CTAs per SM 0.362 ms, three tables and one
-            // CTA 0.384, table kernel 0.383).
-            constexpr int FRCNN_LIST_NA = 1 << 20;
-            auto launch_list = [&](int pitch) -> int {
-                static const int pool_impl = env_int("FRCNN_POOL_IMPL", 0);  // experiments only: 1 = table kernel
-                const int HWp_d = (H * pitch + 3) & ~3;
-                if (!(PH == 7 && C % 4 == 0 && 2 * HWp_d + 2 <= (int)PD_MASK && pool_impl != 1 &&
-                      (int64_t)C * 49 * 4 < ((int64_t)1 << 32)))
-                    return FRCNN_LIST_NA;
-                static const int pool_tables = env_int("FRCNN_POOL_TABLES", 0);  // experiments only: force 2 / 3
-                const size_t smem2t = (size_t)2 * HWp_d * 16 + 32, smem3t = (size_t)3 * HWp_d * 16 + 32;
-                auto ctas_per_sm = [](size_t bytes) { return bytes + 2048 <= 113 * 1024 ? 2 : 1; };
-                if (smem2t > 220 * 1024) return FRCNN_LIST_NA;
-                bool three = smem3t <= 220 * 1024 && 3 * HWp_d + 2 <= (int)PD_MASK && ctas_per_sm(smem3t) == ctas_per_sm(smem2t);
-                if (pool_tables == 2) three = false;
-                if (pool_tables == 3 && smem3t <= 220 * 1024 && 3 * HWp_d + 2 <= (int)PD_MASK) three = true;
-                const size_t gsmem = three ? smem3t : smem2t;
-                const int per_sm = ctas_per_sm(gsmem);
-                Workspace ews(workspace, workspace_bytes);
-                RoiWs w;
-                roi_layout(ews, B, K, &w);
-                if (!ews.ok()) {
-                    set_error("%s: workspace too small or misaligned (%zu needed, %zu given)", who, ews.off, workspace_bytes);
-                    return FRCNN_ERR_WORKSPACE;
-                }
-                uint2* const desc = reinterpret_cast<uint2*>(w.ent);
-                uint2* const extra = desc + (size_t)K * 49;
-                a.pitch = pitch;
-                a.CS = 4;
-                const int slabs = C / 4, th = per_sm == 2 ? 512 : 1024;
-                FRCNN_CHECK_ARG(slabs <= 65535 && B <= 65535, "roi op: too many channel slabs / images");
-                // every CTA builds the slab's tables: split an image's RoIs over several only to reach ~4 waves
-                a.groups = std::max(1, std::min(cdiv(4 * per_sm * sm_count(), B * slabs), cdiv((int64_t)per_image_rois * 49, 8 * th)));
-                static const int groups_override = env_int("FRCNN_POOL_GROUPS", 0);  // experiments only
-                if (groups_override > 0) a.groups = groups_override;
-                roi_pool_desc_kernel<<<cdiv((int64_t)K * 49, 256), 256, 0, stream>>>(a, desc, extra, 7, HWp_d, three ? 3 : 2);
-                FRCNN_LAUNCH_CHECK();
-                const dim3 grid(a.groups, slabs, B);
-#define FRCNN_GATHER(TH_, MB_, NT_)                                                                      \
-    do {                                                                                                \
-        FRCNN_SMEM((roi_pool_gather_kernel<7, TH_, MB_, NT_>), gsmem);                                  \
-        roi_pool_gather_kernel<7, TH_, MB_, NT_><<<grid, TH_, gsmem, stream>>>(a, desc, extra);         \
-        FRCNN_LAUNCH_CHECK();                                                                           \
-        note_roi_kernel("roi_pool_gather_kernel<7,%d,%d,%d>", TH_, MB_, NT_);                           \
-        return FRCNN_OK;                                                                                \
-    } while (0)
-                if (three) {
-                    if (per_sm == 2) FRCNN_GATHER(512, 2, 3);
-                    FRCNN_GATHER(1024, 1, 3);
-                }
-                if (per_sm == 2) FRCNN_GATHER(512, 2, 2);
-                FRCNN_GATHER(1024, 1, 2);
-#undef FRCNN_GATHER
-            };
             // maps whose four 4-channel tables do not fit: two tables (pixels, 2 x 2 windows) with four
             // channels per lookup instead of four tables with two
             const int pitch_d = pitch_for(4);  // (a sweep over 65 ... 71 pixels on the 64-wide map moved the time by < 0.5 %)
@@ -3472,7 +3572,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
                 a.pitch = pitch_d;
                 const bool two = smemd <= budget2;
                 {
-                    const int rc_ = launch_list(pitch_d);
+                    const int rc_ = launch_list(pitch_d, false);
                     if (rc_ != FRCNN_LIST_NA) return rc_;
                 }
 #define FRCNN_TABD(PP_, TH_, MB_)                                                                            \
@@ -3494,7 +3594,7 @@ static int roi_forward_common(bool align, const float* feat, int B, int C, int H
                 // maps small enough for the four-table kernel at two CTAs per SM take the list gather too (38 x 38 x 1024,
                 // 4 800 RoIs: 0.308 vs 0.336 ms)
                 if (PH == 7) {
-                    const int rc_ = launch_list(pitch_for(4));
+                    const int rc_ = launch_list(pitch_for(4), false);
                     if (rc_ != FRCNN_LIST_NA) return rc_;
                 }
                 if (PH == 7) FRCNN_TAB(7, 392, 4, 2, false, 2);
