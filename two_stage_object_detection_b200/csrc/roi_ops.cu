@@ -504,14 +504,6 @@ __device__ __forceinline__ void scan_first_max(float2& v, int2& idx, const float
 __device__ __forceinline__ void scan_first_max(float& v, int& idx, float t, int p) {
     if (t > v) v = t, idx = p;
 }
-#ifndef FRCNN_TRAIN_VARIANTS
-#define FRCNN_TRAIN_VARIANTS 7
-#endif
-#ifndef FRCNN_TRAIN_ROW_UNROLL
-#define FRCNN_TRAIN_ROW_UNROLL 1
-#endif
-#define FRCNN_PRAGMA_(x) _Pragma(#x)
-#define FRCNN_UNROLL(n) FRCNN_PRAGMA_(unroll n)
 // The same update under a per-lane predicate (a pixel column the bin may not have): the predicate joins the compare
 // (FSETP.GT.AND), so a column costs the same three instructions per channel whether it exists or not and the row
 // body stays straight-line.
@@ -538,20 +530,15 @@ __device__ __forceinline__ void scan_first_max_if(float& v, int& idx, float t, i
 // each row in a loop.
 template <int NW, bool LONG, typename V, typename I>
 __device__ __forceinline__ void scan_rows(V& v, I& idx, const V* rp, int p, int hh, int ww, int WP, int W) {
-    const bool w1 = ww > 0, w2 = ww > 1, w3 = ww > 2, w4 = ww > 3, w5 = ww > 4, w6 = ww > 5;
-#ifdef FRCNN_TRAIN_ROW_UNROLL
-    FRCNN_UNROLL(FRCNN_TRAIN_ROW_UNROLL)
-#endif
+    const bool w1 = ww > 0, w2 = ww > 1, w3 = ww > 2, w4 = ww > 3;
+#pragma unroll 1
     for (int y = 0; y < hh; ++y, rp += WP, p += W) {
         // all loads first
-        const V t0 = rp[0], t1 = rp[NW > 1 ? 1 : 0], t2 = rp[NW > 2 ? 2 : 0], t3 = rp[NW > 3 ? 3 : 0];
-        const V t4 = rp[NW > 4 ? 4 : 0], t5 = rp[NW > 5 ? 5 : 0];
+        const V t0 = rp[0], t1 = rp[1], t2 = rp[NW > 2 ? 2 : 0], t3 = rp[NW > 3 ? 3 : 0];
         scan_first_max_if(v, idx, t0, p, w1);
-        if (NW > 1) scan_first_max_if(v, idx, t1, p + 1, w2);
+        scan_first_max_if(v, idx, t1, p + 1, w2);
         if (NW > 2) scan_first_max_if(v, idx, t2, p + 2, w3);
         if (NW > 3) scan_first_max_if(v, idx, t3, p + 3, w4);
-        if (NW > 4) scan_first_max_if(v, idx, t4, p + 4, w5);
-        if (NW > 5) scan_first_max_if(v, idx, t5, p + 5, w6);
         if (LONG)
             for (int x = NW; x < ww; ++x) scan_first_max(v, idx, rp[x], p + x);
     }
@@ -819,31 +806,10 @@ __global__ void __launch_bounds__(TAB_THREADS, MINB) roi_pool_tab_kernel(RoiArgs
                 // select); the row body is chosen per warp by the widest window among its lanes
                 const V* rp = tab + (y0 * WP + x0);
                 const int p0 = y0 * W + x0;
-#if FRCNN_TRAIN_VARIANTS == 1
-                scan_rows<4, true>(v, idx, rp, p0, hh, ww, WP, W);
-#elif FRCNN_TRAIN_VARIANTS == 2
-                if (!__any_sync(0xFFFFFFFFu, ww > 3)) scan_rows<3, false>(v, idx, rp, p0, hh, ww, WP, W);
-                else scan_rows<4, true>(v, idx, rp, p0, hh, ww, WP, W);
-#elif FRCNN_TRAIN_VARIANTS == 3
-                if (!__any_sync(0xFFFFFFFFu, ww > 2)) scan_rows<2, false>(v, idx, rp, p0, hh, ww, WP, W);
-                else if (!__any_sync(0xFFFFFFFFu, ww > 3)) scan_rows<3, false>(v, idx, rp, p0, hh, ww, WP, W);
-                else scan_rows<4, true>(v, idx, rp, p0, hh, ww, WP, W);
-#elif FRCNN_TRAIN_VARIANTS == 4
                 if (!__any_sync(0xFFFFFFFFu, ww > 2)) scan_rows<2, false>(v, idx, rp, p0, hh, ww, WP, W);
                 else if (!__any_sync(0xFFFFFFFFu, ww > 3)) scan_rows<3, false>(v, idx, rp, p0, hh, ww, WP, W);
                 else if (!__any_sync(0xFFFFFFFFu, ww > 4)) scan_rows<4, false>(v, idx, rp, p0, hh, ww, WP, W);
                 else scan_rows<4, true>(v, idx, rp, p0, hh, ww, WP, W);
-#else
-                if (!__any_sync(0xFFFFFFFFu, ww > 3)) {
-                    if (!__any_sync(0xFFFFFFFFu, ww > 1)) scan_rows<1, false>(v, idx, rp, p0, hh, ww, WP, W);
-                    else if (!__any_sync(0xFFFFFFFFu, ww > 2)) scan_rows<2, false>(v, idx, rp, p0, hh, ww, WP, W);
-                    else scan_rows<3, false>(v, idx, rp, p0, hh, ww, WP, W);
-                } else if (!__any_sync(0xFFFFFFFFu, ww > 6)) {
-                    if (!__any_sync(0xFFFFFFFFu, ww > 4)) scan_rows<4, false>(v, idx, rp, p0, hh, ww, WP, W);
-                    else if (!__any_sync(0xFFFFFFFFu, ww > 5)) scan_rows<5, false>(v, idx, rp, p0, hh, ww, WP, W);
-                    else scan_rows<6, false>(v, idx, rp, p0, hh, ww, WP, W);
-                } else scan_rows<4, true>(v, idx, rp, p0, hh, ww, WP, W);
-#endif
                 float* o = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.out) + s_ob[cur][j]) + e;
                 if (valid) {
                     vstore<false>(o, BINS, v, m, cs);
