@@ -1142,7 +1142,9 @@ roi_pool_gather_kernel(RoiArgs a, const uint2* __restrict__ desc, const uint2* _
     const uint32_t kstride_b = (uint32_t)a.C * BINS * 4u;
     int i = blockIdx.x * THREADS + tid;
     uint2 d = i < n_task ? __ldg(dbase + i) : idle;
-#pragma unroll 1
+    // two tasks per trip: the second one's store addresses get registers of their own instead of waiting for the first
+    // one's STGs to leave the memory-instruction queue (0.547 -> 0.541 ms on the 64 x 64 map)
+#pragma unroll 2
     for (int i0 = blockIdx.x * THREADS; i0 < n_task; i0 += step, i += step) {
         const bool valid = i < n_task;
         const uint2 dn = i + step < n_task ? __ldg(dbase + i + step) : idle;  // the next task's list
