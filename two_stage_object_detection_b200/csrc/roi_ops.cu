@@ -1020,7 +1020,9 @@ __global__ void __launch_bounds__(256) roi_pool_desc_kernel(RoiArgs a, uint2* __
     // square windows of side s = min(smax, hh, ww) from table s - 1: a 3 x 3 bin is one lookup, 2 x 3 two, ...
     const bool empty = hh <= 0 || ww <= 0;
     const int s = empty ? 1 : min(smax, min(hh, ww));
-    const int fy = hh / s, fx = ww / s, nry = (hh + s - 1) / s, ncx = (ww + s - 1) / s;
+    // (s is 1, 2 or 3: no general integer division)
+    auto div_s = [s](int v) { return s == 1 ? v : s == 2 ? v >> 1 : v / 3; };
+    const int fy = div_s(hh), fx = div_s(ww), nry = div_s(hh + s - 1), ncx = div_s(ww + s - 1);
     const int n = empty ? 0 : nry * ncx;
     const bool big = n > 16;
     const int base = (s - 1) * HWp;
