@@ -214,3 +214,26 @@ def test_divergence_proof_accepts_threshold_flips_only():
     with pytest.raises(AssertionError):
         first_divergence(np.concatenate([small_r, a]), np.concatenate([[[0, 0, 12, 50]], a]).astype(np.float32),
                          np.array([0.9, 0.8], np.float32), **kw)
+
+
+def test_lookup_list_cover_is_exact():
+    """The rule roi_pool_desc_kernel uses to cover a RoIPool bin with square windows (csrc/roi_ops.cu, pd_anchor):
+    windows of side s = min(smax, height, width) anchored at lo, lo + s, ... and hi - s for the remainder.  The union of
+    the windows must be exactly the bin -- max over a superset would read pixels torchvision's bin does not contain, a
+    subset would miss some -- with ceil(L / s) windows per axis, so every bin up to 8 x 8 fits a 16-entry list with the
+    2 x 2 table alone and a 3 x 3 bin is one lookup with the 3 x 3 table."""
+    def anchors(lo, hi, s):
+        full = (hi - lo) // s
+        return [lo + k * s if k < full else hi - s for k in range(-(-(hi - lo) // s))]
+
+    for smax in (2, 3):
+        for hh in range(1, 20):
+            for ww in range(1, 20):
+                s = min(smax, hh, ww)
+                ry, cx = anchors(5, 5 + hh, s), anchors(9, 9 + ww, s)
+                assert len(ry) == -(-hh // s) and len(cx) == -(-ww // s)
+                covered = {(y + dy, x + dx) for y in ry for x in cx for dy in range(s) for dx in range(s)}
+                assert covered == {(y, x) for y in range(5, 5 + hh) for x in range(9, 9 + ww)}, (smax, hh, ww)
+                if hh <= 8 and ww <= 8 and min(hh, ww) >= 2:
+                    assert len(ry) * len(cx) <= 16
+    assert anchors(0, 3, 3) == [0] and anchors(0, 5, 3) == [0, 2] and anchors(4, 11, 2) == [4, 6, 8, 9]
