@@ -1047,9 +1047,11 @@ __global__ void __launch_bounds__(256) roi_pool_desc_kernel(RoiArgs a, uint2* __
 
 // positions 5..16 of a bin's list (the lanes that have them): stops at the first unused slot
 __device__ __noinline__ float4 pool_desc_more(float4 v, uint32_t tab_s, const uint2* __restrict__ x, unsigned none) {
+    // all three words at once (the list kernel wrote them all): one L2 round trip, not one per word
+    const uint2 w[3] = {__ldg(x), __ldg(x + 1), __ldg(x + 2)};
+#pragma unroll
     for (int q = 0; q < 3; ++q) {
-        const uint2 d = __ldg(x + q);
-        const unsigned o[4] = {d.x & 0xFFFFu, d.x >> 16, d.y & 0xFFFFu, d.y >> 16};
+        const unsigned o[4] = {w[q].x & 0xFFFFu, w[q].x >> 16, w[q].y & 0xFFFFu, w[q].y >> 16};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (o[i] == none) return v;
